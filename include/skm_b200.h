@@ -1,0 +1,225 @@
+/*
+ * skm_b200.h -- C ABI of libskm_b200.so, the B200 (sm_100a) engine for the
+ * sparsified K-means hot path of stephenbeckr/SparsifiedKMeans.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / MATLAB
+ * types.  Citations are relative to the reference repository root.
+ *
+ * Two levels:
+ *
+ *  Level 1 -- stateless replacements for the reference's five MEX gateways.
+ *    Host pointers in, host pointers out, IEEE double arithmetic in the
+ *    reference's operation order (bit-identical results).  A MEX shim unpacks
+ *    its mxArrays and calls exactly one of these (see mex/ and INTEGRATION.md).
+ *
+ *  Level 2 -- resident handles.  The sparsified matrix is uploaded once
+ *    (skm_dataset_*), a Lloyd state is bound to it (skm_lloyd_*), and every
+ *    iteration runs on the GPU: masked distance + argmin (replaces
+ *    private/findClusterAssignments.m:60-83,168-171 +
+ *    private/SparseMatrixMinusCluster.c:117-183), per-cluster sums and support
+ *    counts (replaces kmeans_sparsified.m:430-453), centre finalisation
+ *    (kmeans_sparsified.m:448,470-471).  Multi-GPU: each process owns a
+ *    contiguous block of columns; skm_lloyd_partials() exposes the device
+ *    buffer [S | N | counts | sumsq] that the host all-reduces (NCCL) between
+ *    skm_lloyd_accumulate() and skm_lloyd_finalize().
+ *
+ * Conventions: all matrices column-major (MATLAB); points are COLUMNS of the
+ * p x n sparse matrix X (as inside kmeans_sparsified.m after :213-218); CSC
+ * row indices are 0-based and sorted ascending within a column (what MATLAB
+ * stores); assignments returned to the host are 1-based like MATLAB's.
+ *
+ * Every function returns SKM_OK (0) or an error code; the message is available
+ * from skm_last_error().  Nothing here long-jumps or calls mex*; no host
+ * pointer is retained after a call returns.  Calls on one context are
+ * synchronous with respect to the host unless stated otherwise.
+ */
+#ifndef SKM_B200_H
+#define SKM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SKM_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------ */
+#define SKM_OK               0
+#define SKM_ERR_INVALID      1   /* bad argument; maps to the reference's mexErrMsgTxt usage errors */
+#define SKM_ERR_CUDA         2   /* CUDA runtime / launch failure */
+#define SKM_ERR_NOMEM        3
+#define SKM_ERR_UNSUPPORTED  4
+#define SKM_ERR_STATE        5   /* call order violated (e.g. accumulate before assign) */
+
+/* ---- element types ----------------------------------------------------- */
+#define SKM_F32 0
+#define SKM_F64 1
+#define SKM_I32 2
+#define SKM_I64 3   /* also used for MATLAB mwIndex (uint64 < 2^63) */
+
+typedef struct skm_ctx     skm_ctx;
+typedef struct skm_dataset skm_dataset;
+typedef struct skm_lloyd   skm_lloyd;
+
+/* ---- context ----------------------------------------------------------- */
+
+int         skm_abi_version(void);
+/* Bind to CUDA device `device`.  `cuda_stream` may be NULL (the library creates
+ * its own non-blocking stream) or a cudaStream_t owned by the caller. */
+int         skm_ctx_create(int device, void *cuda_stream, skm_ctx **out);
+void        skm_ctx_destroy(skm_ctx *ctx);
+/* Message of the last failure on this thread ("" if none). ctx may be NULL. */
+const char *skm_last_error(const skm_ctx *ctx);
+void       *skm_ctx_stream(skm_ctx *ctx);          /* the cudaStream_t in use */
+int         skm_ctx_device(const skm_ctx *ctx);
+int         skm_ctx_sync(skm_ctx *ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t     skm_ctx_launch_count(const skm_ctx *ctx);
+
+/* ---- Level 1: stateless, exact fp64, host buffers ----------------------- */
+
+/* dist = SparseMatrixMinusCluster(X, c [,beta])   (private/SparseMatrixMinusCluster.c:2-11,44-47)
+ *   dist[k + K*j] = sqrt( sum_{t in col j} (x[t] - c[ir[t] + p*k])^2 ), terms added in stored
+ *   order (:169-182).  has_beta != 0 selects the K==1-only variant of :118-129.
+ *   jc[n+1], ir[nnz] are MATLAB mwIndex (uint64). */
+int skm_sparse_matrix_minus_cluster(skm_ctx *ctx, int64_t p, int64_t n, int64_t K,
+                                    const uint64_t *jc, const uint64_t *ir, const double *pr,
+                                    const double *centers, int has_beta, double beta,
+                                    double *dist);
+
+/* [innerProd, normX2] = SparseMatrixInnerProduct(X, c)  (private/SparseMatrixInnerProduct.c:2-9,87-100)
+ *   normsq may be NULL.  c has length p (the reference checks it against n, :71-77; we check p). */
+int skm_sparse_matrix_inner_product(skm_ctx *ctx, int64_t p, int64_t n,
+                                    const uint64_t *jc, const uint64_t *ir, const double *pr,
+                                    const double *c, double *inner, double *normsq);
+
+/* normX2 = SparseMatrixColumnNormSq(X)  (private/SparseMatrixColumnNormSq.c:2-8,71-77) */
+int skm_sparse_matrix_column_normsq(skm_ctx *ctx, int64_t p, int64_t n,
+                                    const uint64_t *jc, const double *pr, double *normsq);
+
+/* w = hadamard(x) and w = hadamard_pthreads(x): unnormalised Sylvester-ordered
+ * Walsh-Hadamard transform of each column of the m x n matrix x, m a power of
+ * two >= 2 (private/hadamard.c:57-92,97-111; private/hadamard_pthreads.c:69-90). */
+int skm_hadamard(skm_ctx *ctx, int64_t m, int64_t n, const double *x, double *w);
+
+/* ---- Level 2: resident data -------------------------------------------- */
+
+typedef struct skm_dataset_info {
+    int64_t p, n, nnz;
+    int64_t max_col_nnz;     /* largest number of stored entries in a column */
+    int32_t store_dtype;     /* SKM_F32 (fast path) or SKM_F64 (exact path) */
+    int32_t reserved;
+    int64_t device_bytes;    /* HBM held by this dataset */
+    int64_t stream_bytes;    /* bytes the assignment kernel streams per pass */
+} skm_dataset_info;
+
+/* Upload a p x n CSC matrix.  jc has n+1 entries of type jc_type (SKM_I32/SKM_I64),
+ * ir has nnz entries of type ir_type, val has nnz entries of type val_type
+ * (SKM_F32/SKM_F64).  on_device != 0: the three pointers are device pointers on
+ * ctx's device (used when the data was produced on the GPU).
+ * store_dtype SKM_F64 keeps doubles and every operation is bit-exact with the
+ * reference; SKM_F32 rounds values to float (the "identical input" for parity
+ * is then that rounded value) and enables the fast assignment kernel, whose
+ * assignments are still bit-identical to the reference's on those inputs
+ * (uncertified columns are re-evaluated in fp64 in the reference order). */
+int  skm_dataset_create_csc(skm_ctx *ctx, int64_t p, int64_t n,
+                            const void *jc, int jc_type, const void *ir, int ir_type,
+                            const void *val, int val_type, int store_dtype, int on_device,
+                            skm_dataset **out);
+void skm_dataset_destroy(skm_dataset *ds);
+int  skm_dataset_get_info(const skm_dataset *ds, skm_dataset_info *info);
+/* Densify column j (0-based) into out[p] (kmeans_sparsified.m:436, X(:,iMax)). */
+int  skm_dataset_get_column(skm_dataset *ds, int64_t j, double *out);
+
+/* Operator: [assignments, distances] = findClusterAssignments(X, centers, [], gamma)
+ * for sparse X and dense centers (private/findClusterAssignments.m:77-80,168-171).
+ * centers: host, p x K.  has_gamma != 0: centres are divided by gamma first (:78).
+ * assign_out (1-based) / dist_out (Euclidean, not squared) may each be NULL. */
+int  skm_assign(skm_dataset *ds, const double *centers, int64_t K, int has_gamma, double gamma,
+                int32_t *assign_out, double *dist_out);
+
+/* Same operator, sparse-centres branch (private/findClusterAssignments.m:63-75):
+ * structural zeros of `centers` (exact 0.0) are outside each centre's support;
+ * per centre k the sum runs over rows in supp(X(:,j)) ∩ supp(c_k), the values are
+ * divided by nnz(c_k)/p and the centre by gamma when has_gamma != 0. Exact fp64. */
+int  skm_assign_sparse_centers(skm_dataset *ds, const double *centers, int64_t K,
+                               int has_gamma, double gamma,
+                               int32_t *assign_out, double *dist_out);
+
+/* Full K x n distance matrix for a resident dataset (exact fp64); dist is a HOST buffer. */
+int  skm_masked_distances(skm_dataset *ds, const double *centers, int64_t K, double *dist);
+
+typedef struct skm_iter_stats {
+    double  dff;            /* ||C_old - C_new||_F                 kmeans_sparsified.m:470 */
+    double  sumsq;          /* sum_j distance_j^2  (obj = sqrt)    kmeans_sparsified.m:471 */
+    int64_t n_empty;        /* clusters with no members (left untouched by finalize) */
+    int64_t n_rechecked;    /* columns the fast kernel could not certify (re-done in fp64) */
+    int64_t n_points;       /* points accumulated (global after the all-reduce) */
+    int32_t has_nan;        /* any NaN in the new centres           kmeans_sparsified.m:480 */
+    int32_t reserved;
+} skm_iter_stats;
+
+int   skm_lloyd_create(skm_dataset *ds, int64_t K, skm_lloyd **out);
+void  skm_lloyd_destroy(skm_lloyd *L);
+int   skm_lloyd_set_centers(skm_lloyd *L, const double *centers /* host p x K */);
+int   skm_lloyd_get_centers(skm_lloyd *L, double *centers /* host p x K */);
+int   skm_lloyd_set_center_column(skm_lloyd *L, int64_t k, const double *col /* host p */);
+/* K1: masked distance + argmin of every local column against the current centres
+ * (divided by gamma when has_gamma).  Asynchronous on the context stream. */
+int   skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma);
+/* K2: zero the partials and add this shard's per-cluster row sums S (p x K),
+ * support counts N (p x K), member counts (K) and sum of squared distances (1).
+ * Asynchronous on the context stream. */
+int   skm_lloyd_accumulate(skm_lloyd *L);
+/* Device pointer / length (in doubles) of [S | N | counts | sumsq] for the collective. */
+void *skm_lloyd_partials(skm_lloyd *L, int64_t *n_doubles);
+/* K3: C(:,k) = gamma*S(:,k)./(N(:,k)+1e-16) (ml_correction) or S(:,k)/count_k, for
+ * non-empty clusters (kmeans_sparsified.m:448,450); fills stats (synchronises). */
+int   skm_lloyd_finalize(skm_lloyd *L, double gamma, int ml_correction, skm_iter_stats *stats);
+/* Recompute dff / has_nan against the centres as they are now, without an update: used
+ * after the host patched columns for EmptyAction (kmeans_sparsified.m:432-445,470). */
+int   skm_lloyd_refresh_diff(skm_lloyd *L, skm_iter_stats *stats);
+int   skm_lloyd_get_counts(skm_lloyd *L, int64_t *counts /* host K, after finalize */);
+/* Local results of the last skm_lloyd_assign (1-based assignments; either may be NULL). */
+int   skm_lloyd_get_assignments(skm_lloyd *L, int32_t *assign_out, double *dist_out);
+/* First local column attaining the largest distance (kmeans_sparsified.m:435). */
+int   skm_lloyd_argmax_distance(skm_lloyd *L, double *maxdist, int64_t *j);
+/* Device pointers to the local results (int32 0-based assignments, float/double distances). */
+void *skm_lloyd_assign_ptr(skm_lloyd *L);
+void *skm_lloyd_dist_ptr(skm_lloyd *L, int *dtype);
+
+/* k-means++ support (private/Arthur_initialization.m:39-53): fold the masked
+ * distance to ONE new centre into the running minimum kept on the device.
+ * first != 0 resets the running minimum.  sum_d2 receives sum_j mind_j^2 over
+ * the local columns. */
+int   skm_kpp_update(skm_dataset *ds, const double *center /* host p */, int has_gamma,
+                     double gamma, int first, double *sum_d2);
+/* Smallest local column index j with cumsum(mind^2)[j] > target (clamped to n-1). */
+int   skm_kpp_pick(skm_dataset *ds, double target, int64_t *j);
+int   skm_kpp_get_mindist(skm_dataset *ds, double *mind /* host n */);
+
+/* ---- preconditioning on device (kmeans_sparsified.m:238-248,286-295) ------ */
+
+/* Y = hadamard(D * [X; 0]) / sqrt(p2) for a dense p x n host matrix (fp64 in,
+ * computed in `compute_dtype`, fp64 out, p2 x n).  signs has p2 entries of +-1. */
+int   skm_mix_hadamard(skm_ctx *ctx, int64_t p, int64_t p2, int64_t n, const double *x,
+                       const double *signs, int compute_dtype, double *y);
+
+/* Fused precondition + row sample, all on device, producing a resident dataset:
+ * column j of the result keeps rows `rows[m*j .. m*j+m)` (0-based, distinct; any
+ * order, sorted internally) of hadamard(D*x_j)/sqrt(p2), each divided by
+ * (m/p2) (private/randsample_fixedNumberEntries.m:30-31,62).  x_dev is a device
+ * pointer to a dense p2 x n float matrix (column-major); rows_dev a device
+ * pointer to int32[m*n].  Exact zeros are kept as stored entries with value 0. */
+int   skm_fwht_sample_f32(skm_ctx *ctx, int64_t p2, int64_t n, int64_t m, const float *x_dev,
+                          const float *signs_dev, const int32_t *rows_dev, skm_dataset **out);
+/* In-place device FWHT of a dense p2 x n float matrix with sign flip and 1/sqrt(p2). */
+int   skm_fwht_f32_inplace(skm_ctx *ctx, int64_t p2, int64_t n, float *x_dev,
+                           const float *signs_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKM_B200_H */

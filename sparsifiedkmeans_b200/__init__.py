@@ -1,0 +1,12 @@
+"""sparsifiedkmeans_b200 -- B200-native engine for the sparsified K-means hot path.
+
+Host-side mirror of the reference's interface (same names, argument meaning and error
+behaviour) over libskm_b200.so, hand-written sm_100a CUDA behind a C ABI
+(include/skm_b200.h).  There is no CPU fallback.
+"""
+from .engine import Context, Dataset, IterStats, Lloyd, default_context      # noqa: F401
+from .find_cluster_assignments import findClusterAssignments                  # noqa: F401
+from .ops import (SparseMatrixColumnNormSq, SparseMatrixInnerProduct,         # noqa: F401
+                  SparseMatrixMinusCluster, hadamard, hadamard_pthreads)
+
+__version__ = "0.1.0"

@@ -1,0 +1,862 @@
+// api.cu -- the extern "C" surface declared in include/skm_b200.h: contexts, level-1 stateless
+// MEX replacements, resident datasets, the Lloyd state machine and k-means++ support.
+#include "common.cuh"
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+#include <algorithm>
+#include <new>
+#include <vector>
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+void skm_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *skm_last_error(const skm_ctx *) { return g_err; }
+extern "C" int skm_abi_version(void) { return SKM_ABI_VERSION; }
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+extern "C" int skm_ctx_create(int device, void *cuda_stream, skm_ctx **out)
+{
+    if (!out) { skm_set_error("skm_ctx_create: out is NULL"); return SKM_ERR_INVALID; }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        skm_set_error("no CUDA device available (%s); libskm_b200 has no CPU fallback",
+                      e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return SKM_ERR_CUDA;
+    }
+    SKM_REQUIRE(device >= 0 && device < ndev, "device %d out of range (have %d)", device, ndev);
+    SKM_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SKM_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        skm_set_error("device %d is sm_%d%d; libskm_b200 is built for sm_100a only", device, prop.major, prop.minor);
+        return SKM_ERR_UNSUPPORTED;
+    }
+    skm_ctx *ctx = new (std::nothrow) skm_ctx();
+    if (!ctx) { skm_set_error("out of host memory"); return SKM_ERR_NOMEM; }
+    ctx->device = device;
+    ctx->launches = 0;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; }
+    else {
+        e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete ctx; skm_set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); return SKM_ERR_CUDA; }
+        ctx->own_stream = true;
+    }
+    ctx->d_flag = nullptr;
+    ctx->h_flag = nullptr;
+    if (cudaMalloc((void **)&ctx->d_flag, 16 * sizeof(int)) != cudaSuccess ||
+        cudaMallocHost((void **)&ctx->h_flag, 16 * sizeof(int)) != cudaSuccess) {
+        skm_set_error("context scratch allocation failed");
+        skm_ctx_destroy(ctx);
+        return SKM_ERR_NOMEM;
+    }
+    *out = ctx;
+    return SKM_OK;
+}
+
+extern "C" void skm_ctx_destroy(skm_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->d_flag) cudaFree(ctx->d_flag);
+    if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" void *skm_ctx_stream(skm_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" int skm_ctx_device(const skm_ctx *ctx) { return ctx ? ctx->device : -1; }
+extern "C" int64_t skm_ctx_launch_count(const skm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int skm_ctx_sync(skm_ctx *ctx)
+{
+    SKM_REQUIRE(ctx, "ctx is NULL");
+    SKM_CUDA(cudaSetDevice(ctx->device));
+    SKM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SKM_OK;
+}
+
+static int enter(skm_ctx *ctx)
+{
+    SKM_REQUIRE(ctx, "ctx is NULL");
+    SKM_CUDA(cudaSetDevice(ctx->device));
+    return SKM_OK;
+}
+
+static int dev_alloc(void **ptr, size_t bytes, const char *what)
+{
+    *ptr = nullptr;
+    cudaError_t e = cudaMalloc(ptr, bytes ? bytes : 16);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        skm_set_error("cudaMalloc(%s, %zu bytes) failed: %s", what, bytes, cudaGetErrorString(e));
+        return SKM_ERR_NOMEM;
+    }
+    return SKM_OK;
+}
+
+static int h2d(skm_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (bytes == 0) return SKM_OK;
+    SKM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return SKM_OK;
+}
+
+static int d2h_sync(skm_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (bytes) SKM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SKM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SKM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// datasets
+// ---------------------------------------------------------------------------
+static size_t type_size(int t) { return (t == SKM_F32 || t == SKM_I32) ? 4 : 8; }
+
+extern "C" void skm_dataset_destroy(skm_dataset *ds)
+{
+    if (!ds) return;
+    cudaSetDevice(ds->ctx->device);
+    cudaStreamSynchronize(ds->ctx->stream);
+    cudaFree(ds->colptr);
+    cudaFree(ds->rowidx);
+    cudaFree(ds->val);
+    cudaFree(ds->sell);
+    cudaFree(ds->slice_ptr);
+    cudaFree(ds->kpp_mind);
+    cudaFree(ds->kpp_cum);
+    delete ds;
+}
+
+// takes ownership of colptr/rowidx/val (device, final types)
+static int dataset_finish(skm_dataset *ds)
+{
+    skm_ctx *ctx = ds->ctx;
+    SKM_TRY(skm_validate_csc(ctx, ds->p, ds->n, ds->nnz, ds->colptr, ds->rowidx, &ds->max_col_nnz));
+    ds->device_bytes = (int64_t)sizeof(int64_t) * (ds->n + 1) + (int64_t)sizeof(int32_t) * ds->nnz +
+                       (int64_t)type_size(ds->store_dtype) * ds->nnz;
+    if (ds->store_dtype == SKM_F32) SKM_TRY(skm_build_sell(ds));
+    return SKM_OK;
+}
+
+extern "C" int skm_dataset_create_csc(skm_ctx *ctx, int64_t p, int64_t n, const void *jc, int jc_type,
+                                      const void *ir, int ir_type, const void *val, int val_type,
+                                      int store_dtype, int on_device, skm_dataset **out)
+{
+    SKM_TRY(enter(ctx));
+    SKM_REQUIRE(out, "out is NULL");
+    *out = nullptr;
+    SKM_REQUIRE(p >= 0 && n >= 0, "negative dimensions");
+    SKM_REQUIRE(p < 2147483647LL, "p must be below 2^31-1");
+    SKM_REQUIRE(jc, "jc is NULL");
+    SKM_REQUIRE(jc_type == SKM_I32 || jc_type == SKM_I64, "jc_type must be SKM_I32 or SKM_I64");
+    SKM_REQUIRE(ir_type == SKM_I32 || ir_type == SKM_I64, "ir_type must be SKM_I32 or SKM_I64");
+    SKM_REQUIRE(val_type == SKM_F32 || val_type == SKM_F64, "val_type must be SKM_F32 or SKM_F64");
+    SKM_REQUIRE(store_dtype == SKM_F32 || store_dtype == SKM_F64, "store_dtype must be SKM_F32 or SKM_F64");
+
+    // nnz = jc[n]
+    int64_t nnz = 0;
+    {
+        const char *last = (const char *)jc + (size_t)n * type_size(jc_type);
+        char buf[8] = {0};
+        if (on_device) {
+            SKM_CUDA(cudaMemcpyAsync(buf, last, type_size(jc_type), cudaMemcpyDeviceToHost, ctx->stream));
+            SKM_CUDA(cudaStreamSynchronize(ctx->stream));
+        } else memcpy(buf, last, type_size(jc_type));
+        nnz = (jc_type == SKM_I32) ? (int64_t) * (int32_t *)buf : *(int64_t *)buf;
+    }
+    SKM_REQUIRE(nnz >= 0, "jc[n] is negative");
+    SKM_REQUIRE(nnz == 0 || (ir && val), "ir/val are NULL but nnz > 0");
+
+    skm_dataset *ds = new (std::nothrow) skm_dataset();
+    if (!ds) { skm_set_error("out of host memory"); return SKM_ERR_NOMEM; }
+    memset(ds, 0, sizeof *ds);
+    ds->ctx = ctx;
+    ds->p = p; ds->n = n; ds->nnz = nnz;
+    ds->store_dtype = store_dtype;
+    int rc = SKM_OK;
+    do {
+        if ((rc = dev_alloc((void **)&ds->colptr, sizeof(int64_t) * (n + 1), "colptr"))) break;
+        if ((rc = dev_alloc((void **)&ds->rowidx, sizeof(int32_t) * nnz, "rowidx"))) break;
+        if ((rc = dev_alloc(&ds->val, type_size(store_dtype) * nnz, "val"))) break;
+        // stage raw arrays (host -> device) unless they already live on the device
+        DevBuf sj, si, sv;
+        const void *dj = jc, *di = ir, *dv = val;
+        if (!on_device) {
+            if (jc_type != SKM_I64) {
+                if ((rc = sj.alloc(type_size(jc_type) * (n + 1)))) break;
+                if ((rc = h2d(ctx, sj.ptr, jc, type_size(jc_type) * (n + 1)))) break;
+                dj = sj.ptr;
+            } else {
+                if ((rc = h2d(ctx, ds->colptr, jc, sizeof(int64_t) * (n + 1)))) break;
+                dj = nullptr;
+            }
+            if (nnz) {
+                if (ir_type != SKM_I32) {
+                    if ((rc = si.alloc(type_size(ir_type) * nnz))) break;
+                    if ((rc = h2d(ctx, si.ptr, ir, type_size(ir_type) * nnz))) break;
+                    di = si.ptr;
+                } else {
+                    if ((rc = h2d(ctx, ds->rowidx, ir, sizeof(int32_t) * nnz))) break;
+                    di = nullptr;
+                }
+                if (val_type != store_dtype) {
+                    if ((rc = sv.alloc(type_size(val_type) * nnz))) break;
+                    if ((rc = h2d(ctx, sv.ptr, val, type_size(val_type) * nnz))) break;
+                    dv = sv.ptr;
+                } else {
+                    if ((rc = h2d(ctx, ds->val, val, type_size(val_type) * nnz))) break;
+                    dv = nullptr;
+                }
+            } else { di = nullptr; dv = nullptr; }
+        }
+        if (dj && (rc = skm_launch_convert_index(ctx, dj, jc_type, n + 1, ds->colptr, 1))) break;
+        if (di && nnz && (rc = skm_launch_convert_index(ctx, di, ir_type, nnz, ds->rowidx, 0))) break;
+        if (dv && nnz && (rc = skm_launch_convert_value(ctx, dv, val_type, nnz, ds->val, store_dtype))) break;
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);      // staging buffers die here
+        if (e != cudaSuccess) { skm_set_error("upload failed: %s", cudaGetErrorString(e)); rc = SKM_ERR_CUDA; break; }
+        rc = dataset_finish(ds);
+    } while (0);
+    if (rc != SKM_OK) { skm_dataset_destroy(ds); return rc; }
+    *out = ds;
+    return SKM_OK;
+}
+
+extern "C" int skm_dataset_get_info(const skm_dataset *ds, skm_dataset_info *info)
+{
+    SKM_REQUIRE(ds && info, "NULL argument");
+    info->p = ds->p; info->n = ds->n; info->nnz = ds->nnz;
+    info->max_col_nnz = ds->max_col_nnz;
+    info->store_dtype = ds->store_dtype;
+    info->reserved = 0;
+    info->device_bytes = ds->device_bytes;
+    info->stream_bytes = ds->store_dtype == SKM_F32 ? ds->sell_elems * 16
+                                                    : ds->nnz * 12 + (ds->n + 1) * 8;
+    return SKM_OK;
+}
+
+extern "C" int skm_dataset_get_column(skm_dataset *ds, int64_t j, double *out)
+{
+    SKM_REQUIRE(ds && out, "NULL argument");
+    SKM_TRY(enter(ds->ctx));
+    SKM_REQUIRE(j >= 0 && j < ds->n, "column %lld out of range", (long long)j);
+    skm_ctx *ctx = ds->ctx;
+    int64_t range[2];
+    SKM_TRY(d2h_sync(ctx, range, ds->colptr + j, sizeof range));
+    int64_t cnt = range[1] - range[0];
+    std::vector<int32_t> rows(cnt);
+    std::vector<double> vals(cnt);
+    for (int64_t i = 0; i < ds->p; ++i) out[i] = 0.0;
+    if (cnt == 0) return SKM_OK;
+    SKM_CUDA(cudaMemcpyAsync(rows.data(), ds->rowidx + range[0], sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ds->store_dtype == SKM_F64) {
+        SKM_TRY(d2h_sync(ctx, vals.data(), (const double *)ds->val + range[0], sizeof(double) * cnt));
+    } else {
+        std::vector<float> vf(cnt);
+        SKM_TRY(d2h_sync(ctx, vf.data(), (const float *)ds->val + range[0], sizeof(float) * cnt));
+        for (int64_t i = 0; i < cnt; ++i) vals[i] = (double)vf[i];
+    }
+    for (int64_t i = 0; i < cnt; ++i) out[rows[i]] = vals[i];
+    return SKM_OK;
+}
+
+static ExactArgs exact_args(const skm_dataset *ds, int64_t K, const double *ct)
+{
+    ExactArgs a;
+    a.p = ds->p; a.n = ds->n; a.K = K;
+    a.colptr = ds->colptr; a.rowidx = ds->rowidx; a.val = ds->val;
+    a.val_type = ds->store_dtype;
+    a.ct = ct; a.mask = nullptr; a.xdiv = nullptr;
+    return a;
+}
+
+// ---------------------------------------------------------------------------
+// Lloyd state
+// ---------------------------------------------------------------------------
+extern "C" void skm_lloyd_destroy(skm_lloyd *L)
+{
+    if (!L) return;
+    cudaSetDevice(L->ds->ctx->device);
+    cudaStreamSynchronize(L->ds->ctx->stream);
+    cudaFree(L->centers); cudaFree(L->centers_old); cudaFree(L->cscaled_t); cudaFree(L->table);
+    cudaFree(L->cmax); cudaFree(L->assign); cudaFree(L->dist_f32); cudaFree(L->dist_f64);
+    cudaFree(L->best2); cudaFree(L->flagged); cudaFree(L->nflag); cudaFree(L->partials);
+    cudaFree(L->stats);
+    if (L->h_stats) cudaFreeHost(L->h_stats);
+    if (L->h_counts) cudaFreeHost(L->h_counts);
+    delete L;
+}
+
+extern "C" int skm_lloyd_create(skm_dataset *ds, int64_t K, skm_lloyd **out)
+{
+    SKM_REQUIRE(ds && out, "NULL argument");
+    *out = nullptr;
+    SKM_TRY(enter(ds->ctx));
+    SKM_REQUIRE(K >= 1, "K must be >= 1");
+    SKM_REQUIRE(K < (1 << 24), "K too large");
+    skm_lloyd *L = new (std::nothrow) skm_lloyd();
+    if (!L) { skm_set_error("out of host memory"); return SKM_ERR_NOMEM; }
+    memset(L, 0, sizeof *L);
+    L->ds = ds; L->K = K;
+    const int64_t p = ds->p, n = ds->n;
+    int rc = SKM_OK;
+    do {
+        if ((rc = dev_alloc((void **)&L->centers, sizeof(double) * p * K, "centers"))) break;
+        if ((rc = dev_alloc((void **)&L->centers_old, sizeof(double) * p * K, "centers_old"))) break;
+        if ((rc = dev_alloc((void **)&L->cscaled_t, sizeof(double) * (p + 1) * K, "cscaled"))) break;
+        if ((rc = dev_alloc((void **)&L->assign, sizeof(int32_t) * n, "assign"))) break;
+        if ((rc = dev_alloc((void **)&L->partials, sizeof(double) * (2 * p * K + K + 1), "partials"))) break;
+        if ((rc = dev_alloc((void **)&L->stats, sizeof(double) * 8, "stats"))) break;
+        if ((rc = dev_alloc((void **)&L->nflag, sizeof(int) * 4, "nflag"))) break;
+        if ((rc = dev_alloc((void **)&L->cmax, sizeof(float) * 4, "cmax"))) break;
+        if (ds->store_dtype == SKM_F32) {
+            if ((rc = dev_alloc((void **)&L->dist_f32, sizeof(float) * n, "dist"))) break;
+            if ((rc = dev_alloc((void **)&L->flagged, sizeof(int32_t) * n, "flagged"))) break;
+            FastPlan pl;
+            if (skm_fast_plan(ds->ctx, p, K, &pl)) {
+                if ((rc = dev_alloc((void **)&L->table, sizeof(float) * (size_t)(p + 1) * pl.ks * pl.nchunks, "table"))) break;
+                if (pl.nchunks > 1 && (rc = dev_alloc((void **)&L->best2, sizeof(float) * 2 * n, "best2"))) break;
+            }
+        } else {
+            if ((rc = dev_alloc((void **)&L->dist_f64, sizeof(double) * n, "dist"))) break;
+        }
+        if (cudaMallocHost((void **)&L->h_stats, sizeof(double) * 8) != cudaSuccess ||
+            cudaMallocHost((void **)&L->h_counts, sizeof(int64_t) * (K + 2)) != cudaSuccess) {
+            skm_set_error("pinned host allocation failed");
+            rc = SKM_ERR_NOMEM;
+            break;
+        }
+        cudaError_t e = cudaMemsetAsync(L->centers, 0, sizeof(double) * p * K, ds->ctx->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(L->centers_old, 0, sizeof(double) * p * K, ds->ctx->stream);
+        if (e != cudaSuccess) { skm_set_error("memset failed: %s", cudaGetErrorString(e)); rc = SKM_ERR_CUDA; break; }
+    } while (0);
+    if (rc != SKM_OK) { skm_lloyd_destroy(L); return rc; }
+    *out = L;
+    return SKM_OK;
+}
+
+extern "C" int skm_lloyd_set_centers(skm_lloyd *L, const double *centers)
+{
+    SKM_REQUIRE(L && centers, "NULL argument");
+    SKM_TRY(enter(L->ds->ctx));
+    SKM_TRY(h2d(L->ds->ctx, L->centers, centers, sizeof(double) * L->ds->p * L->K));
+    SKM_CUDA(cudaStreamSynchronize(L->ds->ctx->stream));
+    return SKM_OK;
+}
+
+extern "C" int skm_lloyd_get_centers(skm_lloyd *L, double *centers)
+{
+    SKM_REQUIRE(L && centers, "NULL argument");
+    SKM_TRY(enter(L->ds->ctx));
+    return d2h_sync(L->ds->ctx, centers, L->centers, sizeof(double) * L->ds->p * L->K);
+}
+
+extern "C" int skm_lloyd_set_center_column(skm_lloyd *L, int64_t k, const double *col)
+{
+    SKM_REQUIRE(L && col, "NULL argument");
+    SKM_REQUIRE(k >= 0 && k < L->K, "centre index out of range");
+    SKM_TRY(enter(L->ds->ctx));
+    SKM_TRY(h2d(L->ds->ctx, L->centers + k * L->ds->p, col, sizeof(double) * L->ds->p));
+    SKM_CUDA(cudaStreamSynchronize(L->ds->ctx->stream));
+    return SKM_OK;
+}
+
+extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
+{
+    SKM_REQUIRE(L, "NULL argument");
+    skm_dataset *ds = L->ds;
+    skm_ctx *ctx = ds->ctx;
+    SKM_TRY(enter(ctx));
+    SKM_REQUIRE(!has_gamma || gamma == gamma, "gamma is NaN");
+    SKM_TRY(skm_launch_prep_centers(ctx, ds->p, L->K, L->centers, has_gamma, gamma, L->cscaled_t, nullptr, nullptr));
+    ExactArgs ea = exact_args(ds, L->K, L->cscaled_t);
+    L->last_rechecked = -1;
+    FastPlan pl;
+    if (ds->store_dtype == SKM_F32 && L->table && skm_fast_plan(ctx, ds->p, L->K, &pl)) {
+        SKM_TRY(skm_launch_build_table(ctx, ds->p, L->K, L->cscaled_t, pl, L->table, L->cmax));
+        SKM_TRY(skm_launch_assign_fast(ctx, ds, L->K, pl, L->table, L->cmax, L->assign, L->dist_f32, L->best2,
+                                       L->flagged, L->nflag));
+        // columns the guard could not certify: fp64, reference order
+        SKM_TRY(skm_launch_exact_assign(ctx, ea, L->assign, nullptr, L->dist_f32, L->flagged, L->nflag, ds->n));
+    } else {
+        SKM_TRY(skm_launch_exact_assign(ctx, ea, L->assign, L->dist_f64, L->dist_f32, nullptr, nullptr, 0));
+        SKM_CUDA(cudaMemsetAsync(L->nflag, 0, sizeof(int), ctx->stream));
+    }
+    L->assigned = true;
+    L->accumulated = false;
+    return SKM_OK;
+}
+
+extern "C" int skm_lloyd_accumulate(skm_lloyd *L)
+{
+    SKM_REQUIRE(L, "NULL argument");
+    SKM_TRY(enter(L->ds->ctx));
+    if (!L->assigned) { skm_set_error("skm_lloyd_accumulate called before skm_lloyd_assign"); return SKM_ERR_STATE; }
+    SKM_TRY(skm_launch_accumulate(L->ds->ctx, L->ds, L->K, L->assign, L->dist_f32, L->dist_f64, L->partials));
+    L->accumulated = true;
+    return SKM_OK;
+}
+
+extern "C" void *skm_lloyd_partials(skm_lloyd *L, int64_t *n_doubles)
+{
+    if (!L) return nullptr;
+    if (n_doubles) *n_doubles = 2 * L->ds->p * L->K + L->K + 1;
+    return L->partials;
+}
+
+static int read_stats(skm_lloyd *L, skm_iter_stats *stats)
+{
+    skm_ctx *ctx = L->ds->ctx;
+    const int64_t p = L->ds->p, K = L->K;
+    std::vector<double> tail(K + 1);
+    SKM_CUDA(cudaMemcpyAsync(L->h_stats, L->stats, sizeof(double) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SKM_CUDA(cudaMemcpyAsync(ctx->h_flag, L->nflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SKM_TRY(d2h_sync(ctx, tail.data(), L->partials + 2 * p * K, sizeof(double) * (K + 1)));
+    int64_t n_empty = 0, npts = 0;
+    for (int64_t k = 0; k < K; ++k) {
+        L->h_counts[k] = (int64_t)llround(tail[k]);
+        npts += L->h_counts[k];
+        if (L->h_counts[k] == 0) ++n_empty;
+    }
+    L->last_rechecked = ctx->h_flag[0];
+    if (stats) {
+        stats->dff = sqrt(L->h_stats[0]);
+        stats->sumsq = tail[K];
+        stats->n_empty = n_empty;
+        stats->n_rechecked = L->last_rechecked;
+        stats->n_points = npts;
+        stats->has_nan = L->h_stats[1] != 0.0;
+        stats->reserved = 0;
+    }
+    return SKM_OK;
+}
+
+extern "C" int skm_lloyd_finalize(skm_lloyd *L, double gamma, int ml_correction, skm_iter_stats *stats)
+{
+    SKM_REQUIRE(L, "NULL argument");
+    SKM_TRY(enter(L->ds->ctx));
+    if (!L->accumulated) { skm_set_error("skm_lloyd_finalize called before skm_lloyd_accumulate"); return SKM_ERR_STATE; }
+    SKM_TRY(skm_launch_finalize(L->ds->ctx, L->ds->p, L->K, L->partials, gamma, ml_correction, L->centers,
+                                L->centers_old, L->stats));
+    return read_stats(L, stats);
+}
+
+// recompute dff / has_nan after the host patched centre columns (EmptyAction = singleton)
+extern "C" int skm_lloyd_refresh_diff(skm_lloyd *L, skm_iter_stats *stats)
+{
+    SKM_REQUIRE(L, "NULL argument");
+    SKM_TRY(enter(L->ds->ctx));
+    SKM_TRY(skm_launch_finalize(L->ds->ctx, L->ds->p, L->K, nullptr, 0.0, 0, L->centers, L->centers_old, L->stats));
+    return read_stats(L, stats);
+}
+
+extern "C" int skm_lloyd_get_counts(skm_lloyd *L, int64_t *counts)
+{
+    SKM_REQUIRE(L && counts, "NULL argument");
+    for (int64_t k = 0; k < L->K; ++k) counts[k] = L->h_counts[k];
+    return SKM_OK;
+}
+
+extern "C" int skm_lloyd_get_assignments(skm_lloyd *L, int32_t *assign_out, double *dist_out)
+{
+    SKM_REQUIRE(L, "NULL argument");
+    skm_ctx *ctx = L->ds->ctx;
+    SKM_TRY(enter(ctx));
+    if (!L->assigned) { skm_set_error("no assignments yet"); return SKM_ERR_STATE; }
+    const int64_t n = L->ds->n;
+    if (assign_out) {
+        SKM_TRY(d2h_sync(ctx, assign_out, L->assign, sizeof(int32_t) * n));
+        for (int64_t j = 0; j < n; ++j) assign_out[j] += 1;            // MATLAB is 1-based
+    }
+    if (dist_out) {
+        if (L->dist_f64) SKM_TRY(d2h_sync(ctx, dist_out, L->dist_f64, sizeof(double) * n));
+        else {
+            std::vector<float> tmp(n);
+            SKM_TRY(d2h_sync(ctx, tmp.data(), L->dist_f32, sizeof(float) * n));
+            for (int64_t j = 0; j < n; ++j) dist_out[j] = (double)tmp[j];
+        }
+    }
+    return SKM_OK;
+}
+
+extern "C" int skm_lloyd_argmax_distance(skm_lloyd *L, double *maxdist, int64_t *j)
+{
+    SKM_REQUIRE(L && maxdist && j, "NULL argument");
+    skm_ctx *ctx = L->ds->ctx;
+    SKM_TRY(enter(ctx));
+    if (!L->assigned) { skm_set_error("no assignments yet"); return SKM_ERR_STATE; }
+    if (L->ds->n == 0) { *maxdist = -1.0; *j = -1; return SKM_OK; }
+    DevBuf v, i;
+    SKM_TRY(v.alloc(sizeof(double)));
+    SKM_TRY(i.alloc(sizeof(int64_t)));
+    SKM_TRY(skm_launch_argmax(ctx, L->ds->n, L->dist_f32, L->dist_f64, v.as<double>(), i.as<int64_t>()));
+    SKM_CUDA(cudaMemcpyAsync(maxdist, v.ptr, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return d2h_sync(ctx, j, i.ptr, sizeof(int64_t));
+}
+
+extern "C" void *skm_lloyd_assign_ptr(skm_lloyd *L) { return L ? L->assign : nullptr; }
+extern "C" void *skm_lloyd_dist_ptr(skm_lloyd *L, int *dtype)
+{
+    if (!L) return nullptr;
+    if (L->dist_f64) { if (dtype) *dtype = SKM_F64; return L->dist_f64; }
+    if (dtype) *dtype = SKM_F32;
+    return L->dist_f32;
+}
+
+// ---------------------------------------------------------------------------
+// operator-level calls on a resident dataset
+// ---------------------------------------------------------------------------
+extern "C" int skm_assign(skm_dataset *ds, const double *centers, int64_t K, int has_gamma, double gamma,
+                          int32_t *assign_out, double *dist_out)
+{
+    SKM_REQUIRE(ds && centers, "NULL argument");
+    skm_lloyd *L = nullptr;
+    SKM_TRY(skm_lloyd_create(ds, K, &L));
+    int rc = skm_lloyd_set_centers(L, centers);
+    if (rc == SKM_OK) rc = skm_lloyd_assign(L, has_gamma, gamma);
+    if (rc == SKM_OK) rc = skm_lloyd_get_assignments(L, assign_out, dist_out);
+    skm_lloyd_destroy(L);
+    return rc;
+}
+
+static int exact_with_centers(skm_dataset *ds, const double *centers, int64_t K, int has_gamma, double gamma,
+                              bool sparse_centers, int32_t *assign_out, double *dist_out, double *full_dist)
+{
+    skm_ctx *ctx = ds->ctx;
+    SKM_TRY(enter(ctx));
+    SKM_REQUIRE(K >= 1, "K must be >= 1");
+    const int64_t p = ds->p, n = ds->n;
+    DevBuf dc, ct, mask, xdiv, dassign, ddist;
+    SKM_TRY(dc.alloc(sizeof(double) * p * K));
+    SKM_TRY(ct.alloc(sizeof(double) * (p + 1) * K));
+    if (sparse_centers) {
+        SKM_TRY(mask.alloc((size_t)(p + 1) * K));
+        SKM_TRY(xdiv.alloc(sizeof(double) * K));
+    }
+    SKM_TRY(h2d(ctx, dc.ptr, centers, sizeof(double) * p * K));
+    SKM_TRY(skm_launch_prep_centers(ctx, p, K, dc.as<double>(), has_gamma, gamma, ct.as<double>(),
+                                    sparse_centers ? mask.as<uint8_t>() : nullptr,
+                                    sparse_centers ? xdiv.as<double>() : nullptr));
+    ExactArgs ea = exact_args(ds, K, ct.as<double>());
+    if (sparse_centers) { ea.mask = mask.as<uint8_t>(); ea.xdiv = xdiv.as<double>(); }
+    if (full_dist) {
+        // K x n in column chunks so the device temporary stays bounded
+        const int64_t chunk = std::max<int64_t>(1, (int64_t)(256LL << 20) / (8 * K));
+        DevBuf tmp;
+        SKM_TRY(tmp.alloc(sizeof(double) * std::min(chunk, std::max<int64_t>(n, 1)) * K));
+        for (int64_t j0 = 0; j0 < n; j0 += chunk) {
+            const int64_t j1 = std::min(n, j0 + chunk);
+            SKM_TRY(skm_launch_exact_dist(ctx, ea, j0, j1, tmp.as<double>()));
+            SKM_TRY(d2h_sync(ctx, full_dist + j0 * K, tmp.ptr, sizeof(double) * (j1 - j0) * K));
+        }
+        return SKM_OK;
+    }
+    SKM_TRY(dassign.alloc(sizeof(int32_t) * n));
+    SKM_TRY(ddist.alloc(sizeof(double) * n));
+    SKM_TRY(skm_launch_exact_assign(ctx, ea, dassign.as<int32_t>(), ddist.as<double>(), nullptr, nullptr, nullptr, 0));
+    if (assign_out) {
+        SKM_TRY(d2h_sync(ctx, assign_out, dassign.ptr, sizeof(int32_t) * n));
+        for (int64_t j = 0; j < n; ++j) assign_out[j] += 1;
+    }
+    if (dist_out) SKM_TRY(d2h_sync(ctx, dist_out, ddist.ptr, sizeof(double) * n));
+    SKM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SKM_OK;
+}
+
+extern "C" int skm_assign_sparse_centers(skm_dataset *ds, const double *centers, int64_t K, int has_gamma,
+                                         double gamma, int32_t *assign_out, double *dist_out)
+{
+    SKM_REQUIRE(ds && centers, "NULL argument");
+    return exact_with_centers(ds, centers, K, has_gamma, gamma, true, assign_out, dist_out, nullptr);
+}
+
+extern "C" int skm_masked_distances(skm_dataset *ds, const double *centers, int64_t K, double *dist)
+{
+    SKM_REQUIRE(ds && centers && dist, "NULL argument");
+    return exact_with_centers(ds, centers, K, 0, 0.0, false, nullptr, nullptr, dist);
+}
+
+// ---------------------------------------------------------------------------
+// Level 1
+// ---------------------------------------------------------------------------
+extern "C" int skm_sparse_matrix_minus_cluster(skm_ctx *ctx, int64_t p, int64_t n, int64_t K,
+                                               const uint64_t *jc, const uint64_t *ir, const double *pr,
+                                               const double *centers, int has_beta, double beta, double *dist)
+{
+    SKM_TRY(enter(ctx));
+    SKM_REQUIRE(jc && centers && dist, "NULL argument");
+    SKM_REQUIRE(K >= 1, "Center must have at least one column");
+    if (has_beta && K != 1) {
+        // SparseMatrixMinusCluster.c:119-120
+        skm_set_error("Have not yet implemented case for using 'beta' with p x k (k!=1) centers");
+        return SKM_ERR_INVALID;
+    }
+    skm_dataset *ds = nullptr;
+    SKM_TRY(skm_dataset_create_csc(ctx, p, n, jc, SKM_I64, ir, SKM_I64, pr, SKM_F64, SKM_F64, 0, &ds));
+    int rc;
+    if (!has_beta) rc = skm_masked_distances(ds, centers, K, dist);
+    else {
+        rc = SKM_OK;
+        DevBuf dc, dd;
+        do {
+            if ((rc = dc.alloc(sizeof(double) * p))) break;
+            if ((rc = dd.alloc(sizeof(double) * std::max<int64_t>(n, 1)))) break;
+            if ((rc = h2d(ctx, dc.ptr, centers, sizeof(double) * p))) break;
+            ExactArgs ea = exact_args(ds, 1, dc.as<double>());
+            if ((rc = skm_launch_exact_dist_beta(ctx, ea, beta, dd.as<double>()))) break;
+            rc = d2h_sync(ctx, dist, dd.ptr, sizeof(double) * n);
+        } while (0);
+    }
+    skm_dataset_destroy(ds);
+    return rc;
+}
+
+static int inner_common(skm_ctx *ctx, int64_t p, int64_t n, const uint64_t *jc, const uint64_t *ir,
+                        const double *pr, const double *c, double *inner, double *normsq)
+{
+    SKM_TRY(enter(ctx));
+    skm_dataset *ds = nullptr;
+    // ColumnNormSq never looks at the row indices: fabricate zeros when ir is NULL
+    std::vector<uint64_t> zeros;
+    if (!ir) { zeros.assign((size_t)jc[n], 0); ir = zeros.data(); }
+    SKM_TRY(skm_dataset_create_csc(ctx, p, n, jc, SKM_I64, ir, SKM_I64, pr, SKM_F64, SKM_F64, 0, &ds));
+    int rc = SKM_OK;
+    DevBuf dc, di, dn;
+    do {
+        if (c) {
+            if ((rc = dc.alloc(sizeof(double) * std::max<int64_t>(p, 1)))) break;
+            if ((rc = h2d(ctx, dc.ptr, c, sizeof(double) * p))) break;
+        }
+        if (inner && (rc = di.alloc(sizeof(double) * std::max<int64_t>(n, 1)))) break;
+        if (normsq && (rc = dn.alloc(sizeof(double) * std::max<int64_t>(n, 1)))) break;
+        if ((rc = skm_launch_inner_product(ctx, n, ds->colptr, ds->rowidx, (const double *)ds->val,
+                                           c ? dc.as<double>() : nullptr, inner ? di.as<double>() : nullptr,
+                                           normsq ? dn.as<double>() : nullptr))) break;
+        if (inner && (rc = d2h_sync(ctx, inner, di.ptr, sizeof(double) * n))) break;
+        if (normsq && (rc = d2h_sync(ctx, normsq, dn.ptr, sizeof(double) * n))) break;
+        rc = d2h_sync(ctx, nullptr, nullptr, 0);
+    } while (0);
+    skm_dataset_destroy(ds);
+    return rc;
+}
+
+extern "C" int skm_sparse_matrix_inner_product(skm_ctx *ctx, int64_t p, int64_t n, const uint64_t *jc,
+                                               const uint64_t *ir, const double *pr, const double *c,
+                                               double *inner, double *normsq)
+{
+    SKM_REQUIRE(jc && c && inner, "NULL argument");
+    SKM_REQUIRE(jc[n] == 0 || ir, "ir is NULL");
+    return inner_common(ctx, p, n, jc, ir, pr, c, inner, normsq);
+}
+
+extern "C" int skm_sparse_matrix_column_normsq(skm_ctx *ctx, int64_t p, int64_t n, const uint64_t *jc,
+                                               const double *pr, double *normsq)
+{
+    SKM_REQUIRE(jc && normsq, "NULL argument");
+    return inner_common(ctx, p, n, jc, nullptr, pr, nullptr, nullptr, normsq);
+}
+
+extern "C" int skm_hadamard(skm_ctx *ctx, int64_t m, int64_t n, const double *x, double *w)
+{
+    SKM_TRY(enter(ctx));
+    SKM_REQUIRE(x && w, "NULL argument");
+    // hadamard.c:97-111,134-140
+    SKM_REQUIRE(m >= 2 && (m & (m - 1)) == 0, "hadamard: number of rows must be a power of two >= 2");
+    if (n == 0) return SKM_OK;
+    // column chunks bound the device footprint
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)(1LL << 30) / (8 * m));
+    DevBuf d;
+    SKM_TRY(d.alloc(sizeof(double) * m * std::min(chunk, n)));
+    for (int64_t j0 = 0; j0 < n; j0 += chunk) {
+        const int64_t j1 = std::min(n, j0 + chunk);
+        SKM_TRY(h2d(ctx, d.ptr, x + j0 * m, sizeof(double) * m * (j1 - j0)));
+        SKM_TRY(skm_launch_fwht_f64(ctx, m, j1 - j0, d.as<double>(), nullptr, 0.0));
+        SKM_TRY(d2h_sync(ctx, w + j0 * m, d.ptr, sizeof(double) * m * (j1 - j0)));
+    }
+    return SKM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// preconditioning
+// ---------------------------------------------------------------------------
+namespace {
+__global__ void k_pad_cast(int64_t p, int64_t p2, int64_t n, const double *__restrict__ x, float *__restrict__ y32,
+                           double *__restrict__ y64)
+{
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; idx < p2 * n; idx += stride) {
+        const int64_t col = idx / p2, r = idx % p2;
+        const double v = r < p ? x[col * p + r] : 0.0;
+        if (y32) y32[idx] = (float)v;
+        else y64[idx] = v;
+    }
+}
+__global__ void k_f32_to_f64(int64_t total, const float *__restrict__ a, double *__restrict__ b)
+{
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; idx < total; idx += stride) b[idx] = (double)a[idx];
+}
+}  // namespace
+
+extern "C" int skm_mix_hadamard(skm_ctx *ctx, int64_t p, int64_t p2, int64_t n, const double *x,
+                                const double *signs, int compute_dtype, double *y)
+{
+    SKM_TRY(enter(ctx));
+    SKM_REQUIRE(x && signs && y, "NULL argument");
+    SKM_REQUIRE(p2 >= 2 && (p2 & (p2 - 1)) == 0 && p <= p2, "p2 must be a power of two >= max(2,p)");
+    SKM_REQUIRE(compute_dtype == SKM_F32 || compute_dtype == SKM_F64, "bad compute dtype");
+    if (n == 0) return SKM_OK;
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)(1LL << 29) / (8 * p2));
+    const int64_t cn = std::min(chunk, n);
+    DevBuf din, dwork, dout, dsign;
+    SKM_TRY(din.alloc(sizeof(double) * p * cn));
+    SKM_TRY(dout.alloc(sizeof(double) * p2 * cn));
+    SKM_TRY(dsign.alloc(sizeof(double) * p2));
+    std::vector<float> s32;
+    if (compute_dtype == SKM_F32) {
+        SKM_TRY(dwork.alloc(sizeof(float) * p2 * cn));
+        s32.resize(p2);
+        for (int64_t i = 0; i < p2; ++i) s32[i] = (float)signs[i];
+        SKM_TRY(h2d(ctx, dsign.ptr, s32.data(), sizeof(float) * p2));
+    } else SKM_TRY(h2d(ctx, dsign.ptr, signs, sizeof(double) * p2));
+    const int64_t cap = (int64_t)ctx->sm_count * 32;
+    for (int64_t j0 = 0; j0 < n; j0 += chunk) {
+        const int64_t j1 = std::min(n, j0 + chunk), c = j1 - j0;
+        SKM_TRY(h2d(ctx, din.ptr, x + j0 * p, sizeof(double) * p * c));
+        int64_t blocks = std::min(cap, (p2 * c + 255) / 256);
+        if (compute_dtype == SKM_F32) {
+            k_pad_cast<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p, p2, c, din.as<double>(), dwork.as<float>(), nullptr);
+            SKM_CHECK_LAUNCH(ctx);
+            SKM_TRY(skm_launch_fwht_f32(ctx, p2, c, dwork.as<float>(), dsign.as<float>(), sqrtf((float)p2)));
+            k_f32_to_f64<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p2 * c, dwork.as<float>(), dout.as<double>());
+            SKM_CHECK_LAUNCH(ctx);
+        } else {
+            k_pad_cast<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p, p2, c, din.as<double>(), nullptr, dout.as<double>());
+            SKM_CHECK_LAUNCH(ctx);
+            SKM_TRY(skm_launch_fwht_f64(ctx, p2, c, dout.as<double>(), dsign.as<double>(), sqrt((double)p2)));
+        }
+        SKM_TRY(d2h_sync(ctx, y + j0 * p2, dout.ptr, sizeof(double) * p2 * c));
+    }
+    return SKM_OK;
+}
+
+extern "C" int skm_fwht_f32_inplace(skm_ctx *ctx, int64_t p2, int64_t n, float *x_dev, const float *signs_dev)
+{
+    SKM_TRY(enter(ctx));
+    SKM_REQUIRE(x_dev, "NULL argument");
+    return skm_launch_fwht_f32(ctx, p2, n, x_dev, signs_dev, sqrtf((float)p2));
+}
+
+extern "C" int skm_fwht_sample_f32(skm_ctx *ctx, int64_t p2, int64_t n, int64_t m, const float *x_dev,
+                                   const float *signs_dev, const int32_t *rows_dev, skm_dataset **out)
+{
+    SKM_TRY(enter(ctx));
+    SKM_REQUIRE(x_dev && signs_dev && rows_dev && out, "NULL argument");
+    *out = nullptr;
+    skm_dataset *ds = new (std::nothrow) skm_dataset();
+    if (!ds) { skm_set_error("out of host memory"); return SKM_ERR_NOMEM; }
+    memset(ds, 0, sizeof *ds);
+    ds->ctx = ctx;
+    ds->p = p2; ds->n = n; ds->nnz = n * m;
+    ds->store_dtype = SKM_F32;
+    int rc = SKM_OK;
+    do {
+        if ((rc = dev_alloc((void **)&ds->colptr, sizeof(int64_t) * (n + 1), "colptr"))) break;
+        if ((rc = dev_alloc((void **)&ds->rowidx, sizeof(int32_t) * ds->nnz, "rowidx"))) break;
+        if ((rc = dev_alloc(&ds->val, sizeof(float) * ds->nnz, "val"))) break;
+        if (n == 0) { if ((rc = (cudaMemsetAsync(ds->colptr, 0, sizeof(int64_t), ctx->stream) == cudaSuccess) ? SKM_OK : SKM_ERR_CUDA)) break; }
+        if ((rc = skm_launch_fwht_sample_f32(ctx, p2, n, m, x_dev, signs_dev, rows_dev, ds->colptr, ds->rowidx,
+                                             (float *)ds->val))) break;
+        rc = dataset_finish(ds);
+    } while (0);
+    if (rc != SKM_OK) { skm_dataset_destroy(ds); return rc; }
+    *out = ds;
+    return SKM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// k-means++
+// ---------------------------------------------------------------------------
+extern "C" int skm_kpp_update(skm_dataset *ds, const double *center, int has_gamma, double gamma, int first,
+                              double *sum_d2)
+{
+    SKM_REQUIRE(ds && center, "NULL argument");
+    skm_ctx *ctx = ds->ctx;
+    SKM_TRY(enter(ctx));
+    const int64_t p = ds->p, n = ds->n;
+    const int64_t nb = (n + 1023) / 1024;
+    if (!ds->kpp_mind) {
+        SKM_TRY(dev_alloc((void **)&ds->kpp_mind, sizeof(double) * n, "kpp_mind"));
+        SKM_TRY(dev_alloc((void **)&ds->kpp_cum, sizeof(double) * (nb + 1), "kpp_bsum"));
+        first = 1;
+    }
+    std::vector<double> c(center, center + p);
+    if (has_gamma) for (int64_t i = 0; i < p; ++i) c[i] = center[i] / gamma;    // full(centers)/gamma, IEEE division
+    DevBuf dc;
+    SKM_TRY(dc.alloc(sizeof(double) * std::max<int64_t>(p, 1)));
+    SKM_TRY(h2d(ctx, dc.ptr, c.data(), sizeof(double) * p));
+    SKM_TRY(skm_launch_kpp_update(ctx, ds, dc.as<double>(), first, ds->kpp_mind, nullptr));
+    SKM_TRY(skm_launch_scan_sq(ctx, n, ds->kpp_mind, ds->kpp_cum));
+    std::vector<double> bs(nb);
+    SKM_TRY(d2h_sync(ctx, bs.data(), ds->kpp_cum, sizeof(double) * nb));
+    double tot = 0.0;
+    for (int64_t b = 0; b < nb; ++b) tot += bs[b];
+    if (sum_d2) *sum_d2 = tot;
+    return SKM_OK;
+}
+
+extern "C" int skm_kpp_pick(skm_dataset *ds, double target, int64_t *j)
+{
+    SKM_REQUIRE(ds && j, "NULL argument");
+    skm_ctx *ctx = ds->ctx;
+    SKM_TRY(enter(ctx));
+    if (!ds->kpp_mind) { skm_set_error("skm_kpp_pick before skm_kpp_update"); return SKM_ERR_STATE; }
+    const int64_t n = ds->n, nb = (n + 1023) / 1024;
+    SKM_REQUIRE(n > 0, "empty dataset");
+    std::vector<double> bs(nb);
+    SKM_TRY(d2h_sync(ctx, bs.data(), ds->kpp_cum, sizeof(double) * nb));
+    double acc = 0.0;
+    int64_t b = 0;
+    for (; b < nb; ++b) {
+        if (acc + bs[b] > target) break;
+        acc += bs[b];
+    }
+    if (b >= nb) { *j = n - 1; return SKM_OK; }
+    const int64_t i0 = b * 1024, i1 = std::min(n, i0 + 1024);
+    std::vector<double> md(i1 - i0);
+    SKM_TRY(d2h_sync(ctx, md.data(), ds->kpp_mind + i0, sizeof(double) * (i1 - i0)));
+    for (int64_t i = i0; i < i1; ++i) {
+        acc += md[i - i0] * md[i - i0];
+        if (acc > target) { *j = i; return SKM_OK; }
+    }
+    *j = i1 - 1;     // rounding between the tree sum and the sequential sum
+    return SKM_OK;
+}
+
+extern "C" int skm_kpp_get_mindist(skm_dataset *ds, double *mind)
+{
+    SKM_REQUIRE(ds && mind, "NULL argument");
+    SKM_TRY(enter(ds->ctx));
+    if (!ds->kpp_mind) { skm_set_error("skm_kpp_get_mindist before skm_kpp_update"); return SKM_ERR_STATE; }
+    return d2h_sync(ds->ctx, mind, ds->kpp_mind, sizeof(double) * ds->n);
+}

@@ -1,0 +1,323 @@
+// assign_fast.cu -- K1, the hot kernel: fused masked squared distance + argmin over the
+// SELL-32 image of the sparsified matrix (replaces private/SparseMatrixMinusCluster.c:169-182
+// followed by min, private/findClusterAssignments.m:168-171, without the K x n temporary).
+//
+// Mapping: one thread per column, one warp per 32-column slice, persistent warps striding over
+// slices.  Lane l streams its column's (row, value) pairs with one coalesced 128-bit load per
+// two entries (the slice is stored interleaved, so a warp reads 512 contiguous bytes), gathers
+// the centroid row c'[row, 0:KC) from a padded fp32 table staged once per CTA into shared
+// memory with a TMA bulk copy, and keeps KC running sums in registers.  No tensor cores: this
+// is a sparse gather.  Algorithmic HBM bytes per point: 8 per stored entry + 4 (assignment)
+// + 4 (distance).
+//
+// Exactness: sums are fp32 here, the reference's are fp64.  Each column's winner is certified
+// with a rigorous rounding bound (see guard below); columns that cannot be certified are
+// appended to `flagged` and re-evaluated in fp64 in the reference's order by exact.cu, so the
+// assignments equal the reference's bit for bit.
+#include "common.cuh"
+#include <math.h>
+
+namespace {
+
+struct FastParams {
+    const int4    *sell;
+    const int64_t *slice_ptr;
+    int64_t        nslices, n;
+    int            uniform, width2;
+    const float   *table;        // this chunk's table: [(p+1)][ks]
+    uint32_t       table_bytes;
+    int            ks;
+    int            k0, kvalid, ktotal;   // first centre of the chunk, centres in it, K
+    int            first, last;
+    float          ga;           // guard: relative term  1.01*(m+5)*u
+    float          gb_unit;      // guard: 2.02*u*sqrt(m)      (times cmax)
+    float          ge_unit;      // guard: 2.1*u*u*m           (times cmax^2)
+    const float   *cmax;
+    int32_t       *assign;
+    float         *dist;
+    float2        *best2;
+    int32_t       *flagged;
+    int           *nflag;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// Stage `bytes` (multiple of 16) from global to shared memory with TMA bulk copies tracked by
+// an mbarrier; all threads of the CTA return once the data has landed.
+__device__ __forceinline__ void tma_stage(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    const uint32_t bar_a = smem_u32(bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+        const uint32_t CH = 32768;
+        uint32_t dst = smem_u32(smem_dst);
+        const char *src = (const char *)gsrc;
+        for (uint32_t off = 0; off < bytes; off += CH) {
+            uint32_t sz = min(CH, bytes - off);
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                ::"r"(dst + off), "l"(src + off), "r"(sz), "r"(bar_a) : "memory");
+        }
+    }
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar_a) : "memory");
+    }
+}
+
+template <int KC>
+__device__ __forceinline__ void step(float (&acc)[KC], const float *tab, int ks, int r, float x)
+{
+    const float4 *row = reinterpret_cast<const float4 *>(tab + (size_t)r * ks);
+#pragma unroll
+    for (int c = 0; c < KC / 4; ++c) {
+        const float4 v = row[c];
+        float d;
+        d = x - v.x; acc[4 * c + 0] = fmaf(d, d, acc[4 * c + 0]);
+        d = x - v.y; acc[4 * c + 1] = fmaf(d, d, acc[4 * c + 1]);
+        d = x - v.z; acc[4 * c + 2] = fmaf(d, d, acc[4 * c + 2]);
+        d = x - v.w; acc[4 * c + 3] = fmaf(d, d, acc[4 * c + 3]);
+    }
+}
+
+template <int KC, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_assign_fast(const FastParams P)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    float *tab = reinterpret_cast<float *>(smem_raw);
+    tma_stage(tab, P.table, P.table_bytes, &bar);
+
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = ((int64_t)gridDim.x * THREADS) >> 5;
+    int64_t slice = ((int64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
+    const int ks = P.ks;
+
+    for (; slice < P.nslices; slice += warps_total) {
+        int64_t base;
+        int w2;
+        if (P.uniform) { base = slice * (int64_t)P.width2 * 32; w2 = P.width2; }
+        else { base = P.slice_ptr[slice]; w2 = (int)((P.slice_ptr[slice + 1] - base) >> 5); }
+        const int4 *src = P.sell + base + lane;
+
+        float acc[KC];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) acc[k] = 0.f;
+
+        int t2 = 0;
+        for (; t2 + 4 <= w2; t2 += 4) {
+            const int4 q0 = __ldcs(src + (t2 + 0) * 32);
+            const int4 q1 = __ldcs(src + (t2 + 1) * 32);
+            const int4 q2 = __ldcs(src + (t2 + 2) * 32);
+            const int4 q3 = __ldcs(src + (t2 + 3) * 32);
+            step<KC>(acc, tab, ks, q0.x, __int_as_float(q0.y));
+            step<KC>(acc, tab, ks, q0.z, __int_as_float(q0.w));
+            step<KC>(acc, tab, ks, q1.x, __int_as_float(q1.y));
+            step<KC>(acc, tab, ks, q1.z, __int_as_float(q1.w));
+            step<KC>(acc, tab, ks, q2.x, __int_as_float(q2.y));
+            step<KC>(acc, tab, ks, q2.z, __int_as_float(q2.w));
+            step<KC>(acc, tab, ks, q3.x, __int_as_float(q3.y));
+            step<KC>(acc, tab, ks, q3.z, __int_as_float(q3.w));
+        }
+        for (; t2 < w2; ++t2) {
+            const int4 q = __ldcs(src + t2 * 32);
+            step<KC>(acc, tab, ks, q.x, __int_as_float(q.y));
+            step<KC>(acc, tab, ks, q.z, __int_as_float(q.w));
+        }
+
+        // ---- per-column epilogue: best / second best of this chunk ----
+        const float INF = __int_as_float(0x7f800000);
+        const float QNAN = __int_as_float(0x7fc00000);
+        float b1 = INF, b2 = INF;
+        int i1 = P.k0;
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            if (k < P.kvalid) {
+                const float v = acc[k];
+                if (!(v < INF)) bad = true;                    // NaN or overflow: cannot certify
+                if (v < b1) { b2 = b1; b1 = v; i1 = P.k0 + k; }
+                else if (v < b2) b2 = v;
+            }
+        }
+        if (bad) b2 = QNAN;
+
+        const int64_t j = slice * SKM_SLICE + lane;
+        if (j >= P.n) continue;
+        if (!P.first) {                                        // merge with earlier chunks
+            const float2 r = P.best2[j];
+            const int ri = P.assign[j];
+            const bool nan2 = (r.y != r.y) || (b2 != b2);
+            if (b1 < r.x) { b2 = fminf(r.x, b2); }
+            else { b2 = fminf(r.y, b1); b1 = r.x; i1 = ri; }
+            if (nan2) b2 = QNAN;
+        }
+        if (!P.last) {
+            P.best2[j] = make_float2(b1, b2);
+            P.assign[j] = i1;
+            continue;
+        }
+        // ---- guard: |fp32 sum - exact sum| <= E(s) = ga*s + gb*sqrt(s) + ge   ----
+        const float cm = *P.cmax;
+        const float gb = P.gb_unit * cm, ge = P.ge_unit * cm * cm + 1e-37f;
+        bool certified;
+        if (P.ktotal == 1) certified = (b1 < INF);
+        else {
+            const float E = P.ga * (b1 + b2) + gb * (sqrtf(b1) + sqrtf(b2)) + 2.f * ge;
+            certified = (b2 - b1) > E;                         // false for NaN / inf
+        }
+        P.assign[j] = i1;
+        P.dist[j] = sqrtf(b1);
+        if (!certified) {
+            const int slot = atomicAdd(P.nflag, 1);
+            P.flagged[slot] = (int32_t)j;
+        }
+    }
+}
+
+__global__ void k_build_table(int64_t p, int64_t K, const double *__restrict__ ct, int kc, int ks,
+                              int nchunks, float *__restrict__ table, float *__restrict__ cmax)
+{
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t per_chunk = (p + 1) * ks;
+    int64_t total = per_chunk * nchunks;
+    float m = 0.f;
+    if (idx < total) {
+        int64_t c = idx / per_chunk, rem = idx % per_chunk;
+        int64_t r = rem / ks, kk = rem % ks;
+        int64_t k = c * kc + kk;
+        float v = 0.f;
+        if (kk < kc && k < K) v = (float)ct[r * K + k];
+        table[idx] = v;
+        m = fabsf(v);
+        if (v != v) m = __int_as_float(0x7fc00000);
+    }
+    // block max via warp shuffles on the int image (non-negative floats order like ints; NaN on top)
+    int mi = __float_as_int(m);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mi = max(mi, __shfl_xor_sync(0xffffffffu, mi, o));
+    if ((threadIdx.x & 31) == 0 && mi > 0) atomicMax(reinterpret_cast<int *>(cmax), mi);
+}
+
+template <int KC, int THREADS, int MINB>
+int launch_fast(skm_ctx *ctx, const FastParams &P, size_t smem)
+{
+    auto kern = k_assign_fast<KC, THREADS, MINB>;
+    SKM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+    if (per_sm < 1) {
+        skm_set_error("assign_fast<%d>: kernel does not fit on an SM (smem %zu)", KC, smem);
+        return SKM_ERR_UNSUPPORTED;
+    }
+    int64_t blocks = (int64_t)ctx->sm_count * per_sm;
+    int64_t need = (P.nslices * 32 + THREADS - 1) / THREADS;
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+    kern<<<(unsigned)blocks, THREADS, smem, ctx->stream>>>(P);
+    SKM_CHECK_LAUNCH(ctx);
+    return SKM_OK;
+}
+
+}  // namespace
+
+static const int kKcOptions[] = {4, 8, 12, 16, 24, 32, 48, 64};
+
+static int stride_for(int kc)
+{
+    int chunks = kc / 4;
+    return 4 * (chunks | 1);          // odd number of 16-byte chunks per row spreads the banks
+}
+
+bool skm_fast_plan(const skm_ctx *ctx, int64_t p, int64_t K, FastPlan *plan)
+{
+    const size_t budget = (size_t)ctx->smem_optin - 1024;
+    int best = -1;
+    // smallest chunk that covers K in one launch and fits; else the largest that fits
+    for (int kc : kKcOptions) {
+        size_t bytes = (size_t)(p + 1) * stride_for(kc) * sizeof(float);
+        if (bytes > budget) break;
+        best = kc;
+        if (kc >= K) break;
+    }
+    if (best < 0) return false;
+    plan->kc = best;
+    plan->ks = stride_for(best);
+    plan->nchunks = (int)((K + best - 1) / best);
+    plan->smem = (((size_t)(p + 1) * plan->ks * sizeof(float)) + 127) & ~(size_t)127;
+    plan->threads = 256;
+    return true;
+}
+
+int skm_launch_build_table(skm_ctx *ctx, int64_t p, int64_t K, const double *ct, const FastPlan &pl,
+                           float *table, float *cmax)
+{
+    SKM_CUDA(cudaMemsetAsync(cmax, 0, sizeof(float), ctx->stream));
+    int64_t total = (p + 1) * pl.ks * (int64_t)pl.nchunks;
+    int64_t blocks = (total + 255) / 256;
+    k_build_table<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p, K, ct, pl.kc, pl.ks, pl.nchunks, table, cmax);
+    SKM_CHECK_LAUNCH(ctx);
+    return SKM_OK;
+}
+
+int skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const FastPlan &pl,
+                           const float *table, const float *cmax, int32_t *assign, float *dist,
+                           float *best2, int32_t *flagged, int *nflag)
+{
+    SKM_CUDA(cudaMemsetAsync(nflag, 0, sizeof(int), ctx->stream));
+    if (ds->n == 0) return SKM_OK;
+    const double u = 5.9604644775390625e-08;   // 2^-24
+    const double m = (double)(ds->max_col_nnz > 0 ? ds->max_col_nnz : 1);
+    FastParams P;
+    P.sell = ds->sell;
+    P.slice_ptr = ds->slice_ptr;
+    P.nslices = ds->nslices;
+    P.n = ds->n;
+    P.uniform = ds->uniform_width ? 1 : 0;
+    P.width2 = ds->sell_width2;
+    P.ks = pl.ks;
+    P.table_bytes = (uint32_t)((size_t)(ds->p + 1) * pl.ks * sizeof(float));
+    P.ktotal = (int)K;
+    P.ga = (float)(1.01 * (m + 5.0) * u);
+    P.gb_unit = (float)(2.02 * u * sqrt(m));
+    P.ge_unit = (float)(2.1 * u * u * m);
+    P.cmax = cmax;
+    P.assign = assign;
+    P.dist = dist;
+    P.best2 = reinterpret_cast<float2 *>(best2);
+    P.flagged = flagged;
+    P.nflag = nflag;
+    for (int c = 0; c < pl.nchunks; ++c) {
+        P.table = table + (size_t)c * (ds->p + 1) * pl.ks;
+        P.k0 = c * pl.kc;
+        P.kvalid = (int)((K - P.k0) < pl.kc ? (K - P.k0) : pl.kc);
+        P.first = (c == 0);
+        P.last = (c == pl.nchunks - 1);
+        int rc;
+        switch (pl.kc) {
+            case 4:  rc = launch_fast<4, 256, 4>(ctx, P, pl.smem); break;
+            case 8:  rc = launch_fast<8, 256, 4>(ctx, P, pl.smem); break;
+            case 12: rc = launch_fast<12, 256, 4>(ctx, P, pl.smem); break;
+            case 16: rc = launch_fast<16, 256, 4>(ctx, P, pl.smem); break;
+            case 24: rc = launch_fast<24, 256, 3>(ctx, P, pl.smem); break;
+            case 32: rc = launch_fast<32, 256, 2>(ctx, P, pl.smem); break;
+            case 48: rc = launch_fast<48, 256, 2>(ctx, P, pl.smem); break;
+            case 64: rc = launch_fast<64, 256, 2>(ctx, P, pl.smem); break;
+            default: skm_set_error("assign_fast: unsupported chunk %d", pl.kc); return SKM_ERR_UNSUPPORTED;
+        }
+        if (rc != SKM_OK) return rc;
+    }
+    return SKM_OK;
+}

@@ -1,0 +1,197 @@
+// common.cuh -- shared declarations of libskm_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include "../../include/skm_b200.h"
+
+#define SKM_SLICE 32          // columns per SELL slice == warp width
+
+void skm_set_error(const char *fmt, ...);
+
+#define SKM_CUDA(call)                                                              \
+    do {                                                                            \
+        cudaError_t e__ = (call);                                                   \
+        if (e__ != cudaSuccess) {                                                   \
+            skm_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),  \
+                          __FILE__, __LINE__);                                      \
+            return SKM_ERR_CUDA;                                                    \
+        }                                                                           \
+    } while (0)
+
+#define SKM_CHECK_LAUNCH(ctx)                                                       \
+    do {                                                                            \
+        (ctx)->launches++;                                                          \
+        cudaError_t e__ = cudaGetLastError();                                       \
+        if (e__ != cudaSuccess) {                                                   \
+            skm_set_error("kernel launch failed: %s (%s:%d)",                       \
+                          cudaGetErrorString(e__), __FILE__, __LINE__);             \
+            return SKM_ERR_CUDA;                                                    \
+        }                                                                           \
+    } while (0)
+
+#define SKM_TRY(expr)                                                               \
+    do {                                                                            \
+        int rc__ = (expr);                                                          \
+        if (rc__ != SKM_OK) return rc__;                                            \
+    } while (0)
+
+#define SKM_REQUIRE(cond, ...)                                                      \
+    do {                                                                            \
+        if (!(cond)) {                                                              \
+            skm_set_error(__VA_ARGS__);                                             \
+            return SKM_ERR_INVALID;                                                 \
+        }                                                                           \
+    } while (0)
+
+struct skm_ctx {
+    int          device;
+    cudaStream_t stream;
+    bool         own_stream;
+    int64_t      launches;
+    int          sm_count;
+    int          smem_optin;       // max dynamic shared memory per block (bytes)
+    int         *d_flag;           // device int[4] scratch (validation / counters)
+    int         *h_flag;           // pinned host mirror
+};
+
+// RAII device buffer used for temporaries inside one API call.
+struct DevBuf {
+    void  *ptr = nullptr;
+    size_t bytes = 0;
+    DevBuf() {}
+    ~DevBuf() { if (ptr) cudaFree(ptr); }
+    int alloc(size_t n) {
+        if (ptr) { cudaFree(ptr); ptr = nullptr; }
+        bytes = n;
+        if (n == 0) return SKM_OK;
+        cudaError_t e = cudaMalloc(&ptr, n);
+        if (e != cudaSuccess) {
+            ptr = nullptr;
+            skm_set_error("cudaMalloc(%zu bytes) failed: %s", n, cudaGetErrorString(e));
+            cudaGetLastError();
+            return SKM_ERR_NOMEM;
+        }
+        return SKM_OK;
+    }
+    template <class T> T *as() const { return (T *)ptr; }
+    void *release() { void *p = ptr; ptr = nullptr; return p; }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+
+struct skm_dataset {
+    skm_ctx *ctx;
+    int64_t  p, n, nnz, max_col_nnz;
+    int      store_dtype;               // SKM_F32 | SKM_F64
+    // CSC in stored order (always present)
+    int64_t *colptr;                    // [n+1]
+    int32_t *rowidx;                    // [nnz]
+    void    *val;                       // float[nnz] or double[nnz]
+    // SELL-32 image for the fast kernel (SKM_F32 only):
+    //   slice s holds columns [32s, 32s+32); its entries are interleaved so that lane l's
+    //   pair t2 = (row_{2t2}, val_{2t2}, row_{2t2+1}, val_{2t2+1}) sits at
+    //   sell[slice_ptr[s] + t2*32 + l]; pad entries are (row = p, val = 0).
+    int4    *sell;
+    int64_t *slice_ptr;                 // [nslices+1], in int4 units
+    int64_t  nslices, sell_elems;       // sell_elems in int4 units
+    bool     uniform_width;             // every slice has the same width
+    int      sell_width2;               // pairs per column if uniform_width
+    // k-means++ running minimum distance (allocated on first use)
+    double  *kpp_mind;                  // [n]
+    double  *kpp_cum;                   // [n] inclusive scan of mind^2
+    int64_t  device_bytes;
+};
+
+struct skm_lloyd {
+    skm_dataset *ds;
+    int64_t  K;
+    double  *centers;        // [p*K] column-major, current centres (unscaled)
+    double  *centers_old;    // [p*K]
+    double  *cscaled_t;      // [(p+1)*K] row-major c' = centers/gamma (double), row p = 0
+    float   *table;          // fast-path table, fp32, row-major with padded stride
+    float   *cmax;           // [1] max |c'|
+    int32_t *assign;         // [n] 0-based
+    float   *dist_f32;       // [n] (SKM_F32 datasets)
+    double  *dist_f64;       // [n] (SKM_F64 datasets, and rechecked columns mirror)
+    float   *best2;          // [2n] running best/second-best for K-chunked launches
+    int32_t *flagged;        // [n] uncertified columns
+    int     *nflag;          // device counter
+    double  *partials;       // [2*p*K + K + 1]
+    double  *stats;          // device [8]: dff^2, has_nan, n_empty, ...
+    double  *h_stats;        // pinned
+    int64_t *h_counts;       // pinned [K]
+    bool     assigned, accumulated;
+    int64_t  last_rechecked;
+};
+
+// ---- launchers (implemented across the .cu files) -------------------------
+
+// convert.cu
+int skm_launch_convert_index(skm_ctx *ctx, const void *src, int src_type, int64_t count,
+                             void *dst, int dst_is_i64);
+int skm_launch_convert_value(skm_ctx *ctx, const void *src, int src_type, int64_t count,
+                             void *dst, int dst_type);
+int skm_validate_csc(skm_ctx *ctx, int64_t p, int64_t n, int64_t nnz, const int64_t *colptr,
+                     const int32_t *rowidx, int64_t *max_col_nnz);
+int skm_build_sell(skm_dataset *ds);
+
+// exact.cu
+struct ExactArgs {
+    int64_t p, n, K;
+    const int64_t *colptr;
+    const int32_t *rowidx;
+    const void    *val;
+    int            val_type;        // SKM_F32 / SKM_F64
+    const double  *ct;              // row-major [p][K] scaled centres
+    const uint8_t *mask;            // optional row-major [p][K] support mask (sparse centres)
+    const double  *xdiv;            // optional [K] divisor applied to x (sparse centres)
+};
+int skm_launch_exact_dist(skm_ctx *ctx, const ExactArgs &a, int64_t j0, int64_t j1, double *dist);
+int skm_launch_exact_dist_beta(skm_ctx *ctx, const ExactArgs &a, double beta, double *dist);
+int skm_launch_exact_assign(skm_ctx *ctx, const ExactArgs &a, int32_t *assign, double *dist64,
+                            float *dist32, const int32_t *subset, const int *subset_count_dev,
+                            int64_t subset_max);
+int skm_launch_inner_product(skm_ctx *ctx, int64_t n, const int64_t *colptr, const int32_t *rowidx,
+                             const double *val, const double *c, double *inner, double *normsq);
+int skm_launch_prep_centers(skm_ctx *ctx, int64_t p, int64_t K, const double *centers,
+                            int has_gamma, double gamma, double *ct /* [(p+1)*K] */,
+                            uint8_t *mask /* nullable */, double *xdiv /* nullable */);
+
+// assign_fast.cu
+struct FastPlan {
+    int kc;           // centres per launch (compile-time chunk)
+    int ks;           // table row stride in floats
+    int nchunks;      // launches per assignment pass
+    size_t smem;      // dynamic shared memory per block
+    int threads;
+};
+bool skm_fast_plan(const skm_ctx *ctx, int64_t p, int64_t K, FastPlan *plan);
+int  skm_launch_build_table(skm_ctx *ctx, int64_t p, int64_t K, const double *ct, const FastPlan &pl,
+                            float *table, float *cmax);
+int  skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const FastPlan &pl,
+                            const float *table, const float *cmax, int32_t *assign, float *dist,
+                            float *best2, int32_t *flagged, int *nflag);
+
+// update.cu
+int skm_launch_accumulate(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const int32_t *assign,
+                          const float *dist32, const double *dist64, double *partials);
+int skm_launch_finalize(skm_ctx *ctx, int64_t p, int64_t K, const double *partials, double gamma,
+                        int ml_correction, double *centers, double *centers_old, double *stats);
+int skm_launch_argmax(skm_ctx *ctx, int64_t n, const float *dist32, const double *dist64,
+                      double *out_val, int64_t *out_idx);
+
+// fwht.cu
+int skm_launch_fwht_f64(skm_ctx *ctx, int64_t m, int64_t n, double *x_inplace,
+                        const double *signs /* nullable, length m */, double divide_by /* 0 = none */);
+int skm_launch_fwht_f32(skm_ctx *ctx, int64_t m, int64_t n, float *x_inplace,
+                        const float *signs /* nullable */, float divide_by /* 0 = none */);
+int skm_launch_fwht_sample_f32(skm_ctx *ctx, int64_t p2, int64_t n, int64_t m, const float *x,
+                               const float *signs, const int32_t *rows, int64_t *colptr,
+                               int32_t *rowidx, float *val);
+
+// kpp.cu
+int skm_launch_kpp_update(skm_ctx *ctx, const skm_dataset *ds, const double *c_scaled /* dev [p] */,
+                          int first, double *mind, double *sum_out_dev);
+int skm_launch_scan_sq(skm_ctx *ctx, int64_t n, const double *mind, double *cum);

@@ -1,0 +1,220 @@
+// convert.cu -- upload-time conversions: index/value narrowing, CSC validation and the
+// SELL-32 image the fast assignment kernel streams (layout described in common.cuh).
+#include "common.cuh"
+#include <vector>
+
+namespace {
+
+template <typename S, typename D>
+__global__ void k_convert(const S *__restrict__ src, D *__restrict__ dst, int64_t count)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < count; i += stride) dst[i] = (D)src[i];
+}
+
+template <typename S, typename D>
+int convert(skm_ctx *ctx, const void *src, void *dst, int64_t count)
+{
+    if (count == 0) return SKM_OK;
+    int threads = 256;
+    int64_t blocks = (count + threads - 1) / threads;
+    int64_t cap = (int64_t)ctx->sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    k_convert<S, D><<<(unsigned)blocks, threads, 0, ctx->stream>>>((const S *)src, (D *)dst, count);
+    SKM_CHECK_LAUNCH(ctx);
+    return SKM_OK;
+}
+
+// flag[0] |= 1 if colptr is not non-decreasing / does not start at 0 / does not end at nnz
+// flag[0] |= 2 if a row index is outside [0,p)
+// flag[1]  = max column length
+__global__ void k_validate_cols(int64_t n, int64_t nnz, const int64_t *__restrict__ colptr, int *flag)
+{
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int bad = 0, mx = 0;
+    if (j == 0 && (colptr[0] != 0 || colptr[n] != nnz)) bad = 1;
+    for (; j < n; j += stride) {
+        int64_t a = colptr[j], b = colptr[j + 1];
+        if (b < a || a < 0 || b > nnz) bad = 1;
+        else if (b - a > mx) mx = (int)min((int64_t)INT32_MAX, b - a);
+    }
+    if (bad) atomicOr(&flag[0], 1);
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(&flag[1], mx);
+}
+
+__global__ void k_validate_rows(int64_t p, int64_t nnz, const int32_t *__restrict__ rowidx, int *flag)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int bad = 0;
+    for (; i < nnz; i += stride) {
+        int32_t r = rowidx[i];
+        if (r < 0 || (int64_t)r >= p) bad = 1;
+    }
+    if (bad) atomicOr(&flag[0], 2);
+}
+
+// pairs per column of each slice (max column length in the slice, rounded up to even, / 2)
+__global__ void k_slice_width(int64_t n, int64_t nslices, const int64_t *__restrict__ colptr,
+                              int32_t *__restrict__ width2)
+{
+    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= nslices) return;
+    int64_t j = warp * SKM_SLICE + lane;
+    int len = 0;
+    if (j < n) len = (int)(colptr[j + 1] - colptr[j]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if (lane == 0) width2[warp] = (len + 1) >> 1;
+}
+
+template <typename VT>
+__global__ void k_fill_sell(int64_t p, int64_t n, int64_t nslices, const int64_t *__restrict__ colptr,
+                            const int32_t *__restrict__ rowidx, const VT *__restrict__ val,
+                            const int64_t *__restrict__ slice_ptr, int4 *__restrict__ sell)
+{
+    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= nslices) return;
+    int64_t j = warp * SKM_SLICE + lane;
+    int64_t a = 0, b = 0;
+    if (j < n) { a = colptr[j]; b = colptr[j + 1]; }
+    int64_t base = slice_ptr[warp];
+    int w2 = (int)((slice_ptr[warp + 1] - base) >> 5);
+    const int pad_row = (int)p;
+    for (int t2 = 0; t2 < w2; ++t2) {
+        int4 q;
+        int64_t t = a + 2 * (int64_t)t2;
+        if (t < b) { q.x = rowidx[t]; q.y = __float_as_int((float)val[t]); }
+        else       { q.x = pad_row;   q.y = 0; }
+        if (t + 1 < b) { q.z = rowidx[t + 1]; q.w = __float_as_int((float)val[t + 1]); }
+        else           { q.z = pad_row;       q.w = 0; }
+        sell[base + (int64_t)t2 * 32 + lane] = q;
+    }
+}
+
+}  // namespace
+
+int skm_launch_convert_index(skm_ctx *ctx, const void *src, int src_type, int64_t count, void *dst,
+                             int dst_is_i64)
+{
+    if (src_type == SKM_I64) {
+        return dst_is_i64 ? convert<int64_t, int64_t>(ctx, src, dst, count)
+                          : convert<int64_t, int32_t>(ctx, src, dst, count);
+    } else if (src_type == SKM_I32) {
+        return dst_is_i64 ? convert<int32_t, int64_t>(ctx, src, dst, count)
+                          : convert<int32_t, int32_t>(ctx, src, dst, count);
+    }
+    skm_set_error("index type must be SKM_I32 or SKM_I64");
+    return SKM_ERR_INVALID;
+}
+
+int skm_launch_convert_value(skm_ctx *ctx, const void *src, int src_type, int64_t count, void *dst,
+                             int dst_type)
+{
+    if (src_type == SKM_F64 && dst_type == SKM_F64) return convert<double, double>(ctx, src, dst, count);
+    if (src_type == SKM_F64 && dst_type == SKM_F32) return convert<double, float>(ctx, src, dst, count);
+    if (src_type == SKM_F32 && dst_type == SKM_F64) return convert<float, double>(ctx, src, dst, count);
+    if (src_type == SKM_F32 && dst_type == SKM_F32) return convert<float, float>(ctx, src, dst, count);
+    skm_set_error("value type must be SKM_F32 or SKM_F64");
+    return SKM_ERR_INVALID;
+}
+
+int skm_validate_csc(skm_ctx *ctx, int64_t p, int64_t n, int64_t nnz, const int64_t *colptr,
+                     const int32_t *rowidx, int64_t *max_col_nnz)
+{
+    SKM_CUDA(cudaMemsetAsync(ctx->d_flag, 0, 4 * sizeof(int), ctx->stream));
+    int64_t cap = (int64_t)ctx->sm_count * 16;
+    if (n > 0) {
+        int64_t blocks = (n + 255) / 256;
+        if (blocks > cap) blocks = cap;
+        k_validate_cols<<<(unsigned)blocks, 256, 0, ctx->stream>>>(n, nnz, colptr, ctx->d_flag);
+        SKM_CHECK_LAUNCH(ctx);
+    }
+    if (nnz > 0) {
+        int64_t blocks = (nnz + 255) / 256;
+        if (blocks > cap) blocks = cap;
+        k_validate_rows<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p, nnz, rowidx, ctx->d_flag);
+        SKM_CHECK_LAUNCH(ctx);
+    }
+    SKM_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    SKM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_flag[0] & 1) {
+        skm_set_error("invalid CSC column pointers (must start at 0, be non-decreasing, end at nnz)");
+        return SKM_ERR_INVALID;
+    }
+    if (ctx->h_flag[0] & 2) {
+        skm_set_error("invalid CSC row index (must lie in [0,p))");
+        return SKM_ERR_INVALID;
+    }
+    *max_col_nnz = ctx->h_flag[1];
+    return SKM_OK;
+}
+
+int skm_build_sell(skm_dataset *ds)
+{
+    skm_ctx *ctx = ds->ctx;
+    int64_t n = ds->n;
+    int64_t nslices = (n + SKM_SLICE - 1) / SKM_SLICE;
+    ds->nslices = nslices;
+    ds->sell = nullptr;
+    ds->slice_ptr = nullptr;
+    ds->sell_elems = 0;
+    if (nslices == 0) return SKM_OK;
+
+    DevBuf w2;
+    SKM_TRY(w2.alloc(sizeof(int32_t) * nslices));
+    {
+        int64_t threads_total = nslices * 32;
+        int64_t blocks = (threads_total + 255) / 256;
+        k_slice_width<<<(unsigned)blocks, 256, 0, ctx->stream>>>(n, nslices, ds->colptr, w2.as<int32_t>());
+        SKM_CHECK_LAUNCH(ctx);
+    }
+    std::vector<int32_t> hw(nslices);
+    SKM_CUDA(cudaMemcpyAsync(hw.data(), w2.ptr, sizeof(int32_t) * nslices, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    SKM_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<int64_t> hp(nslices + 1);
+    hp[0] = 0;
+    bool uniform = true;
+    for (int64_t s = 0; s < nslices; ++s) {
+        hp[s + 1] = hp[s] + (int64_t)hw[s] * 32;
+        if (hw[s] != hw[0]) uniform = false;
+    }
+    ds->uniform_width = uniform;
+    ds->sell_width2 = hw[0];
+    ds->sell_elems = hp[nslices];
+
+    void *d = nullptr;
+    cudaError_t e = cudaMalloc(&d, sizeof(int64_t) * (nslices + 1));
+    if (e != cudaSuccess) { skm_set_error("cudaMalloc(slice_ptr) failed: %s", cudaGetErrorString(e)); return SKM_ERR_NOMEM; }
+    ds->slice_ptr = (int64_t *)d;
+    SKM_CUDA(cudaMemcpyAsync(ds->slice_ptr, hp.data(), sizeof(int64_t) * (nslices + 1),
+                             cudaMemcpyHostToDevice, ctx->stream));
+    size_t sell_bytes = sizeof(int4) * (size_t)(ds->sell_elems > 0 ? ds->sell_elems : 1);
+    e = cudaMalloc(&d, sell_bytes);
+    if (e != cudaSuccess) { skm_set_error("cudaMalloc(sell, %zu bytes) failed: %s", sell_bytes, cudaGetErrorString(e)); return SKM_ERR_NOMEM; }
+    ds->sell = (int4 *)d;
+    ds->device_bytes += (int64_t)sell_bytes + (int64_t)sizeof(int64_t) * (nslices + 1);
+    if (ds->sell_elems > 0) {
+        int64_t blocks = (nslices * 32 + 255) / 256;
+        if (ds->store_dtype == SKM_F32)
+            k_fill_sell<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>(
+                ds->p, n, nslices, ds->colptr, ds->rowidx, (const float *)ds->val, ds->slice_ptr, ds->sell);
+        else
+            k_fill_sell<double><<<(unsigned)blocks, 256, 0, ctx->stream>>>(
+                ds->p, n, nslices, ds->colptr, ds->rowidx, (const double *)ds->val, ds->slice_ptr, ds->sell);
+        SKM_CHECK_LAUNCH(ctx);
+    }
+    SKM_CUDA(cudaStreamSynchronize(ctx->stream));   // hp goes out of scope
+    return SKM_OK;
+}

@@ -1,0 +1,326 @@
+"""Handle wrappers over the level-2 C ABI: Context, Dataset (resident sparsified matrix) and
+Lloyd (per-K iteration state).  Everything numeric happens inside libskm_b200.so; this
+module only marshals numpy buffers (host) or raw device pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import SKM_F32, SKM_F64, SKM_I32, SKM_I64, check
+
+_NP_INDEX = {np.dtype(np.int32): SKM_I32, np.dtype(np.int64): SKM_I64, np.dtype(np.uint64): SKM_I64}
+_NP_VALUE = {np.dtype(np.float32): SKM_F32, np.dtype(np.float64): SKM_F64}
+
+
+def _ptr(a) -> int:
+    return None if a is None else a.ctypes.data
+
+
+def _centers(a, rows: int):
+    """(rows, K) array -> (contiguous column-major float64 copy (flat), K)."""
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 1:
+        a = a.reshape(-1, 1)
+    if a.ndim != 2 or a.shape[0] != rows:
+        raise ValueError("Array of centers not of correct size")   # findClusterAssignments.m:55
+    if a.shape[1] < 1:
+        raise ValueError("need at least one centre")
+    return np.ascontiguousarray(a.T).reshape(-1), int(a.shape[1])
+
+
+class Context:
+    """One per process / GPU (skm_ctx)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        check(self._lib.skm_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise RuntimeError("context destroyed")
+        return self._h
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.skm_ctx_stream(self.handle) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.skm_ctx_launch_count(self.handle))
+
+    def synchronize(self):
+        check(self._lib.skm_ctx_sync(self.handle))
+
+    def close(self):
+        if self._h is not None:
+            self._lib.skm_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx: dict[int, Context] = {}
+
+
+def default_context(device: int = 0) -> Context:
+    ctx = _default_ctx.get(device)
+    if ctx is None:
+        ctx = _default_ctx[device] = Context(device)
+    return ctx
+
+
+@dataclass
+class IterStats:
+    dff: float
+    sumsq: float
+    n_empty: int
+    n_rechecked: int
+    n_points: int
+    has_nan: bool
+
+    @property
+    def objective(self) -> float:          # kmeans_sparsified.m:471
+        return float(np.sqrt(self.sumsq))
+
+
+class Dataset:
+    """A p x n sparsified matrix resident in HBM (skm_dataset). Points are columns."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self._lib = ctx._lib
+        self._h = handle
+        info = _lib.DatasetInfo()
+        check(self._lib.skm_dataset_get_info(handle, C.byref(info)))
+        self.p, self.n, self.nnz = int(info.p), int(info.n), int(info.nnz)
+        self.max_col_nnz = int(info.max_col_nnz)
+        self.store_dtype = "f32" if info.store_dtype == SKM_F32 else "f64"
+        self.device_bytes = int(info.device_bytes)
+        self.stream_bytes = int(info.stream_bytes)
+
+    # -- construction -----------------------------------------------------
+    @classmethod
+    def from_csc(cls, p: int, n: int, jc, ir, val, store: str = "f32", ctx: Context | None = None):
+        """Upload host CSC arrays (any of int32/int64/uint64 indices, float32/float64 values)."""
+        ctx = ctx or default_context()
+        jc = np.ascontiguousarray(jc)
+        ir = np.ascontiguousarray(ir)
+        val = np.ascontiguousarray(val)
+        if jc.dtype not in _NP_INDEX:
+            jc = jc.astype(np.int64)
+        if ir.dtype not in _NP_INDEX:
+            ir = ir.astype(np.int64)
+        if val.dtype not in _NP_VALUE:
+            val = val.astype(np.float64)
+        if jc.shape[0] != n + 1:
+            raise ValueError("jc must have n+1 entries")
+        h = C.c_void_p()
+        check(ctx._lib.skm_dataset_create_csc(
+            ctx.handle, p, n, _ptr(jc), _NP_INDEX[jc.dtype], _ptr(ir), _NP_INDEX[ir.dtype],
+            _ptr(val), _NP_VALUE[val.dtype], SKM_F32 if store == "f32" else SKM_F64, 0, C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def from_scipy(cls, X, store: str = "f32", ctx: Context | None = None):
+        """X: scipy.sparse matrix of shape (p, n), points as columns."""
+        import scipy.sparse as sp
+        X = sp.csc_matrix(X)
+        X.sort_indices()
+        return cls.from_csc(X.shape[0], X.shape[1], X.indptr, X.indices, X.data, store, ctx)
+
+    @classmethod
+    def from_device_csc(cls, p: int, n: int, jc_ptr: int, jc_type: int, ir_ptr: int, ir_type: int,
+                        val_ptr: int, val_type: int, store: str = "f32", ctx: Context | None = None):
+        """Adopt CSC arrays that already live on the GPU (copied into the library's layout)."""
+        ctx = ctx or default_context()
+        h = C.c_void_p()
+        check(ctx._lib.skm_dataset_create_csc(
+            ctx.handle, p, n, jc_ptr, jc_type, ir_ptr, ir_type, val_ptr, val_type,
+            SKM_F32 if store == "f32" else SKM_F64, 1, C.byref(h)))
+        return cls(ctx, h)
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise RuntimeError("dataset destroyed")
+        return self._h
+
+    def close(self):
+        if self._h is not None:
+            self._lib.skm_dataset_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- operators ----------------------------------------------------------
+    def get_column(self, j: int) -> np.ndarray:
+        out = np.empty(self.p, dtype=np.float64)
+        check(self._lib.skm_dataset_get_column(self.handle, int(j), _ptr(out)))
+        return out
+
+    def assign(self, centers, gamma=None, want_dist: bool = True):
+        """findClusterAssignments, dense centres: returns (assign 1-based int32, dist float64)."""
+        c, K = _centers(centers, self.p)
+        a = np.empty(self.n, dtype=np.int32)
+        d = np.empty(self.n, dtype=np.float64) if want_dist else None
+        check(self._lib.skm_assign(self.handle, _ptr(c), K, int(gamma is not None),
+                                   float(gamma if gamma is not None else 0.0), _ptr(a), _ptr(d)))
+        return a, d
+
+    def assign_sparse_centers(self, centers, gamma=None):
+        c, K = _centers(centers, self.p)
+        a = np.empty(self.n, dtype=np.int32)
+        d = np.empty(self.n, dtype=np.float64)
+        check(self._lib.skm_assign_sparse_centers(self.handle, _ptr(c), K, int(gamma is not None),
+                                                  float(gamma if gamma is not None else 0.0), _ptr(a), _ptr(d)))
+        return a, d
+
+    def masked_distances(self, centers) -> np.ndarray:
+        """K x n exact masked distances (SparseMatrixMinusCluster on resident data)."""
+        c, K = _centers(centers, self.p)
+        out = np.empty(K * self.n, dtype=np.float64)
+        check(self._lib.skm_masked_distances(self.handle, _ptr(c), K, _ptr(out)))
+        return out.reshape(self.n, K).T
+
+    # -- k-means++ ------------------------------------------------------------
+    def kpp_update(self, center, gamma=None, first: bool = False) -> float:
+        c = np.ascontiguousarray(center, dtype=np.float64).reshape(-1)
+        if c.shape[0] != self.p:
+            raise ValueError("centre must have p entries")
+        tot = C.c_double()
+        check(self._lib.skm_kpp_update(self.handle, _ptr(c), int(gamma is not None),
+                                       float(gamma if gamma is not None else 0.0), int(first), C.byref(tot)))
+        return tot.value
+
+    def kpp_pick(self, target: float) -> int:
+        j = C.c_int64()
+        check(self._lib.skm_kpp_pick(self.handle, float(target), C.byref(j)))
+        return int(j.value)
+
+    def kpp_mindist(self) -> np.ndarray:
+        out = np.empty(self.n, dtype=np.float64)
+        check(self._lib.skm_kpp_get_mindist(self.handle, _ptr(out)))
+        return out
+
+
+class Lloyd:
+    """Iteration state for K centres on one resident shard (skm_lloyd)."""
+
+    def __init__(self, ds: Dataset, K: int):
+        self.ds = ds
+        self.K = int(K)
+        self._lib = ds._lib
+        h = C.c_void_p()
+        check(self._lib.skm_lloyd_create(ds.handle, self.K, C.byref(h)))
+        self._h = h
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise RuntimeError("lloyd state destroyed")
+        return self._h
+
+    def close(self):
+        if self._h is not None:
+            self._lib.skm_lloyd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_centers(self, centers):
+        c, K = _centers(centers, self.ds.p)
+        if K != self.K:
+            raise ValueError("centers must be p x K")
+        check(self._lib.skm_lloyd_set_centers(self.handle, _ptr(c)))
+
+    def get_centers(self) -> np.ndarray:
+        out = np.empty(self.ds.p * self.K, dtype=np.float64)
+        check(self._lib.skm_lloyd_get_centers(self.handle, _ptr(out)))
+        return out.reshape(self.K, self.ds.p).T.copy()
+
+    def set_center_column(self, k: int, col):
+        c = np.ascontiguousarray(col, dtype=np.float64).reshape(-1)
+        check(self._lib.skm_lloyd_set_center_column(self.handle, int(k), _ptr(c)))
+
+    def assign(self, gamma=None):
+        check(self._lib.skm_lloyd_assign(self.handle, int(gamma is not None),
+                                         float(gamma if gamma is not None else 0.0)))
+
+    def accumulate(self):
+        check(self._lib.skm_lloyd_accumulate(self.handle))
+
+    def partials_ptr(self) -> tuple[int, int]:
+        n = C.c_int64()
+        p = self._lib.skm_lloyd_partials(self.handle, C.byref(n))
+        return int(p or 0), int(n.value)
+
+    def partials_tensor(self):
+        """The device buffer [S | N | counts | sumsq] as a torch float64 tensor (no copy)."""
+        import torch
+        ptr, n = self.partials_ptr()
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False),
+                                        "version": 2, "strides": None}
+        return torch.as_tensor(_Raw(), device=f"cuda:{self.ds.ctx.device}")
+
+    @staticmethod
+    def _stats(s: _lib.IterStats) -> IterStats:
+        return IterStats(float(s.dff), float(s.sumsq), int(s.n_empty), int(s.n_rechecked),
+                         int(s.n_points), bool(s.has_nan))
+
+    def finalize(self, gamma: float, ml_correction: bool = True) -> IterStats:
+        s = _lib.IterStats()
+        check(self._lib.skm_lloyd_finalize(self.handle, float(gamma), int(ml_correction), C.byref(s)))
+        return self._stats(s)
+
+    def refresh_diff(self) -> IterStats:
+        s = _lib.IterStats()
+        check(self._lib.skm_lloyd_refresh_diff(self.handle, C.byref(s)))
+        return self._stats(s)
+
+    def counts(self) -> np.ndarray:
+        out = np.empty(self.K, dtype=np.int64)
+        check(self._lib.skm_lloyd_get_counts(self.handle, _ptr(out)))
+        return out
+
+    def assignments(self, want_dist: bool = True):
+        a = np.empty(self.ds.n, dtype=np.int32)
+        d = np.empty(self.ds.n, dtype=np.float64) if want_dist else None
+        check(self._lib.skm_lloyd_get_assignments(self.handle, _ptr(a), _ptr(d)))
+        return a, d
+
+    def argmax_distance(self) -> tuple[float, int]:
+        v = C.c_double()
+        j = C.c_int64()
+        check(self._lib.skm_lloyd_argmax_distance(self.handle, C.byref(v), C.byref(j)))
+        return v.value, int(j.value)
+
+    def step(self, gamma_dist, gamma_update: float, ml_correction: bool = True, reduce=None) -> IterStats:
+        """One Lloyd iteration on this shard: K1 assign, K2 accumulate, optional collective
+        (`reduce(partials_tensor)`), K3 finalize."""
+        self.assign(gamma_dist)
+        self.accumulate()
+        if reduce is not None:
+            reduce(self)
+        return self.finalize(gamma_update, ml_correction)
