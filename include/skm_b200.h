@@ -78,6 +78,13 @@ int         skm_ctx_sync(skm_ctx *ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t     skm_ctx_launch_count(const skm_ctx *ctx);
 
+/* Per-kernel device timing with CUDA events on the context stream (off by default).
+ * skm_ctx_timing_read synchronises, writes the summed milliseconds and launch-group counts
+ * of the 8 slots {assign, recheck, accumulate, finalize, prep, fwht, kpp, upload} since the
+ * previous read into ms[8] / counts[8], and resets them. */
+int         skm_ctx_timing_enable(skm_ctx *ctx, int on);
+int         skm_ctx_timing_read(skm_ctx *ctx, double *ms, int64_t *counts);
+
 /* ---- Level 1: stateless, exact fp64, host buffers ----------------------- */
 
 /* dist = SparseMatrixMinusCluster(X, c [,beta])   (private/SparseMatrixMinusCluster.c:2-11,44-47)
@@ -169,6 +176,9 @@ int   skm_lloyd_set_center_column(skm_lloyd *L, int64_t k, const double *col /* 
 /* K1: masked distance + argmin of every local column against the current centres
  * (divided by gamma when has_gamma).  Asynchronous on the context stream. */
 int   skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma);
+/* Same, sparse-centres branch (private/findClusterAssignments.m:63-75): exact zeros of the
+ * current centres are structural zeros.  Exact fp64.  Synchronous. */
+int   skm_lloyd_assign_sparse(skm_lloyd *L, int has_gamma, double gamma);
 /* K2: zero the partials and add this shard's per-cluster row sums S (p x K),
  * support counts N (p x K), member counts (K) and sum of squared distances (1).
  * Asynchronous on the context stream. */

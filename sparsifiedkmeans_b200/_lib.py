@@ -52,6 +52,8 @@ SIGNATURES = {
     "skm_ctx_device": (_int, [_vp]),
     "skm_ctx_sync": (_int, [_vp]),
     "skm_ctx_launch_count": (_i64, [_vp]),
+    "skm_ctx_timing_enable": (_int, [_vp, _int]),
+    "skm_ctx_timing_read": (_int, [_vp, _vp, _vp]),
     "skm_sparse_matrix_minus_cluster": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _int, _dbl, _vp]),
     "skm_sparse_matrix_inner_product": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "skm_sparse_matrix_column_normsq": (_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
@@ -70,6 +72,7 @@ SIGNATURES = {
     "skm_lloyd_get_centers": (_int, [_vp, _vp]),
     "skm_lloyd_set_center_column": (_int, [_vp, _i64, _vp]),
     "skm_lloyd_assign": (_int, [_vp, _int, _dbl]),
+    "skm_lloyd_assign_sparse": (_int, [_vp, _int, _dbl]),
     "skm_lloyd_accumulate": (_int, [_vp]),
     "skm_lloyd_partials": (_vp, [_vp, C.POINTER(_i64)]),
     "skm_lloyd_finalize": (_int, [_vp, _dbl, _int, C.POINTER(IterStats)]),

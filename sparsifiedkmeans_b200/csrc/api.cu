@@ -61,6 +61,9 @@ extern "C" int skm_ctx_create(int device, void *cuda_stream, skm_ctx **out)
     }
     ctx->d_flag = nullptr;
     ctx->h_flag = nullptr;
+    ctx->timing = false;
+    ctx->ev = nullptr;
+    memset(ctx->ev_count, 0, sizeof ctx->ev_count);
     if (cudaMalloc((void **)&ctx->d_flag, 16 * sizeof(int)) != cudaSuccess ||
         cudaMallocHost((void **)&ctx->h_flag, 16 * sizeof(int)) != cudaSuccess) {
         skm_set_error("context scratch allocation failed");
@@ -78,6 +81,11 @@ extern "C" void skm_ctx_destroy(skm_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->d_flag) cudaFree(ctx->d_flag);
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+    if (ctx->ev) {
+        for (int s = 0; s < SKM_T_SLOTS; ++s)
+            for (int i = 0; i < SKM_T_RING; ++i) { cudaEventDestroy(ctx->ev[s][i][0]); cudaEventDestroy(ctx->ev[s][i][1]); }
+        delete[] ctx->ev;
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -90,6 +98,42 @@ extern "C" int skm_ctx_sync(skm_ctx *ctx)
     SKM_REQUIRE(ctx, "ctx is NULL");
     SKM_CUDA(cudaSetDevice(ctx->device));
     SKM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SKM_OK;
+}
+
+extern "C" int skm_ctx_timing_enable(skm_ctx *ctx, int on)
+{
+    SKM_REQUIRE(ctx, "ctx is NULL");
+    SKM_CUDA(cudaSetDevice(ctx->device));
+    if (on && !ctx->ev) {
+        ctx->ev = new (std::nothrow) cudaEvent_t[SKM_T_SLOTS][SKM_T_RING][2];
+        if (!ctx->ev) { skm_set_error("out of host memory"); return SKM_ERR_NOMEM; }
+        for (int s = 0; s < SKM_T_SLOTS; ++s)
+            for (int i = 0; i < SKM_T_RING; ++i) {
+                SKM_CUDA(cudaEventCreate(&ctx->ev[s][i][0]));
+                SKM_CUDA(cudaEventCreate(&ctx->ev[s][i][1]));
+            }
+    }
+    ctx->timing = on != 0;
+    return SKM_OK;
+}
+
+extern "C" int skm_ctx_timing_read(skm_ctx *ctx, double *ms, int64_t *counts)
+{
+    SKM_REQUIRE(ctx && ms && counts, "NULL argument");
+    SKM_CUDA(cudaSetDevice(ctx->device));
+    SKM_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int s = 0; s < SKM_T_SLOTS; ++s) {
+        double tot = 0.0;
+        for (int i = 0; i < ctx->ev_count[s]; ++i) {
+            float t = 0.f;
+            SKM_CUDA(cudaEventElapsedTime(&t, ctx->ev[s][i][0], ctx->ev[s][i][1]));
+            tot += t;
+        }
+        ms[s] = tot;
+        counts[s] = ctx->ev_count[s];
+        ctx->ev_count[s] = 0;
+    }
     return SKM_OK;
 }
 
@@ -305,7 +349,13 @@ extern "C" void skm_lloyd_destroy(skm_lloyd *L)
     delete L;
 }
 
+static int skm_lloyd_create_ex(skm_dataset *ds, int64_t K, int want_f64_dist, skm_lloyd **out);
 extern "C" int skm_lloyd_create(skm_dataset *ds, int64_t K, skm_lloyd **out)
+{
+    return skm_lloyd_create_ex(ds, K, 1, out);
+}
+
+static int skm_lloyd_create_ex(skm_dataset *ds, int64_t K, int want_f64_dist, skm_lloyd **out)
 {
     SKM_REQUIRE(ds && out, "NULL argument");
     *out = nullptr;
@@ -335,8 +385,9 @@ extern "C" int skm_lloyd_create(skm_dataset *ds, int64_t K, skm_lloyd **out)
                 if ((rc = dev_alloc((void **)&L->table, sizeof(float) * (size_t)(p + 1) * pl.ks * pl.nchunks, "table"))) break;
                 if (pl.nchunks > 1 && (rc = dev_alloc((void **)&L->best2, sizeof(float) * 2 * n, "best2"))) break;
             }
-        } else {
-            if ((rc = dev_alloc((void **)&L->dist_f64, sizeof(double) * n, "dist"))) break;
+        }
+        if (ds->store_dtype == SKM_F64 || want_f64_dist) {
+            if ((rc = dev_alloc((void **)&L->dist_f64, sizeof(double) * n, "dist64"))) break;
         }
         if (cudaMallocHost((void **)&L->h_stats, sizeof(double) * 8) != cudaSuccess ||
             cudaMallocHost((void **)&L->h_counts, sizeof(int64_t) * (K + 2)) != cudaSuccess) {
@@ -386,19 +437,30 @@ extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
     skm_ctx *ctx = ds->ctx;
     SKM_TRY(enter(ctx));
     SKM_REQUIRE(!has_gamma || gamma == gamma, "gamma is NaN");
-    SKM_TRY(skm_launch_prep_centers(ctx, ds->p, L->K, L->centers, has_gamma, gamma, L->cscaled_t, nullptr, nullptr));
+    FastPlan pl;
+    const bool fast = ds->store_dtype == SKM_F32 && L->table && skm_fast_plan(ctx, ds->p, L->K, &pl);
+    {
+        SkmTimed t(ctx, SKM_T_PREP);
+        SKM_TRY(skm_launch_prep_centers(ctx, ds->p, L->K, L->centers, has_gamma, gamma, L->cscaled_t, nullptr, nullptr));
+        if (fast) SKM_TRY(skm_launch_build_table(ctx, ds->p, L->K, L->cscaled_t, pl, L->table, L->cmax));
+    }
     ExactArgs ea = exact_args(ds, L->K, L->cscaled_t);
     L->last_rechecked = -1;
-    FastPlan pl;
-    if (ds->store_dtype == SKM_F32 && L->table && skm_fast_plan(ctx, ds->p, L->K, &pl)) {
-        SKM_TRY(skm_launch_build_table(ctx, ds->p, L->K, L->cscaled_t, pl, L->table, L->cmax));
-        SKM_TRY(skm_launch_assign_fast(ctx, ds, L->K, pl, L->table, L->cmax, L->assign, L->dist_f32, L->best2,
-                                       L->flagged, L->nflag));
+    if (fast) {
+        {
+            SkmTimed t(ctx, SKM_T_ASSIGN);
+            SKM_TRY(skm_launch_assign_fast(ctx, ds, L->K, pl, L->table, L->cmax, L->assign, L->dist_f32, L->best2,
+                                           L->flagged, L->nflag));
+        }
         // columns the guard could not certify: fp64, reference order
+        SkmTimed t(ctx, SKM_T_RECHECK);
         SKM_TRY(skm_launch_exact_assign(ctx, ea, L->assign, nullptr, L->dist_f32, L->flagged, L->nflag, ds->n));
+        L->dist_is_f64 = false;
     } else {
+        SkmTimed t(ctx, SKM_T_ASSIGN);
         SKM_TRY(skm_launch_exact_assign(ctx, ea, L->assign, L->dist_f64, L->dist_f32, nullptr, nullptr, 0));
         SKM_CUDA(cudaMemsetAsync(L->nflag, 0, sizeof(int), ctx->stream));
+        L->dist_is_f64 = true;
     }
     L->assigned = true;
     L->accumulated = false;
@@ -410,7 +472,8 @@ extern "C" int skm_lloyd_accumulate(skm_lloyd *L)
     SKM_REQUIRE(L, "NULL argument");
     SKM_TRY(enter(L->ds->ctx));
     if (!L->assigned) { skm_set_error("skm_lloyd_accumulate called before skm_lloyd_assign"); return SKM_ERR_STATE; }
-    SKM_TRY(skm_launch_accumulate(L->ds->ctx, L->ds, L->K, L->assign, L->dist_f32, L->dist_f64, L->partials));
+    SkmTimed t(L->ds->ctx, SKM_T_ACCUM);
+    SKM_TRY(skm_launch_accumulate(L->ds->ctx, L->ds, L->K, L->assign, L->dist_f32, L->dist_is_f64 ? L->dist_f64 : nullptr, L->partials));
     L->accumulated = true;
     return SKM_OK;
 }
@@ -454,8 +517,11 @@ extern "C" int skm_lloyd_finalize(skm_lloyd *L, double gamma, int ml_correction,
     SKM_REQUIRE(L, "NULL argument");
     SKM_TRY(enter(L->ds->ctx));
     if (!L->accumulated) { skm_set_error("skm_lloyd_finalize called before skm_lloyd_accumulate"); return SKM_ERR_STATE; }
-    SKM_TRY(skm_launch_finalize(L->ds->ctx, L->ds->p, L->K, L->partials, gamma, ml_correction, L->centers,
-                                L->centers_old, L->stats));
+    {
+        SkmTimed t(L->ds->ctx, SKM_T_FINAL);
+        SKM_TRY(skm_launch_finalize(L->ds->ctx, L->ds->p, L->K, L->partials, gamma, ml_correction, L->centers,
+                                    L->centers_old, L->stats));
+    }
     return read_stats(L, stats);
 }
 
@@ -487,7 +553,7 @@ extern "C" int skm_lloyd_get_assignments(skm_lloyd *L, int32_t *assign_out, doub
         for (int64_t j = 0; j < n; ++j) assign_out[j] += 1;            // MATLAB is 1-based
     }
     if (dist_out) {
-        if (L->dist_f64) SKM_TRY(d2h_sync(ctx, dist_out, L->dist_f64, sizeof(double) * n));
+        if (L->dist_is_f64) SKM_TRY(d2h_sync(ctx, dist_out, L->dist_f64, sizeof(double) * n));
         else {
             std::vector<float> tmp(n);
             SKM_TRY(d2h_sync(ctx, tmp.data(), L->dist_f32, sizeof(float) * n));
@@ -507,7 +573,7 @@ extern "C" int skm_lloyd_argmax_distance(skm_lloyd *L, double *maxdist, int64_t 
     DevBuf v, i;
     SKM_TRY(v.alloc(sizeof(double)));
     SKM_TRY(i.alloc(sizeof(int64_t)));
-    SKM_TRY(skm_launch_argmax(ctx, L->ds->n, L->dist_f32, L->dist_f64, v.as<double>(), i.as<int64_t>()));
+    SKM_TRY(skm_launch_argmax(ctx, L->ds->n, L->dist_f32, L->dist_is_f64 ? L->dist_f64 : nullptr, v.as<double>(), i.as<int64_t>()));
     SKM_CUDA(cudaMemcpyAsync(maxdist, v.ptr, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     return d2h_sync(ctx, j, i.ptr, sizeof(int64_t));
 }
@@ -516,7 +582,7 @@ extern "C" void *skm_lloyd_assign_ptr(skm_lloyd *L) { return L ? L->assign : nul
 extern "C" void *skm_lloyd_dist_ptr(skm_lloyd *L, int *dtype)
 {
     if (!L) return nullptr;
-    if (L->dist_f64) { if (dtype) *dtype = SKM_F64; return L->dist_f64; }
+    if (L->dist_is_f64) { if (dtype) *dtype = SKM_F64; return L->dist_f64; }
     if (dtype) *dtype = SKM_F32;
     return L->dist_f32;
 }
@@ -537,47 +603,28 @@ extern "C" int skm_assign(skm_dataset *ds, const double *centers, int64_t K, int
     return rc;
 }
 
-static int exact_with_centers(skm_dataset *ds, const double *centers, int64_t K, int has_gamma, double gamma,
-                              bool sparse_centers, int32_t *assign_out, double *dist_out, double *full_dist)
+// sparse-centres branch on the Lloyd state (findClusterAssignments.m:63-75): exact fp64
+extern "C" int skm_lloyd_assign_sparse(skm_lloyd *L, int has_gamma, double gamma)
 {
+    SKM_REQUIRE(L, "NULL argument");
+    skm_dataset *ds = L->ds;
     skm_ctx *ctx = ds->ctx;
     SKM_TRY(enter(ctx));
-    SKM_REQUIRE(K >= 1, "K must be >= 1");
-    const int64_t p = ds->p, n = ds->n;
-    DevBuf dc, ct, mask, xdiv, dassign, ddist;
-    SKM_TRY(dc.alloc(sizeof(double) * p * K));
-    SKM_TRY(ct.alloc(sizeof(double) * (p + 1) * K));
-    if (sparse_centers) {
-        SKM_TRY(mask.alloc((size_t)(p + 1) * K));
-        SKM_TRY(xdiv.alloc(sizeof(double) * K));
-    }
-    SKM_TRY(h2d(ctx, dc.ptr, centers, sizeof(double) * p * K));
-    SKM_TRY(skm_launch_prep_centers(ctx, p, K, dc.as<double>(), has_gamma, gamma, ct.as<double>(),
-                                    sparse_centers ? mask.as<uint8_t>() : nullptr,
-                                    sparse_centers ? xdiv.as<double>() : nullptr));
-    ExactArgs ea = exact_args(ds, K, ct.as<double>());
-    if (sparse_centers) { ea.mask = mask.as<uint8_t>(); ea.xdiv = xdiv.as<double>(); }
-    if (full_dist) {
-        // K x n in column chunks so the device temporary stays bounded
-        const int64_t chunk = std::max<int64_t>(1, (int64_t)(256LL << 20) / (8 * K));
-        DevBuf tmp;
-        SKM_TRY(tmp.alloc(sizeof(double) * std::min(chunk, std::max<int64_t>(n, 1)) * K));
-        for (int64_t j0 = 0; j0 < n; j0 += chunk) {
-            const int64_t j1 = std::min(n, j0 + chunk);
-            SKM_TRY(skm_launch_exact_dist(ctx, ea, j0, j1, tmp.as<double>()));
-            SKM_TRY(d2h_sync(ctx, full_dist + j0 * K, tmp.ptr, sizeof(double) * (j1 - j0) * K));
-        }
-        return SKM_OK;
-    }
-    SKM_TRY(dassign.alloc(sizeof(int32_t) * n));
-    SKM_TRY(ddist.alloc(sizeof(double) * n));
-    SKM_TRY(skm_launch_exact_assign(ctx, ea, dassign.as<int32_t>(), ddist.as<double>(), nullptr, nullptr, nullptr, 0));
-    if (assign_out) {
-        SKM_TRY(d2h_sync(ctx, assign_out, dassign.ptr, sizeof(int32_t) * n));
-        for (int64_t j = 0; j < n; ++j) assign_out[j] += 1;
-    }
-    if (dist_out) SKM_TRY(d2h_sync(ctx, dist_out, ddist.ptr, sizeof(double) * n));
-    SKM_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int64_t p = ds->p, K = L->K;
+    DevBuf mask, xdiv;
+    SKM_TRY(mask.alloc((size_t)(p + 1) * K));
+    SKM_TRY(xdiv.alloc(sizeof(double) * K));
+    SKM_TRY(skm_launch_prep_centers(ctx, p, K, L->centers, has_gamma, gamma, L->cscaled_t, mask.as<uint8_t>(),
+                                    xdiv.as<double>()));
+    ExactArgs ea = exact_args(ds, K, L->cscaled_t);
+    ea.mask = mask.as<uint8_t>();
+    ea.xdiv = xdiv.as<double>();
+    SKM_TRY(skm_launch_exact_assign(ctx, ea, L->assign, L->dist_f64, L->dist_f32, nullptr, nullptr, 0));
+    SKM_CUDA(cudaMemsetAsync(L->nflag, 0, sizeof(int), ctx->stream));
+    SKM_CUDA(cudaStreamSynchronize(ctx->stream));        // mask/xdiv are freed on return
+    L->assigned = true;
+    L->accumulated = false;
+    L->dist_is_f64 = true;
     return SKM_OK;
 }
 
@@ -585,13 +632,38 @@ extern "C" int skm_assign_sparse_centers(skm_dataset *ds, const double *centers,
                                          double gamma, int32_t *assign_out, double *dist_out)
 {
     SKM_REQUIRE(ds && centers, "NULL argument");
-    return exact_with_centers(ds, centers, K, has_gamma, gamma, true, assign_out, dist_out, nullptr);
+    skm_lloyd *L = nullptr;
+    SKM_TRY(skm_lloyd_create_ex(ds, K, 1, &L));
+    int rc = skm_lloyd_set_centers(L, centers);
+    if (rc == SKM_OK) rc = skm_lloyd_assign_sparse(L, has_gamma, gamma);
+    if (rc == SKM_OK) rc = skm_lloyd_get_assignments(L, assign_out, dist_out);
+    skm_lloyd_destroy(L);
+    return rc;
 }
 
 extern "C" int skm_masked_distances(skm_dataset *ds, const double *centers, int64_t K, double *dist)
 {
     SKM_REQUIRE(ds && centers && dist, "NULL argument");
-    return exact_with_centers(ds, centers, K, 0, 0.0, false, nullptr, nullptr, dist);
+    skm_ctx *ctx = ds->ctx;
+    SKM_TRY(enter(ctx));
+    SKM_REQUIRE(K >= 1, "K must be >= 1");
+    const int64_t p = ds->p, n = ds->n;
+    DevBuf dc, ct, tmp;
+    SKM_TRY(dc.alloc(sizeof(double) * p * K));
+    SKM_TRY(ct.alloc(sizeof(double) * (p + 1) * K));
+    SKM_TRY(h2d(ctx, dc.ptr, centers, sizeof(double) * p * K));
+    SKM_TRY(skm_launch_prep_centers(ctx, p, K, dc.as<double>(), 0, 0.0, ct.as<double>(), nullptr, nullptr));
+    ExactArgs ea = exact_args(ds, K, ct.as<double>());
+    // K x n in column chunks so the device temporary stays bounded
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)(256LL << 20) / (8 * K));
+    SKM_TRY(tmp.alloc(sizeof(double) * std::min(chunk, std::max<int64_t>(n, 1)) * K));
+    for (int64_t j0 = 0; j0 < n; j0 += chunk) {
+        const int64_t j1 = std::min(n, j0 + chunk);
+        SKM_TRY(skm_launch_exact_dist(ctx, ea, j0, j1, tmp.as<double>()));
+        SKM_TRY(d2h_sync(ctx, dist + j0 * K, tmp.ptr, sizeof(double) * (j1 - j0) * K));
+    }
+    SKM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SKM_OK;
 }
 
 // ---------------------------------------------------------------------------

@@ -45,6 +45,11 @@ void skm_set_error(const char *fmt, ...);
         }                                                                           \
     } while (0)
 
+// per-kernel device timing (CUDA events on the launching stream), off by default
+enum { SKM_T_ASSIGN = 0, SKM_T_RECHECK = 1, SKM_T_ACCUM = 2, SKM_T_FINAL = 3, SKM_T_PREP = 4,
+       SKM_T_FWHT = 5, SKM_T_KPP = 6, SKM_T_UPLOAD = 7, SKM_T_SLOTS = 8 };
+#define SKM_T_RING 512
+
 struct skm_ctx {
     int          device;
     cudaStream_t stream;
@@ -54,6 +59,20 @@ struct skm_ctx {
     int          smem_optin;       // max dynamic shared memory per block (bytes)
     int         *d_flag;           // device int[4] scratch (validation / counters)
     int         *h_flag;           // pinned host mirror
+    bool         timing;
+    cudaEvent_t (*ev)[SKM_T_RING][2];   // [SKM_T_SLOTS][SKM_T_RING][2], created lazily
+    int          ev_count[SKM_T_SLOTS];
+};
+
+// RAII: records a start event now and a stop event at scope exit when timing is enabled
+struct SkmTimed {
+    skm_ctx *ctx; int slot; int idx;
+    SkmTimed(skm_ctx *c, int s) : ctx(c), slot(s), idx(-1) {
+        if (!c->timing || !c->ev || c->ev_count[s] >= SKM_T_RING) return;
+        idx = c->ev_count[s]++;
+        cudaEventRecord(c->ev[s][idx][0], c->stream);
+    }
+    ~SkmTimed() { if (idx >= 0) cudaEventRecord(ctx->ev[slot][idx][1], ctx->stream); }
 };
 
 // RAII device buffer used for temporaries inside one API call.
@@ -123,6 +142,7 @@ struct skm_lloyd {
     double  *h_stats;        // pinned
     int64_t *h_counts;       // pinned [K]
     bool     assigned, accumulated;
+    bool     dist_is_f64;    // which of dist_f64 / dist_f32 the last assignment wrote
     int64_t  last_rechecked;
 };
 

@@ -59,6 +59,18 @@ class Context:
     def synchronize(self):
         check(self._lib.skm_ctx_sync(self.handle))
 
+    TIMING_SLOTS = ("assign", "recheck", "accumulate", "finalize", "prep", "fwht", "kpp", "upload")
+
+    def timing_enable(self, on: bool = True):
+        check(self._lib.skm_ctx_timing_enable(self.handle, int(on)))
+
+    def timing_read(self) -> dict:
+        """{slot: (milliseconds, launch groups)} since the previous read (synchronises)."""
+        ms = np.zeros(8, dtype=np.float64)
+        cnt = np.zeros(8, dtype=np.int64)
+        check(self._lib.skm_ctx_timing_read(self.handle, _ptr(ms), _ptr(cnt)))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.TIMING_SLOTS)}
+
     def close(self):
         if self._h is not None:
             self._lib.skm_ctx_destroy(self._h)
@@ -265,6 +277,11 @@ class Lloyd:
     def assign(self, gamma=None):
         check(self._lib.skm_lloyd_assign(self.handle, int(gamma is not None),
                                          float(gamma if gamma is not None else 0.0)))
+
+    def assign_sparse(self, gamma=None):
+        """Sparse-centres branch (findClusterAssignments.m:63-75) against the current centres."""
+        check(self._lib.skm_lloyd_assign_sparse(self.handle, int(gamma is not None),
+                                                float(gamma if gamma is not None else 0.0)))
 
     def accumulate(self):
         check(self._lib.skm_lloyd_accumulate(self.handle))
