@@ -172,6 +172,8 @@ int   skm_lloyd_create(skm_dataset *ds, int64_t K, skm_lloyd **out);
 void  skm_lloyd_destroy(skm_lloyd *L);
 int   skm_lloyd_set_centers(skm_lloyd *L, const double *centers /* host p x K */);
 int   skm_lloyd_get_centers(skm_lloyd *L, double *centers /* host p x K */);
+/* centres as they were before the last skm_lloyd_finalize (centersOld, kmeans_sparsified.m:428) */
+int   skm_lloyd_get_centers_old(skm_lloyd *L, double *centers /* host p x K */);
 int   skm_lloyd_set_center_column(skm_lloyd *L, int64_t k, const double *col /* host p */);
 /* K1: masked distance + argmin of every local column against the current centres
  * (divided by gamma when has_gamma).  Asynchronous on the context stream. */

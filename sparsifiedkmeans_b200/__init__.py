@@ -6,6 +6,8 @@ behaviour) over libskm_b200.so, hand-written sm_100a CUDA behind a C ABI
 """
 from .engine import Context, Dataset, IterStats, Lloyd, default_context      # noqa: F401
 from .find_cluster_assignments import findClusterAssignments                  # noqa: F401
+from .kmeans import (Arthur_initialization, KMeansError, kmeans_sparsified,    # noqa: F401
+                     randsample_block, randsample_fixedNumberEntries)
 from .ops import (SparseMatrixColumnNormSq, SparseMatrixInnerProduct,         # noqa: F401
                   SparseMatrixMinusCluster, hadamard, hadamard_pthreads)
 

@@ -70,6 +70,7 @@ SIGNATURES = {
     "skm_lloyd_destroy": (None, [_vp]),
     "skm_lloyd_set_centers": (_int, [_vp, _vp]),
     "skm_lloyd_get_centers": (_int, [_vp, _vp]),
+    "skm_lloyd_get_centers_old": (_int, [_vp, _vp]),
     "skm_lloyd_set_center_column": (_int, [_vp, _i64, _vp]),
     "skm_lloyd_assign": (_int, [_vp, _int, _dbl]),
     "skm_lloyd_assign_sparse": (_int, [_vp, _int, _dbl]),

@@ -420,6 +420,13 @@ extern "C" int skm_lloyd_get_centers(skm_lloyd *L, double *centers)
     return d2h_sync(L->ds->ctx, centers, L->centers, sizeof(double) * L->ds->p * L->K);
 }
 
+extern "C" int skm_lloyd_get_centers_old(skm_lloyd *L, double *centers)
+{
+    SKM_REQUIRE(L && centers, "NULL argument");
+    SKM_TRY(enter(L->ds->ctx));
+    return d2h_sync(L->ds->ctx, centers, L->centers_old, sizeof(double) * L->ds->p * L->K);
+}
+
 extern "C" int skm_lloyd_set_center_column(skm_lloyd *L, int64_t k, const double *col)
 {
     SKM_REQUIRE(L && col, "NULL argument");

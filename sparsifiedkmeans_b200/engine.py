@@ -270,6 +270,11 @@ class Lloyd:
         check(self._lib.skm_lloyd_get_centers(self.handle, _ptr(out)))
         return out.reshape(self.K, self.ds.p).T.copy()
 
+    def get_centers_old(self) -> np.ndarray:
+        out = np.empty(self.ds.p * self.K, dtype=np.float64)
+        check(self._lib.skm_lloyd_get_centers_old(self.handle, _ptr(out)))
+        return out.reshape(self.K, self.ds.p).T.copy()
+
     def set_center_column(self, k: int, col):
         c = np.ascontiguousarray(col, dtype=np.float64).reshape(-1)
         check(self._lib.skm_lloyd_set_center_column(self.handle, int(k), _ptr(c)))

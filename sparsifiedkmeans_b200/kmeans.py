@@ -1,0 +1,354 @@
+"""kmeans_sparsified: host-side mirror of the reference's entry point for the sparsified path.
+
+    [IDX, C, SUMD, D, OUTPUT] = kmeans_sparsified(X, K, 'Name', value, ...)   (kmeans_sparsified.m:1)
+
+Same option names, defaults and error behaviour as the reference's inputParser
+(kmeans_sparsified.m:130-156).  The preconditioning, the per-iteration assignment, the
+per-cluster sums and the centre update run on the GPU through libskm_b200; this file only
+sequences them the way kmeans_sparsified.m:213-607 does.
+
+Scope: the sparsified path (`Sparsify=True`) with the Hadamard sketch
+(or 'none').  The dense path (Sparsify=False), the DCT sketch, loading from disk (`DataFile`)
+and the two-pass outputs (nargout > 5) are outside the hot path and raise NotImplementedError.
+
+Randomness: MATLAB's generators are closed source, so the random draws (Rademacher signs, row
+samples, k-means++ picks) come from `numpy.random.default_rng(Seed)`; every draw can also be
+supplied explicitly (`Signs`, `SampleRows`, `StartIndices`) so a run can be reproduced
+bit-for-bit against the oracle.
+"""
+from __future__ import annotations
+
+import math
+import time
+import warnings
+
+import numpy as np
+
+from . import ops
+from .engine import Context, Dataset, Lloyd, default_context
+
+__version__ = 2.1          # the reference's version number (kmeans_sparsified.m:121)
+
+_DEFAULTS = dict(
+    Replicates=1, Start="Arthur", MaxIter=100, Display=False, PrintEvery=10, Tol=1e-6,
+    Sparsify=False, SparsityLevel=0.01, SketchType="auto", EmptyAction="singleton",
+    ColumnSamples=False, MLcorrection=True, DataFile=None, MB_limit=500, DataFileVerbose=False,
+    SparsityIgnoreUpsampling=False, FORCE_BUG=False, tryBuiltinMex=True, unbiasedDistance=True,
+    unbiasedInitialization=True, denseCenters=False,
+)
+_EXTRA = dict(Seed=None, Signs=None, SampleRows=None, StartIndices=None, Store="f32", Device=0,
+              MixDtype="f64", nargout=5, Context=None)
+
+
+class KMeansError(RuntimeError):
+    """error('id','msg') of the reference; `identifier` carries the id."""
+
+    def __init__(self, msg, identifier=""):
+        super().__init__(msg)
+        self.identifier = identifier
+
+
+def matlab_round(v: float) -> int:
+    """MATLAB round(): half away from zero."""
+    return int(math.floor(abs(v) + 0.5) * (1 if v >= 0 else -1))
+
+
+def _nextpow2_size(p: int) -> int:
+    p2 = 1
+    while p2 < p:
+        p2 <<= 1
+    return p2
+
+
+def randsample_block(rng, n: int, k: int, n_rep: int) -> np.ndarray:
+    """(k, n_rep) 0-based distinct row indices per column, uniform without replacement
+    (contract of private/randsample_block.m:44-84; the order inside a column is irrelevant
+    because sparse() sorts, randsample_fixedNumberEntries.m:62)."""
+    out = np.empty((k, n_rep), dtype=np.int32)
+    step = max(1, (64 << 20) // max(n, 1))
+    for c0 in range(0, n_rep, step):
+        c = min(step, n_rep - c0)
+        keys = rng.random((c, n), dtype=np.float32)
+        idx = np.argpartition(keys, k - 1, axis=1)[:, :k] if k < n else np.tile(np.arange(n), (c, 1))
+        idx.sort(axis=1)
+        out[:, c0:c0 + c] = idx.T
+    return out
+
+
+def randsample_fixedNumberEntries(Xmixed: np.ndarray, small_p: int, rows: np.ndarray):
+    """Y = randsample_fixedNumberEntries(X, small_p) with the row sets `rows` (small_p, n):
+    keeps X(rows(:,j), j) / (small_p/p2); exact zeros are dropped as sparse() does
+    (private/randsample_fixedNumberEntries.m:30-31,62)."""
+    import scipy.sparse as sp
+    p2, n = Xmixed.shape
+    level = small_p / p2
+    cols = np.repeat(np.arange(n), small_p)
+    r = np.asarray(rows).T.reshape(-1)
+    vals = Xmixed[r, cols] / level
+    Y = sp.csc_matrix((vals, (r, cols)), shape=(p2, n))
+    Y.sum_duplicates()
+    Y.eliminate_zeros()
+    Y.sort_indices()
+    return Y
+
+
+def Arthur_initialization(ds: Dataset, K: int, gamma, rng=None, first=None, uniforms=None):
+    """k-means++ on the resident sparsified matrix (private/Arthur_initialization.m:24-69).
+
+    Each round folds the masked distance to the newest centre into a running minimum on the
+    GPU (identical values to the reference's recomputation against all chosen centres), then
+    samples the next index with probability proportional to the squared distance.  Returns the
+    chosen 0-based column indices."""
+    n = ds.n
+    rng = rng or np.random.default_rng()
+    it = iter(uniforms) if uniforms is not None else None
+
+    def draw():
+        return float(next(it)) if it is not None else float(rng.random())
+
+    chosen = [int(first) if first is not None else int(rng.integers(n))]           # :35
+    for _ in range(K - 1):
+        tot = ds.kpp_update(ds.get_column(chosen[-1]), gamma, first=(len(chosen) == 1))
+        if not (tot > 0):                                                          # :44-48 all-zero distances
+            pick = lambda: min(int(draw() * n), n - 1)                              # noqa: E731
+        else:
+            pick = lambda: ds.kpp_pick(draw() * tot)                                # noqa: E731
+        i = pick()
+        counter = 1
+        while i in chosen and counter < 400:                                       # :54-61
+            i = pick()
+            counter += 1
+        if i in chosen:
+            raise KMeansError("Cannot sample with replacement with this distribution")
+        chosen.append(i)
+    return np.asarray(chosen, dtype=np.int64)
+
+
+def kmeans_sparsified(X=None, K=None, **opts):
+    """See the module docstring.  Returns (IDX, C, SUMD, D, OUTPUT)."""
+    if X is None and K is None:                                                    # :120-125
+        print(f"Sparsified K-Means, Version {__version__:.1f}, June 1 2016")
+        return __version__
+    t0 = time.perf_counter()
+    unknown = set(opts) - set(_DEFAULTS) - set(_EXTRA)
+    if unknown:
+        raise KMeansError(f"'{sorted(unknown)[0]}' is not a recognized parameter", "MATLAB:InputParser:UnmatchedParameter")
+    o = {**_DEFAULTS, **_EXTRA, **opts}
+    if not (0 < o["SparsityLevel"] <= 1):
+        raise KMeansError("The value of 'SparsityLevel' is invalid", "MATLAB:InputParser:ArgumentFailedValidation")
+    if str(o["EmptyAction"]).lower() not in ("singleton", "error", "drop"):
+        raise KMeansError("The value of 'EmptyAction' is invalid", "MATLAB:InputParser:ArgumentFailedValidation")
+    if isinstance(X, str) or o["DataFile"]:
+        raise NotImplementedError("DataFile / load-from-disk (sampleAndMixFromLargeFile.m) is outside the hot path")
+    if not o["Sparsify"]:
+        raise NotImplementedError("Sparsify=false (dense K-means through pdist2) is outside the sparsified hot path")
+    if o["nargout"] > 5:
+        raise NotImplementedError("two-pass outputs (kmeans_sparsified.m:525-571) are outside the hot path")
+    import scipy.sparse as sp
+    rng = np.random.default_rng(o["Seed"])
+    ctx: Context = o["Context"] or default_context(int(o["Device"]))
+    OUTPUT = {"LoadFromDisk": False, "Options": {k: o[k] for k in _DEFAULTS}, "Sparsify": True}
+
+    Xd = np.asarray(X.todense() if sp.issparse(X) else X, dtype=np.float64)
+    if np.iscomplexobj(X):
+        raise KMeansError("Code and distance computations require real data")        # :311-313
+    if not o["ColumnSamples"]:
+        Xd = Xd.T                                                                     # :213-215
+    p, n = Xd.shape
+    K = int(K)
+    if n < K:
+        raise KMeansError("X must have more samples than the number of clusters.", "kmeans_sparsified:badDimensions")
+
+    # ---- sketch selection (:224-296) ----
+    sketch = o["SketchType"]
+    if isinstance(sketch, str) and sketch.lower() == "auto":
+        sketch = "Hadamard" if p == _nextpow2_size(p) else "DCT"
+        OUTPUT["SketchType"] = sketch
+    if not isinstance(sketch, str):
+        raise NotImplementedError("function-handle sketches are outside the hot path")
+    sk = sketch.lower()
+    p2 = p
+    if sk == "hadamard":
+        p2 = _nextpow2_size(p)
+        OUTPUT["SlowHadamard"] = False
+    elif sk == "dct":
+        raise NotImplementedError("SketchType 'DCT' (kmeans_sparsified.m:256-258) is not built yet; "
+                                  "pass SketchType='Hadamard' (rows are zero-padded to a power of two)")
+    elif sk not in ("nothing", "none"):
+        raise KMeansError('bad type for "SketchType"')
+    if sk == "hadamard":
+        d = o["Signs"]
+        if d is None:
+            d = np.ones(p2) if o["FORCE_BUG"] else np.sign(rng.standard_normal(p2))    # :283-287
+            d[d == 0] = 1.0
+        d = np.asarray(d, dtype=np.float64).reshape(-1)
+        if d.shape[0] != p2:
+            raise ValueError("Signs must have 2^nextpow2(p) entries")
+    else:
+        d = None
+    Xd = Xd * (1 + 2 * np.finfo(np.float64).eps)                                      # :281 / :292
+
+    def mix(A):                                                                       # :295
+        if d is None:
+            return np.asarray(A, dtype=np.float64)
+        A = np.asarray(A, dtype=np.float64)
+        Af = np.ascontiguousarray(A.T).reshape(-1)
+        out = np.empty(p2 * A.shape[1], dtype=np.float64)
+        from ._lib import SKM_F32, SKM_F64, check
+        check(ctx._lib.skm_mix_hadamard(ctx.handle, A.shape[0], p2, A.shape[1], Af.ctypes.data, d.ctypes.data,
+                                        SKM_F64 if o["MixDtype"] == "f64" else SKM_F32, out.ctypes.data))
+        return out.reshape(A.shape[1], p2).T
+
+    def unmix(C):                                                                     # :296
+        if d is None:
+            return C
+        Y = ops.hadamard(C, ctx) / math.sqrt(p2)
+        return (d.reshape(-1, 1) * Y)[:p, :]
+
+    t1 = time.perf_counter()
+    Xm = mix(Xd)
+    OUTPUT["TimeToSketch"] = time.perf_counter() - t1
+
+    small_p = max(1, matlab_round(o["SparsityLevel"] * p2))                           # :325-331
+    gamma = small_p / p
+    t1 = time.perf_counter()
+    rows = o["SampleRows"]
+    if rows is None:
+        rows = randsample_block(rng, p2, small_p, n)
+    Xs = randsample_fixedNumberEntries(Xm, small_p, np.asarray(rows))                 # :334
+    del Xm
+    OUTPUT["TimeToSample"] = time.perf_counter() - t1
+    display = str(o["Display"]).lower() if o["Display"] else "off"
+    if display in ("iter", "final"):
+        print(f"Randomly mixing of type {sketch}")
+        print("Randomly taking %.1f%% of the data; actual dataset is %.1f%% sparse"
+              % (100 * gamma, 100 * Xs.nnz / (Xs.shape[0] * Xs.shape[1])))
+
+    ds = Dataset.from_scipy(Xs, store=o["Store"], ctx=ctx)
+    ml = bool(o["MLcorrection"])
+    g_dist = gamma if o["unbiasedDistance"] else None                                 # :369-373
+    start = o["Start"]
+    R = int(o["Replicates"])
+    OUTPUT.update(iterations=np.zeros(R, dtype=np.int64), stoppingDiff=np.zeros(R), objectives=np.zeros(R),
+                  replicateTimes=np.zeros(R), replicateTimesJustInitialization=np.zeros(R))
+    best = dict(obj=math.inf)
+    distances = None
+    try:
+        for trial in range(R):
+            t1 = time.perf_counter()
+            centers_sparse = False
+            if isinstance(start, str):
+                s = start.lower()
+                if s == "sample":
+                    ind = rng.choice(n, size=K, replace=False) if o["StartIndices"] is None else np.asarray(o["StartIndices"])
+                    centers = np.asarray(Xs[:, ind].todense())
+                    centers_sparse = True
+                elif s == "uniform":
+                    mn, mx = float(Xs.min()), float(Xs.max())
+                    centers = (mx - mn) * rng.random((p2, K)) - mn                     # :390 (sign as in the reference)
+                elif s in ("arthur", "++", "kmeans++", "k-means++", "k-means-++"):
+                    if o["StartIndices"] is not None:
+                        ind = np.asarray(o["StartIndices"], dtype=np.int64)
+                    else:
+                        ind = Arthur_initialization(ds, K, gamma if o["unbiasedInitialization"] else None, rng)
+                    centers = np.asarray(Xs[:, ind].todense())
+                    centers_sparse = True
+                else:
+                    raise KMeansError('cannot handle other types of "Start" values')
+            else:
+                st = np.asarray(start, dtype=np.float64)
+                if not o["ColumnSamples"]:
+                    st = st.T
+                centers = mix(st)                                                     # :401-405
+                if R > 1:
+                    warnings.warn("initialization is specified, so running more than 1 replicate is not helpful")
+            if o["denseCenters"]:
+                centers_sparse = False                                                # :412-414
+            OUTPUT["replicateTimesJustInitialization"][trial] = time.perf_counter() - t1
+
+            Kt = K
+            L = Lloyd(ds, Kt)
+            L.set_centers(centers)
+            its = 0
+            dff = obj = math.nan
+            assignments = None
+            dropped_last = False
+            for its in range(1, int(o["MaxIter"]) + 1):
+                dropped_last = False
+                if centers_sparse:
+                    L.assign_sparse(g_dist)                                           # findClusterAssignments.m:63-75
+                else:
+                    L.assign(g_dist)                                                  # :420
+                L.accumulate()
+                stt = L.finalize(gamma, ml)                                           # :447-450
+                if stt.n_empty:
+                    action = str(o["EmptyAction"]).lower()
+                    warnings.warn("cluster has lost all its members")                 # :433
+                    counts = L.counts()
+                    empty = np.flatnonzero(counts == 0)
+                    if action == "singleton":                                         # :434-437
+                        _, imax = L.argmax_distance()
+                        col = ds.get_column(imax)
+                        for ki in empty:
+                            L.set_center_column(int(ki), col)
+                        stt2 = L.refresh_diff()
+                        stt.dff, stt.has_nan = stt2.dff, stt2.has_nan
+                    elif action == "error":
+                        raise KMeansError("One cluster lost all its members")
+                    else:                                                             # drop, :454-459
+                        keep = np.flatnonzero(counts > 0)
+                        cen = L.get_centers()[:, keep]
+                        old = L.get_centers_old()[:, keep]
+                        _, distances = L.assignments()
+                        L.close()
+                        Kt = keep.size
+                        L = Lloyd(ds, Kt)
+                        L.set_centers(cen)
+                        assignments = np.zeros(0, dtype=np.int32)                     # :457 assignments = []
+                        dropped_last = True
+                        stt.dff = float(np.linalg.norm(old - cen, "fro"))
+                        stt.has_nan = bool(np.isnan(cen).any())
+                if centers_sparse:                                                    # :460-464
+                    cen = L.get_centers()
+                    if np.count_nonzero(cen) / cen.size > 0.99:
+                        centers_sparse = False
+                dff, obj = stt.dff, stt.objective                                     # :470-471
+                if display == "iter" and its % int(o["PrintEvery"]) == 0:
+                    print("Iter: %3d; change in cluster centers: %.2e; objective: %.2e" % (its, dff, obj))
+                if dff < o["Tol"]:                                                    # :476-478
+                    break
+                if stt.has_nan:
+                    raise KMeansError("Found NaN in centers")                         # :480-484
+            if not dropped_last:
+                assignments, distances = L.assignments()
+            OUTPUT["replicateTimes"][trial] = time.perf_counter() - t1
+            OUTPUT["stoppingDiff"][trial] = dff
+            OUTPUT["objectives"][trial] = obj
+            OUTPUT["iterations"][trial] = its
+            is_best = obj < best["obj"]
+            if is_best:                                                               # :493-503
+                best = dict(obj=obj, assignments=assignments, distances=distances, centers=L.get_centers(), K=Kt)
+            if display == "iter" or (display == "final" and is_best):
+                tail = " (this is the best trial so far)" if is_best else " (best so far was %.2e)" % best["obj"]
+                print("Trial %3d of %3d total, objective %.2e%s" % (trial + 1, R, obj, tail))
+            L.close()
+    finally:
+        ds.close()
+    if "assignments" not in best:
+        raise KMeansError("no replicate produced a finite objective")
+    OUTPUT["TimeInitialization"] = float(np.sum(OUTPUT["replicateTimesJustInitialization"]))
+    OUTPUT["TimeAlgo_wo_initialization"] = float(np.sum(OUTPUT["replicateTimes"])) - OUTPUT["TimeInitialization"]
+
+    # SUMD uses the LAST trial's distances with the best assignments, as the reference does (:514-518)
+    Kb = best["K"]
+    SUMD = np.zeros(Kb)
+    if best["assignments"].size:
+        for ki in range(Kb):
+            SUMD[ki] = np.sum(distances[best["assignments"] == ki + 1] ** 2)
+    OUTPUT["TimeOverall_OnePass"] = time.perf_counter() - t0
+    C = unmix(best["centers"])                                                        # :523
+    IDX, D = best["assignments"], best["distances"]
+    if not o["ColumnSamples"]:                                                        # :586-591
+        C = C.T
+    OUTPUT["TimeOverall"] = time.perf_counter() - t0
+    return IDX, C, SUMD, D, OUTPUT
