@@ -187,6 +187,11 @@ extern "C" void skm_dataset_destroy(skm_dataset *ds)
     cudaFree(ds->slice_ptr);
     cudaFree(ds->kpp_mind);
     cudaFree(ds->kpp_cum);
+    cudaFree(ds->csr);
+    cudaFree(ds->rowptr);
+    cudaFree(ds->unit_row);
+    cudaFree(ds->unit_start);
+    free(ds->h_rowptr);
     delete ds;
 }
 
@@ -197,7 +202,10 @@ static int dataset_finish(skm_dataset *ds)
     SKM_TRY(skm_validate_csc(ctx, ds->p, ds->n, ds->nnz, ds->colptr, ds->rowidx, &ds->max_col_nnz));
     ds->device_bytes = (int64_t)sizeof(int64_t) * (ds->n + 1) + (int64_t)sizeof(int32_t) * ds->nnz +
                        (int64_t)type_size(ds->store_dtype) * ds->nnz;
-    if (ds->store_dtype == SKM_F32) SKM_TRY(skm_build_sell(ds));
+    if (ds->store_dtype == SKM_F32) {
+        SKM_TRY(skm_build_sell(ds));
+        SKM_TRY(skm_build_csr(ds));
+    }
     return SKM_OK;
 }
 
@@ -341,6 +349,7 @@ extern "C" void skm_lloyd_destroy(skm_lloyd *L)
     cudaSetDevice(L->ds->ctx->device);
     cudaStreamSynchronize(L->ds->ctx->stream);
     cudaFree(L->centers); cudaFree(L->centers_old); cudaFree(L->cscaled_t); cudaFree(L->table);
+    cudaFree(L->assign_c);
     cudaFree(L->cmax); cudaFree(L->assign); cudaFree(L->dist_f32); cudaFree(L->dist_f64);
     cudaFree(L->best2); cudaFree(L->flagged); cudaFree(L->nflag); cudaFree(L->partials);
     cudaFree(L->stats);
@@ -373,6 +382,7 @@ static int skm_lloyd_create_ex(skm_dataset *ds, int64_t K, int want_f64_dist, sk
         if ((rc = dev_alloc((void **)&L->centers_old, sizeof(double) * p * K, "centers_old"))) break;
         if ((rc = dev_alloc((void **)&L->cscaled_t, sizeof(double) * (p + 1) * K, "cscaled"))) break;
         if ((rc = dev_alloc((void **)&L->assign, sizeof(int32_t) * n, "assign"))) break;
+        if ((rc = dev_alloc(&L->assign_c, sizeof(int32_t) * n, "assign_c"))) break;
         if ((rc = dev_alloc((void **)&L->partials, sizeof(double) * (2 * p * K + K + 1), "partials"))) break;
         if ((rc = dev_alloc((void **)&L->stats, sizeof(double) * 8, "stats"))) break;
         if ((rc = dev_alloc((void **)&L->nflag, sizeof(int) * 4, "nflag"))) break;
@@ -480,7 +490,7 @@ extern "C" int skm_lloyd_accumulate(skm_lloyd *L)
     SKM_TRY(enter(L->ds->ctx));
     if (!L->assigned) { skm_set_error("skm_lloyd_accumulate called before skm_lloyd_assign"); return SKM_ERR_STATE; }
     SkmTimed t(L->ds->ctx, SKM_T_ACCUM);
-    SKM_TRY(skm_launch_accumulate(L->ds->ctx, L->ds, L->K, L->assign, L->dist_f32, L->dist_is_f64 ? L->dist_f64 : nullptr, L->partials));
+    SKM_TRY(skm_launch_accumulate(L->ds->ctx, L->ds, L->K, L->assign, L->assign_c, L->dist_f32, L->dist_is_f64 ? L->dist_f64 : nullptr, L->partials));
     L->accumulated = true;
     return SKM_OK;
 }

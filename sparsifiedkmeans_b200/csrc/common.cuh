@@ -117,6 +117,14 @@ struct skm_dataset {
     int64_t  nslices, sell_elems;       // sell_elems in int4 units
     bool     uniform_width;             // every slice has the same width
     int      sell_width2;               // pairs per column if uniform_width
+    // row-major image for K2 (SKM_F32 only, see csr.cu): (column, value bits) pairs per row
+    int2    *csr;
+    int64_t *rowptr;                    // [p+1] device
+    int64_t *h_rowptr;                  // [p+1] host copy
+    // K2 work list: unit u covers csr[unit_start[u] .. unit_start[u+1]) of row unit_row[u]
+    int32_t *unit_row;
+    int64_t *unit_start;                // [2*nunits]: starts then ends; a unit never crosses a row
+    int64_t  nunits;
     // k-means++ running minimum distance (allocated on first use)
     double  *kpp_mind;                  // [n]
     double  *kpp_cum;                   // [n] inclusive scan of mind^2
@@ -132,6 +140,7 @@ struct skm_lloyd {
     float   *table;          // fast-path table, fp32, row-major with padded stride
     float   *cmax;           // [1] max |c'|
     int32_t *assign;         // [n] 0-based
+    void    *assign_c;       // [n] compact copy for K2's gather (uint8 if K<=256 else uint16/int32)
     float   *dist_f32;       // [n] (SKM_F32 datasets)
     double  *dist_f64;       // [n] (SKM_F64 datasets, and rechecked columns mirror)
     float   *best2;          // [2n] running best/second-best for K-chunked launches
@@ -156,6 +165,7 @@ int skm_launch_convert_value(skm_ctx *ctx, const void *src, int src_type, int64_
 int skm_validate_csc(skm_ctx *ctx, int64_t p, int64_t n, int64_t nnz, const int64_t *colptr,
                      const int32_t *rowidx, int64_t *max_col_nnz);
 int skm_build_sell(skm_dataset *ds);
+int skm_build_csr(skm_dataset *ds);      // csr.cu
 
 // exact.cu
 struct ExactArgs {
@@ -196,7 +206,7 @@ int  skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, cons
 
 // update.cu
 int skm_launch_accumulate(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const int32_t *assign,
-                          const float *dist32, const double *dist64, double *partials);
+                          void *assign_c, const float *dist32, const double *dist64, double *partials);
 int skm_launch_finalize(skm_ctx *ctx, int64_t p, int64_t K, const double *partials, double gamma,
                         int ml_correction, double *centers, double *centers_old, double *stats);
 int skm_launch_argmax(skm_ctx *ctx, int64_t n, const float *dist32, const double *dist64,

@@ -1,6 +1,7 @@
 // convert.cu -- upload-time conversions: index/value narrowing, CSC validation and the
 // SELL-32 image the fast assignment kernel streams (layout described in common.cuh).
 #include "common.cuh"
+#include <stdlib.h>
 #include <vector>
 
 namespace {
@@ -98,6 +99,97 @@ __global__ void k_fill_sell(int64_t p, int64_t n, int64_t nslices, const int64_t
         if (t + 1 < b) { q.z = rowidx[t + 1]; q.w = __float_as_int((float)val[t + 1]); }
         else           { q.z = pad_row;       q.w = 0; }
         sell[base + (int64_t)t2 * 32 + lane] = q;
+    }
+}
+
+
+// Bank-aware variant of k_fill_sell.  The fast kernel gathers one 16-byte chunk of a centroid
+// row per lane per LDS.128; the hardware serves a quarter-warp (8 lanes) per wavefront when the
+// 8 chunks fall in 8 different 16-byte bank groups.  With an odd number of chunks per table
+// row the bank group of a chunk is a bijection of (row mod 8), so the order in which a column's
+// entries are visited decides the conflicts (measured 2.46 wavefronts per quarter-warp in
+// stored order, profiles/r1_a_first_path.md).  The order is free -- the fast kernel's guard
+// bound does not depend on it and the fp64 re-evaluation reads the CSC copy -- so each slice
+// is scheduled greedily here: at every step the 8 lanes of a quarter pick, in rotating order,
+// the residue class (row mod 8) with the most remaining entries among the classes no lane of
+// the quarter has taken yet.
+template <typename VT>
+__global__ void k_fill_sell_banked(int64_t p, int64_t n, int64_t nslices, int wmax,
+                                   const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
+                                   const VT *__restrict__ val, const int64_t *__restrict__ slice_ptr,
+                                   int4 *__restrict__ sell)
+{
+    extern __shared__ unsigned short s_all[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (warp >= nslices) return;
+    unsigned short *ord = s_all + (size_t)wib * wmax * 32;        // [t][lane]: entry ids sorted by class
+    const int64_t j = warp * SKM_SLICE + lane;
+    int64_t a = 0, b = 0;
+    if (j < n) { a = colptr[j]; b = colptr[j + 1]; }
+    const int len = (int)(b - a);
+    const int64_t base = slice_ptr[warp];
+    const int w2 = (int)((slice_ptr[warp + 1] - base) >> 5);
+    const int pad_row = (int)p;
+
+    // counting sort of this lane's entries by (row & 7)
+    int cnt[8], start[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) cnt[c] = 0;
+    for (int t = 0; t < len; ++t) {
+        const int c = rowidx[a + t] & 7;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) cnt[q] += (q == c);
+    }
+    int run = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { start[c] = run; run += cnt[c]; }
+    {
+        int fill[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) fill[c] = start[c];
+        for (int t = 0; t < len; ++t) {
+            const int c = rowidx[a + t] & 7;
+            int pos = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { if (q == c) { pos = fill[q]; fill[q] = pos + 1; } }
+            ord[pos * 32 + lane] = (unsigned short)t;
+        }
+    }
+    __syncwarp();
+
+    int rem = len;
+    int4 q4 = make_int4(pad_row, 0, pad_row, 0);
+    const int qbase = lane & ~7, me = lane & 7;
+    for (int step = 0; step < 2 * w2; ++step) {
+        unsigned load = 0;                       // 4-bit load per class, shared by the quarter
+        int pick = -1;
+        for (int i = 0; i < 8; ++i) {
+            const int chooser = (step + i) & 7;
+            if (me == chooser && rem > 0) {
+                int best = -2147483647 - 1, bestc = 0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int l = (load >> (4 * c)) & 15;
+                    const int sc = (l == 0 ? (1 << 20) : 0) - l * 1024 + cnt[c];
+                    if (cnt[c] > 0 && sc > best) { best = sc; bestc = c; }
+                }
+                int pos = 0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { if (c == bestc) { pos = start[c]; start[c] = pos + 1; cnt[c] -= 1; } }
+                pick = ord[pos * 32 + lane];
+                rem -= 1;
+                const unsigned l = (load >> (4 * bestc)) & 15;
+                if (l < 15) load += 1u << (4 * bestc);
+            }
+            load = __shfl_sync(0xffffffffu, load, qbase | chooser);
+        }
+        int r = pad_row, xb = 0;
+        if (pick >= 0) { r = rowidx[a + pick]; xb = __float_as_int((float)val[a + pick]); }
+        if (step & 1) {
+            q4.z = r; q4.w = xb;
+            sell[base + (int64_t)(step >> 1) * 32 + lane] = q4;
+        } else { q4.x = r; q4.y = xb; q4.z = pad_row; q4.w = 0; }
     }
 }
 
@@ -205,7 +297,19 @@ int skm_build_sell(skm_dataset *ds)
     if (e != cudaSuccess) { skm_set_error("cudaMalloc(sell, %zu bytes) failed: %s", sell_bytes, cudaGetErrorString(e)); return SKM_ERR_NOMEM; }
     ds->sell = (int4 *)d;
     ds->device_bytes += (int64_t)sell_bytes + (int64_t)sizeof(int64_t) * (nslices + 1);
-    if (ds->sell_elems > 0) {
+    int wmax = 0;
+    for (int64_t s2 = 0; s2 < nslices; ++s2) wmax = hw[s2] * 2 > wmax ? hw[s2] * 2 : wmax;
+    const bool banked = ds->sell_elems > 0 && ds->store_dtype == SKM_F32 && wmax > 0 && wmax <= 1024 && !getenv("SKM_NO_BANKED");
+    if (banked) {
+        int warps = 8;
+        while (warps > 1 && (size_t)warps * wmax * 64 > (size_t)ctx->smem_optin - 1024) warps >>= 1;
+        const size_t smem = (size_t)warps * wmax * 64;
+        SKM_CUDA(cudaFuncSetAttribute(k_fill_sell_banked<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int64_t blocks = (nslices + warps - 1) / warps;
+        k_fill_sell_banked<float><<<(unsigned)blocks, warps * 32, smem, ctx->stream>>>(
+            ds->p, n, nslices, wmax, ds->colptr, ds->rowidx, (const float *)ds->val, ds->slice_ptr, ds->sell);
+        SKM_CHECK_LAUNCH(ctx);
+    } else if (ds->sell_elems > 0) {
         int64_t blocks = (nslices * 32 + 255) / 256;
         if (ds->store_dtype == SKM_F32)
             k_fill_sell<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>(

@@ -47,6 +47,101 @@ __global__ void k_accumulate_csc(int64_t p, int64_t n, int64_t K, const int64_t 
     }
 }
 
+
+// members per cluster, sum of squared distances, and the compact copy of the assignments that
+// K2's row-major pass gathers from (1 byte per column when K <= 256).
+template <typename AT>
+__global__ void k_count_sumsq(int64_t n, int64_t K, const int32_t *__restrict__ assign,
+                              const float *__restrict__ dist32, const double *__restrict__ dist64,
+                              AT *__restrict__ assign_c, double *__restrict__ counts, double *__restrict__ sumsq)
+{
+    extern __shared__ int hist[];
+    for (int k = threadIdx.x; k < K; k += blockDim.x) hist[k] = 0;
+    __syncthreads();
+    double local = 0.0;
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; j < n; j += stride) {
+        const int a = assign[j];
+        assign_c[j] = (AT)a;
+        if (a >= 0 && a < K) {
+            atomicAdd(&hist[a], 1);
+            const double d = dist64 ? dist64[j] : (double)dist32[j];
+            local += d * d;
+        }
+    }
+    __shared__ double red[32];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x)
+        if (hist[k]) atomicAdd(&counts[k], (double)hist[k]);
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+        if (s != 0.0 || s != s) atomicAdd(sumsq, s);
+    }
+}
+
+// K2 over the row-major image: one warp per work unit (a run of one row's entries).  Every lane
+// owns a private column of bins [cluster][lane] in shared memory (fp64 sums, int counts), so
+// the read-modify-writes are conflict-free and need no atomics; the bins are folded across
+// lanes with a rotated read (also conflict-free) and leave the SM as one fp64 atomic per
+// (row, cluster, unit).
+template <typename AT>
+__global__ void k_accumulate_csr(int64_t p, int k0, int kb, int64_t nunits,
+                                 const int32_t *__restrict__ unit_row, const int64_t *__restrict__ unit_start,
+                                 const int2 *__restrict__ csr, const AT *__restrict__ assign_c,
+                                 double *__restrict__ S, double *__restrict__ N)
+{
+    extern __shared__ __align__(16) unsigned char acc_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double *binS = reinterpret_cast<double *>(acc_raw) + (size_t)warp * kb * 32;
+    int *binN = reinterpret_cast<int *>(reinterpret_cast<double *>(acc_raw) + (size_t)nw * kb * 32) + (size_t)warp * kb * 32;
+    const int64_t *unit_end = unit_start + nunits;
+    int64_t u = (int64_t)blockIdx.x * nw + warp;
+    const int64_t ustride = (int64_t)gridDim.x * nw;
+    for (; u < nunits; u += ustride) {
+        for (int k = 0; k < kb; ++k) { binS[k * 32 + lane] = 0.0; binN[k * 32 + lane] = 0; }
+        const int64_t r = unit_row[u], s = unit_start[u], e = unit_end[u];
+        int64_t i = s + lane;
+        for (; i + 96 < e; i += 128) {
+            const int2 q0 = __ldcs(csr + i), q1 = __ldcs(csr + i + 32), q2 = __ldcs(csr + i + 64), q3 = __ldcs(csr + i + 96);
+            const int a0 = (int)__ldg(assign_c + q0.x) - k0, a1 = (int)__ldg(assign_c + q1.x) - k0;
+            const int a2 = (int)__ldg(assign_c + q2.x) - k0, a3 = (int)__ldg(assign_c + q3.x) - k0;
+            if ((unsigned)a0 < (unsigned)kb) { binS[a0 * 32 + lane] += (double)__int_as_float(q0.y); binN[a0 * 32 + lane] += 1; }
+            if ((unsigned)a1 < (unsigned)kb) { binS[a1 * 32 + lane] += (double)__int_as_float(q1.y); binN[a1 * 32 + lane] += 1; }
+            if ((unsigned)a2 < (unsigned)kb) { binS[a2 * 32 + lane] += (double)__int_as_float(q2.y); binN[a2 * 32 + lane] += 1; }
+            if ((unsigned)a3 < (unsigned)kb) { binS[a3 * 32 + lane] += (double)__int_as_float(q3.y); binN[a3 * 32 + lane] += 1; }
+        }
+        for (; i < e; i += 32) {
+            const int2 q = __ldcs(csr + i);
+            const int a = (int)__ldg(assign_c + q.x) - k0;
+            if ((unsigned)a < (unsigned)kb) { binS[a * 32 + lane] += (double)__int_as_float(q.y); binN[a * 32 + lane] += 1; }
+        }
+        __syncwarp();
+        for (int kblk = 0; kblk < kb; kblk += 32) {
+            const int k = kblk + lane;
+            double sum = 0.0;
+            int cnt = 0;
+            if (k < kb) {
+#pragma unroll 8
+                for (int t = 0; t < 32; ++t) {
+                    const int idx = k * 32 + ((t + lane) & 31);
+                    sum += binS[idx];
+                    cnt += binN[idx];
+                }
+                if (cnt) {
+                    atomicAdd(&S[(int64_t)(k0 + k) * p + r], sum);
+                    atomicAdd(&N[(int64_t)(k0 + k) * p + r], (double)cnt);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // stats[0] += sum (old-new)^2 ; stats[1] = 1 if any NaN in new centres
 __global__ void k_finalize(int64_t p, int64_t K, const double *__restrict__ partials, double gamma,
                            int ml, double *__restrict__ centers, double *__restrict__ centers_old,
@@ -166,12 +261,57 @@ __global__ void k_argmax_final(int nb, const double *__restrict__ bval, const in
 
 }  // namespace
 
-int skm_launch_accumulate(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const int32_t *assign,
+template <typename AT>
+static int accumulate_csr(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const int32_t *assign, void *assign_c,
+                          const float *dist32, const double *dist64, double *partials)
+{
+    const int64_t p = ds->p, n = ds->n;
+    double *S = partials, *N = partials + p * K, *counts = partials + 2 * p * K, *sumsq = counts + K;
+    {
+        int64_t blocks = (n + 255) / 256;
+        const int64_t cap = (int64_t)ctx->sm_count * 8;
+        if (blocks > cap) blocks = cap;
+        const size_t sm = sizeof(int) * (size_t)K;
+        if (sm > 48 * 1024) SKM_CUDA(cudaFuncSetAttribute(k_count_sumsq<AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k_count_sumsq<AT><<<(unsigned)blocks, 256, sm, ctx->stream>>>(n, K, assign, dist32, dist64, (AT *)assign_c, counts, sumsq);
+        SKM_CHECK_LAUNCH(ctx);
+    }
+    // bins: 12 bytes x 32 lanes per cluster per warp
+    const size_t budget = (size_t)ctx->smem_optin - 2048;
+    int warps = 8;
+    while (warps > 1 && (size_t)warps * 384 * (size_t)(K < 32 ? K : 32) > budget) warps >>= 1;
+    int64_t kb = (int64_t)(budget / ((size_t)warps * 384));
+    if (kb > K) kb = K;
+    // prefer several resident blocks when the bins are small
+    const size_t smem = (size_t)warps * kb * 384;
+    auto kern = k_accumulate_csr<AT>;
+    SKM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    SKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    int64_t blocks = (int64_t)ctx->sm_count * per_sm;
+    const int64_t need = (ds->nunits + warps - 1) / warps;
+    if (blocks > need) blocks = need;
+    for (int64_t k0 = 0; k0 < K; k0 += kb) {
+        const int kbb = (int)((K - k0) < kb ? (K - k0) : kb);
+        kern<<<(unsigned)blocks, warps * 32, smem, ctx->stream>>>(p, (int)k0, kbb, ds->nunits, ds->unit_row, ds->unit_start,
+                                                               ds->csr, (const AT *)assign_c, S, N);
+        SKM_CHECK_LAUNCH(ctx);
+    }
+    return SKM_OK;
+}
+
+int skm_launch_accumulate(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const int32_t *assign, void *assign_c,
                           const float *dist32, const double *dist64, double *partials)
 {
     const int64_t p = ds->p, n = ds->n;
     SKM_CUDA(cudaMemsetAsync(partials, 0, sizeof(double) * (size_t)(2 * p * K + K + 1), ctx->stream));
     if (n == 0) return SKM_OK;
+    if (ds->csr && ds->nunits > 0 && assign_c) {
+        if (K <= 256) return accumulate_csr<uint8_t>(ctx, ds, K, assign, assign_c, dist32, dist64, partials);
+        if (K <= 65536) return accumulate_csr<uint16_t>(ctx, ds, K, assign, assign_c, dist32, dist64, partials);
+        return accumulate_csr<int32_t>(ctx, ds, K, assign, assign_c, dist32, dist64, partials);
+    }
     int64_t blocks = (n * 32 + 255) / 256;
     int64_t cap = (int64_t)ctx->sm_count * 8;
     if (blocks > cap) blocks = cap;
