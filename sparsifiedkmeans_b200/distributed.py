@@ -1,0 +1,157 @@
+"""Column-sharded Lloyd iteration: one process per GPU, one all-reduce per iteration.
+
+The reference is single-process; the path shards naturally because points (columns) are
+independent in K1 and K2 needs exactly one exchange: the sum over ranks of
+[S (p*K) | N (p*K) | counts (K) | sumsq (1)].  After the all-reduce every
+rank holds identical partials, runs K3 identically, and the centres never drift apart.
+
+`ShardedLloyd` is written against a small engine protocol so the host logic can be exercised
+on CPU with the gloo backend (tests/test_distributed_gloo.py drives it with an oracle-backed
+engine); in production the engine is `CudaShardEngine` (libskm_b200 on this rank's GPU) and the
+collective is NCCL over NVLink on the library's own stream.
+
+Engine protocol (all indices local to the shard):
+    n_local, p, K
+    set_centers(C), get_centers() -> C
+    assign(gamma_dist)                       K1 on the local columns
+    accumulate() -> partials                 K2; returns the tensor to all-reduce (in place)
+    finalize(gamma, ml) -> IterStats         K3 from the (reduced) partials
+    refresh_diff() -> IterStats
+    counts() -> int64[K]                      global member counts after finalize
+    argmax_distance() -> (value, local j)
+    get_column(j) -> dense p-vector
+    set_center_column(k, col)
+    assignments() -> (1-based int32[n_local], float64[n_local])
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous column block [lo, hi) of `rank` (GPU g owns columns [g*n/G, (g+1)*n/G))."""
+    return n * rank // world, n * (rank + 1) // world
+
+
+class CudaShardEngine:
+    """libskm_b200 on this rank's GPU."""
+
+    def __init__(self, ds, K: int):
+        from .engine import Lloyd
+        self.ds = ds
+        self.L = Lloyd(ds, K)
+        self.n_local, self.p, self.K = ds.n, ds.p, int(K)
+        self._ext = None
+
+    def stream(self):
+        """torch view of the library's stream, so the collective is ordered after K2."""
+        import torch
+        if self._ext is None:
+            self._ext = torch.cuda.ExternalStream(self.ds.ctx.stream, device=f"cuda:{self.ds.ctx.device}")
+        return self._ext
+
+    def set_centers(self, C): self.L.set_centers(C)
+    def get_centers(self): return self.L.get_centers()
+    def assign(self, gamma_dist): self.L.assign(gamma_dist)
+    def finalize(self, gamma, ml): return self.L.finalize(gamma, ml)
+    def refresh_diff(self): return self.L.refresh_diff()
+    def counts(self): return self.L.counts()
+    def argmax_distance(self): return self.L.argmax_distance()
+    def get_column(self, j): return self.ds.get_column(j)
+    def set_center_column(self, k, col): self.L.set_center_column(k, col)
+    def assignments(self): return self.L.assignments()
+
+    def accumulate(self):
+        self.L.accumulate()
+        return self.L.partials_tensor()
+
+    def close(self):
+        self.L.close()
+
+
+class ShardedLloyd:
+    """The Lloyd loop of kmeans_sparsified.m:417-486 over column shards."""
+
+    def __init__(self, engine, group=None):
+        self.e = engine
+        self.group = group
+
+    # -- collectives ---------------------------------------------------------
+    def _dist(self):
+        import torch.distributed as dist
+        return dist if dist.is_available() and dist.is_initialized() else None
+
+    def _allreduce(self, t):
+        dist = self._dist()
+        if dist is None or dist.get_world_size(self.group) == 1:
+            return
+        stream = self.e.stream() if hasattr(self.e, "stream") else None
+        if stream is not None:
+            import torch
+            with torch.cuda.stream(stream):
+                dist.all_reduce(t, group=self.group)
+        else:
+            dist.all_reduce(t, group=self.group)
+
+    def _gather_objects(self, obj):
+        dist = self._dist()
+        if dist is None or dist.get_world_size(self.group) == 1:
+            return [obj]
+        out = [None] * dist.get_world_size(self.group)
+        dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def _bcast_object(self, obj, src):
+        dist = self._dist()
+        if dist is None or dist.get_world_size(self.group) == 1:
+            return obj
+        box = [obj]
+        dist.broadcast_object_list(box, src=src, group=self.group)
+        return box[0]
+
+    # -- one iteration ---------------------------------------------------------
+    def step(self, gamma_dist, gamma_update, ml_correction=True, empty_action="singleton"):
+        """K1, K2, all-reduce, K3, then the reference's EmptyAction (kmeans_sparsified.m:432-445).
+        Returns the IterStats of the iteration (identical on every rank)."""
+        e = self.e
+        e.assign(gamma_dist)
+        part = e.accumulate()
+        self._allreduce(part)
+        st = e.finalize(gamma_update, ml_correction)
+        if st.n_empty:
+            action = str(empty_action).lower()
+            if action == "error":
+                raise RuntimeError("One cluster lost all its members")
+            if action == "singleton":
+                # global first-occurrence arg-max of the distances: ranks own ascending column
+                # blocks, so the lowest rank wins ties, then the lowest local index
+                v, j = e.argmax_distance() if e.n_local else (-np.inf, -1)
+                cands = self._gather_objects((float(v), int(j)))
+                owner, best = 0, -np.inf
+                for r, (cv, cj) in enumerate(cands):
+                    if cj >= 0 and (cv > best or (np.isnan(best) and not np.isnan(cv))):
+                        owner, best = r, cv
+                dist = self._dist()
+                me = dist.get_rank(self.group) if dist is not None else 0
+                col = e.get_column(cands[owner][1]) if me == owner else None
+                col = self._bcast_object(col, owner)
+                for k in np.flatnonzero(e.counts() == 0):
+                    e.set_center_column(int(k), col)
+                st2 = e.refresh_diff()
+                st.dff, st.has_nan = st2.dff, st2.has_nan
+            elif action != "drop":
+                raise ValueError("invalid EmptyAction choice")
+        return st
+
+    def run(self, centers, gamma_dist, gamma_update, max_iter=100, tol=1e-6, ml_correction=True,
+            empty_action="singleton"):
+        """Iterate to convergence; returns (iterations, last IterStats)."""
+        self.e.set_centers(centers)
+        st, its = None, 0
+        for its in range(1, max_iter + 1):
+            st = self.step(gamma_dist, gamma_update, ml_correction, empty_action)
+            if st.dff < tol:
+                break
+            if st.has_nan:
+                raise RuntimeError("Found NaN in centers")
+        return its, st

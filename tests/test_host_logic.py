@@ -1,0 +1,61 @@
+"""Host-side logic of the kmeans_sparsified mirror that needs no GPU.  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import host_ref
+from sparsifiedkmeans_b200 import kmeans as km
+from sparsifiedkmeans_b200.distributed import shard_bounds
+
+
+def test_matlab_round_is_half_away_from_zero():
+    assert [km.matlab_round(v) for v in (0.5, 1.5, 2.5, -0.5, -2.5, 2.4999)] == [1, 2, 3, -1, -3, 2]
+    assert km.matlab_round(0.05 * 1024) == 51 and km.matlab_round(0.1 * 784) == 78
+    assert km.matlab_round(0.05 * 50) == 3                                            # Python's round() gives 2
+
+
+def test_randsample_block_contract():
+    rng = np.random.default_rng(0)
+    rows = km.randsample_block(rng, 64, 5, 2000)        # randsample_block.m: k distinct indices per column
+    assert rows.shape == (5, 2000) and rows.min() >= 0 and rows.max() < 64
+    assert np.all(np.diff(rows, axis=0) > 0)            # distinct and sorted
+    freq = np.bincount(rows.ravel(), minlength=64) / (5 * 2000)
+    assert abs(freq.max() - 1 / 64) < 0.006 and abs(freq.min() - 1 / 64) < 0.006       # uniform
+
+
+def test_randsample_fixed_entries_matches_oracle():
+    rng = np.random.default_rng(1)
+    Xm = rng.standard_normal((32, 50))
+    Xm[3, 7] = 0.0                                       # exact zero must be dropped by sparse()
+    rows = km.randsample_block(rng, 32, 4, 50)
+    rows[0, 7] = 3 if 3 not in rows[1:, 7] else rows[0, 7]
+    Y = km.randsample_fixedNumberEntries(Xm, 4, rows)
+    W = host_ref.sample_fixed_entries(Xm, rows)
+    assert (Y != W).nnz == 0
+    assert np.all(np.diff(Y.indptr) <= 4)
+    j = 0
+    np.testing.assert_array_equal(Y[:, j].data, Xm[rows[:, j], j] / (4 / 32))          # randsample_fixedNumberEntries.m:30-31
+
+
+def test_option_validation_mirrors_input_parser():
+    X = np.zeros((10, 4))
+    with pytest.raises(km.KMeansError):
+        km.kmeans_sparsified(X, 2, Sparsify=True, NoSuchOption=1)
+    with pytest.raises(km.KMeansError):
+        km.kmeans_sparsified(X, 2, Sparsify=True, SparsityLevel=0.0)
+    with pytest.raises(km.KMeansError):
+        km.kmeans_sparsified(X, 2, Sparsify=True, EmptyAction="explode")
+    with pytest.raises(NotImplementedError):
+        km.kmeans_sparsified(X, 2)                       # dense path is out of scope
+    with pytest.raises(NotImplementedError):
+        km.kmeans_sparsified("data.mat", 2, Sparsify=True)
+    assert km.kmeans_sparsified() == 2.1
+
+
+def test_shard_bounds_cover_all_columns():
+    for n in (0, 1, 7, 1000, 10**8):
+        for world in (1, 2, 3, 8):
+            b = [shard_bounds(n, world, r) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
