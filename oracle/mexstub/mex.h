@@ -28,7 +28,7 @@ typedef ptrdiff_t mwSignedIndex;
 
 typedef enum { mxREAL = 0, mxCOMPLEX = 1 } mxComplexity;
 typedef enum {
-    mxUNKNOWN_CLASS = 0, mxDOUBLE_CLASS = 6, mxSINGLE_CLASS = 7,
+    mxUNKNOWN_CLASS = 0, mxCHAR_CLASS = 4, mxDOUBLE_CLASS = 6, mxSINGLE_CLASS = 7,
     mxINT32_CLASS = 12, mxUINT64_CLASS = 15
 } mxClassID;
 
@@ -57,6 +57,8 @@ int      mxIsSingle(const mxArray *a);
 int      mxIsEmpty(const mxArray *a);
 mwSize   mxGetNumberOfElements(const mxArray *a);
 double   mxGetScalar(const mxArray *a);
+int      mxIsChar(const mxArray *a);
+char    *mxArrayToString(const mxArray *a);   /* stub char arrays hold one byte per character */
 mxArray *mxCreateDoubleMatrix(mwSize m, mwSize n, mxComplexity c);
 mxArray *mxCreateNumericMatrix(mwSize m, mwSize n, mxClassID cls, mxComplexity c);
 mxArray *mxCreateDoubleScalar(double v);

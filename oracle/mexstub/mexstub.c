@@ -1,6 +1,6 @@
 /*
  * Stub MEX runtime -- TEST INFRASTRUCTURE ONLY (oracle/).  See mex.h here.
- * Linked into every oracle/_ref/*.so and into the test build of mex/ shims.
+ * Linked into every library under oracle/_ref and into the test build of the mex/ shims.
  */
 #include "mex.h"
 #include <setjmp.h>
@@ -28,9 +28,19 @@ int mxIsSingle(const mxArray *a) { return a->classid == mxSINGLE_CLASS; }
 mwSize mxGetNumberOfElements(const mxArray *a) { return a->m * a->n; }
 int mxIsEmpty(const mxArray *a) { return a->m == 0 || a->n == 0; }
 double mxGetScalar(const mxArray *a) { return ((double *)a->pr)[0]; }
+int mxIsChar(const mxArray *a) { return a->classid == mxCHAR_CLASS; }
+char *mxArrayToString(const mxArray *a) {
+    size_t n = a->m * a->n;
+    char *s = (char *)malloc(n + 1);
+    if (a->classid != mxCHAR_CLASS) { free(s); return NULL; }
+    memcpy(s, a->pr, n);
+    s[n] = 0;
+    return s;
+}
 
 static size_t class_size(mxClassID c) {
     switch (c) {
+        case mxCHAR_CLASS: return 1;
         case mxDOUBLE_CLASS: return 8;
         case mxSINGLE_CLASS: return 4;
         case mxINT32_CLASS: return 4;

@@ -20,6 +20,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(_HERE, "_ref")
 
+mxCHAR_CLASS = 4
 mxDOUBLE_CLASS = 6
 mxSINGLE_CLASS = 7
 
@@ -78,6 +79,17 @@ def mx_dense(a: np.ndarray, keep: list, classid: int = mxDOUBLE_CLASS,
     keep.append(a)
     return MxArray(a.shape[0], a.shape[1], a.ctypes.data, None, None, 0,
                    int(is_complex), classid, 0, 0)
+
+
+def mx_string(text: str, keep: list) -> MxArray:
+    """A MATLAB char row vector (the stub stores one byte per character)."""
+    b = np.frombuffer(text.encode(), dtype=np.uint8).copy()
+    keep.append(b)
+    return MxArray(1, b.shape[0], b.ctypes.data, None, None, 0, 0, mxCHAR_CLASS, 0, 0)
+
+
+def mx_empty() -> MxArray:
+    return MxArray(0, 0, None, None, None, 0, 0, mxDOUBLE_CLASS, 0, 0)
 
 
 def mx_sparse(p: int, n: int, jc: np.ndarray, ir: np.ndarray, x: np.ndarray,
