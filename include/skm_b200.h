@@ -202,6 +202,20 @@ int   skm_lloyd_argmax_distance(skm_lloyd *L, double *maxdist, int64_t *j);
 void *skm_lloyd_assign_ptr(skm_lloyd *L);
 void *skm_lloyd_dist_ptr(skm_lloyd *L, int *dtype);
 
+/* One Lloyd iteration over a matrix that lives in HOST memory (the stateless form of the path,
+ * and the out-of-core form for matrices larger than HBM): columns are streamed in chunks of
+ * `chunk_cols` (0 = automatic) over PCIe on a copy stream while the previous chunk is laid out,
+ * assigned (K1 + fp64 re-evaluation) and accumulated (K2) on the compute stream; K3 runs at the
+ * end.  Same arithmetic and exactness guarantee as skm_lloyd_assign/accumulate/finalize on an
+ * SKM_F32 dataset.  Pinned host buffers overlap best.  assign_out (1-based) / dist_out may be
+ * NULL; centers_out receives the updated centres (empty clusters keep their input column). */
+int   skm_lloyd_step_host(skm_ctx *ctx, int64_t p, int64_t n, const void *jc, int jc_type,
+                          const void *ir, int ir_type, const void *val, int val_type,
+                          const double *centers, int64_t K, int has_gamma, double gamma_dist,
+                          double gamma_update, int ml_correction, int64_t chunk_cols,
+                          double *centers_out, int32_t *assign_out, double *dist_out,
+                          skm_iter_stats *stats);
+
 /* k-means++ support (private/Arthur_initialization.m:39-53): fold the masked
  * distance to ONE new centre into the running minimum kept on the device.
  * first != 0 resets the running minimum.  sum_d2 receives sum_j mind_j^2 over

@@ -33,6 +33,7 @@ struct FastParams {
     float          gb_unit;      // guard: 2.02*u*sqrt(m)      (times cmax)
     float          ge_unit;      // guard: 2.1*u*u*m           (times cmax^2)
     const float   *cmax;
+    const int     *m_dev;        // optional: max entries per column on the device (streamed path)
     int32_t       *assign;
     float         *dist;
     float2        *best2;
@@ -171,11 +172,16 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assign_fast(const FastParams 
         }
         // ---- guard: |fp32 sum - exact sum| <= E(s) = ga*s + gb*sqrt(s) + ge   ----
         const float cm = *P.cmax;
-        const float gb = P.gb_unit * cm, ge = P.ge_unit * cm * cm + 1e-37f;
+        float ga = P.ga, gbu = P.gb_unit, geu = P.ge_unit;
+        if (P.m_dev) {                                          // same constants, rounded up in fp32
+            const float U = 5.9604644775390625e-08f, mm = (float)max(*P.m_dev, 1);
+            ga = 1.02f * (mm + 5.f) * U; gbu = 2.04f * U * sqrtf(mm); geu = 2.2f * U * U * mm;
+        }
+        const float gb = gbu * cm, ge = geu * cm * cm + 1e-37f;
         bool certified;
         if (P.ktotal == 1) certified = (b1 < INF);
         else {
-            const float E = P.ga * (b1 + b2) + gb * (sqrtf(b1) + sqrtf(b2)) + 2.f * ge;
+            const float E = ga * (b1 + b2) + gb * (sqrtf(b1) + sqrtf(b2)) + 2.f * ge;
             certified = (b2 - b1) > E;                         // false for NaN / inf
         }
         P.assign[j] = i1;
@@ -274,7 +280,7 @@ int skm_launch_build_table(skm_ctx *ctx, int64_t p, int64_t K, const double *ct,
 
 int skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const FastPlan &pl,
                            const float *table, const float *cmax, int32_t *assign, float *dist,
-                           float *best2, int32_t *flagged, int *nflag)
+                           float *best2, int32_t *flagged, int *nflag, const int *m_dev)
 {
     SKM_CUDA(cudaMemsetAsync(nflag, 0, sizeof(int), ctx->stream));
     if (ds->n == 0) return SKM_OK;
@@ -294,6 +300,7 @@ int skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const
     P.gb_unit = (float)(2.02 * u * sqrt(m));
     P.ge_unit = (float)(2.1 * u * u * m);
     P.cmax = cmax;
+    P.m_dev = m_dev;
     P.assign = assign;
     P.dist = dist;
     P.best2 = reinterpret_cast<float2 *>(best2);

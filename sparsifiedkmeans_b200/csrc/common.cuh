@@ -166,6 +166,13 @@ int skm_validate_csc(skm_ctx *ctx, int64_t p, int64_t n, int64_t nnz, const int6
                      const int32_t *rowidx, int64_t *max_col_nnz);
 int skm_build_sell(skm_dataset *ds);
 int skm_build_csr(skm_dataset *ds);      // csr.cu
+// asynchronous pieces used by the streamed path (stream.cu); no host synchronisation inside
+int skm_launch_validate_async(skm_ctx *ctx, int64_t p, int64_t n, int64_t nnz, const int64_t *colptr,
+                              const int32_t *rowidx, int *flags_dev /* [0]=error bits, [1]=max col nnz */);
+int skm_launch_rebase_colptr(skm_ctx *ctx, const void *src, int src_type, int64_t count, int64_t base, int64_t *dst);
+int skm_build_sell_async(skm_ctx *ctx, skm_dataset *view, int32_t *width2_scratch, int64_t *elems_scratch,
+                         void *cub_tmp, size_t cub_tmp_bytes);
+size_t skm_sell_scan_tmp_bytes(int64_t nslices);
 
 // exact.cu
 struct ExactArgs {
@@ -202,11 +209,12 @@ int  skm_launch_build_table(skm_ctx *ctx, int64_t p, int64_t K, const double *ct
                             float *table, float *cmax);
 int  skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const FastPlan &pl,
                             const float *table, const float *cmax, int32_t *assign, float *dist,
-                            float *best2, int32_t *flagged, int *nflag);
+                            float *best2, int32_t *flagged, int *nflag, const int *m_dev = nullptr);
 
 // update.cu
 int skm_launch_accumulate(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const int32_t *assign,
-                          void *assign_c, const float *dist32, const double *dist64, double *partials);
+                          void *assign_c, const float *dist32, const double *dist64, double *partials,
+                          bool zero_first = true);
 int skm_launch_finalize(skm_ctx *ctx, int64_t p, int64_t K, const double *partials, double gamma,
                         int ml_correction, double *centers, double *centers_old, double *stats);
 int skm_launch_argmax(skm_ctx *ctx, int64_t n, const float *dist32, const double *dist64,

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include <stdlib.h>
 #include <vector>
+#include <cub/device/device_scan.cuh>
 
 namespace {
 
@@ -194,6 +195,82 @@ __global__ void k_fill_sell_banked(int64_t p, int64_t n, int64_t nslices, int wm
 }
 
 }  // namespace
+
+
+namespace {
+template <typename S>
+__global__ void k_rebase(const S *__restrict__ src, int64_t count, int64_t base, int64_t *__restrict__ dst)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < count; i += stride) dst[i] = (int64_t)src[i] - base;
+}
+__global__ void k_width_to_elems(int64_t nslices, const int32_t *__restrict__ w2, int64_t *__restrict__ elems)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nslices) elems[i] = (int64_t)w2[i] * 32;
+    if (i == nslices) elems[i] = 0;
+}
+}  // namespace
+
+int skm_launch_validate_async(skm_ctx *ctx, int64_t p, int64_t n, int64_t nnz, const int64_t *colptr,
+                              const int32_t *rowidx, int *flags_dev)
+{
+    const int64_t cap = (int64_t)ctx->sm_count * 16;
+    if (n > 0) {
+        int64_t blocks = (n + 255) / 256;
+        if (blocks > cap) blocks = cap;
+        k_validate_cols<<<(unsigned)blocks, 256, 0, ctx->stream>>>(n, nnz, colptr, flags_dev);
+        SKM_CHECK_LAUNCH(ctx);
+    }
+    if (nnz > 0) {
+        int64_t blocks = (nnz + 255) / 256;
+        if (blocks > cap) blocks = cap;
+        k_validate_rows<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p, nnz, rowidx, flags_dev);
+        SKM_CHECK_LAUNCH(ctx);
+    }
+    return SKM_OK;
+}
+
+int skm_launch_rebase_colptr(skm_ctx *ctx, const void *src, int src_type, int64_t count, int64_t base, int64_t *dst)
+{
+    if (count == 0) return SKM_OK;
+    int64_t blocks = (count + 255) / 256;
+    const int64_t cap = (int64_t)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    if (src_type == SKM_I64) k_rebase<int64_t><<<(unsigned)blocks, 256, 0, ctx->stream>>>((const int64_t *)src, count, base, dst);
+    else k_rebase<int32_t><<<(unsigned)blocks, 256, 0, ctx->stream>>>((const int32_t *)src, count, base, dst);
+    SKM_CHECK_LAUNCH(ctx);
+    return SKM_OK;
+}
+
+size_t skm_sell_scan_tmp_bytes(int64_t nslices)
+{
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int64_t *)nullptr, (int64_t *)nullptr, nslices + 1);
+    return bytes;
+}
+
+// plain (stored-order) SELL image of a view whose colptr/rowidx/val are on the device; slice_ptr and
+// sell must be preallocated (slice_ptr: nslices+1).  No host synchronisation.
+int skm_build_sell_async(skm_ctx *ctx, skm_dataset *ds, int32_t *w2, int64_t *elems, void *cub_tmp, size_t cub_tmp_bytes)
+{
+    const int64_t n = ds->n, nslices = (n + SKM_SLICE - 1) / SKM_SLICE;
+    ds->nslices = nslices;
+    ds->uniform_width = false;
+    if (nslices == 0) return SKM_OK;
+    int64_t blocks = (nslices * 32 + 255) / 256;
+    k_slice_width<<<(unsigned)blocks, 256, 0, ctx->stream>>>(n, nslices, ds->colptr, w2);
+    SKM_CHECK_LAUNCH(ctx);
+    k_width_to_elems<<<(unsigned)((nslices + 1 + 255) / 256), 256, 0, ctx->stream>>>(nslices, w2, elems);
+    SKM_CHECK_LAUNCH(ctx);
+    SKM_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_tmp_bytes, elems, ds->slice_ptr, nslices + 1, ctx->stream));
+    ctx->launches++;
+    k_fill_sell<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>(ds->p, n, nslices, ds->colptr, ds->rowidx,
+                                                                 (const float *)ds->val, ds->slice_ptr, ds->sell);
+    SKM_CHECK_LAUNCH(ctx);
+    return SKM_OK;
+}
 
 int skm_launch_convert_index(skm_ctx *ctx, const void *src, int src_type, int64_t count, void *dst,
                              int dst_is_i64)

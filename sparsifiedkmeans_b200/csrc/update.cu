@@ -302,10 +302,11 @@ static int accumulate_csr(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const 
 }
 
 int skm_launch_accumulate(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const int32_t *assign, void *assign_c,
-                          const float *dist32, const double *dist64, double *partials)
+                          const float *dist32, const double *dist64, double *partials, bool zero_first)
 {
     const int64_t p = ds->p, n = ds->n;
-    SKM_CUDA(cudaMemsetAsync(partials, 0, sizeof(double) * (size_t)(2 * p * K + K + 1), ctx->stream));
+    if (zero_first)
+        SKM_CUDA(cudaMemsetAsync(partials, 0, sizeof(double) * (size_t)(2 * p * K + K + 1), ctx->stream));
     if (n == 0) return SKM_OK;
     if (ds->csr && ds->nunits > 0 && assign_c) {
         if (K <= 256) return accumulate_csr<uint8_t>(ctx, ds, K, assign, assign_c, dist32, dist64, partials);

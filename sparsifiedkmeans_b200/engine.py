@@ -346,3 +346,32 @@ class Lloyd:
         if reduce is not None:
             reduce(self)
         return self.finalize(gamma_update, ml_correction)
+
+
+def lloyd_step_host(p: int, n: int, jc, ir, val, centers, gamma_dist, gamma_update: float,
+                    ml_correction: bool = True, chunk_cols: int = 0, want_assign: bool = True,
+                    want_dist: bool = False, ctx: Context | None = None):
+    """One Lloyd iteration with X in HOST memory, streamed over PCIe in column chunks
+    (skm_lloyd_step_host).  jc/ir/val are numpy arrays (int32/int64, float32/float64; pinned
+    memory overlaps best).  Returns (new_centers, assign 1-based or None, dist or None, IterStats)."""
+    ctx = ctx or default_context()
+    jc = np.ascontiguousarray(jc)
+    ir = np.ascontiguousarray(ir)
+    val = np.ascontiguousarray(val)
+    if jc.dtype not in _NP_INDEX:
+        jc = jc.astype(np.int64)
+    if ir.dtype not in _NP_INDEX:
+        ir = ir.astype(np.int64)
+    if val.dtype not in _NP_VALUE:
+        val = val.astype(np.float64)
+    c, K = _centers(centers, p)
+    out_c = np.empty(p * K, dtype=np.float64)
+    a = np.empty(n, dtype=np.int32) if want_assign else None
+    d = np.empty(n, dtype=np.float64) if want_dist else None
+    st = _lib.IterStats()
+    check(ctx._lib.skm_lloyd_step_host(
+        ctx.handle, p, n, _ptr(jc), _NP_INDEX[jc.dtype], _ptr(ir), _NP_INDEX[ir.dtype], _ptr(val),
+        _NP_VALUE[val.dtype], _ptr(c), K, int(gamma_dist is not None),
+        float(gamma_dist if gamma_dist is not None else 0.0), float(gamma_update), int(ml_correction),
+        int(chunk_cols), _ptr(out_c), _ptr(a), _ptr(d), C.byref(st)))
+    return out_c.reshape(K, p).T.copy(), a, d, Lloyd._stats(st)

@@ -239,3 +239,32 @@ def test_kpp_running_min_matches_reference(ctx):
     for u in (0.0, 0.1, 0.5, 0.999999):
         assert ds.kpp_pick(u * tot) == host_ref.weighted_pick(w, u)
     ds.close()
+
+
+# ------------------------------------------------------------ streamed -----
+@pytest.mark.parametrize("K,p,m,chunk", [(5, 64, 8, 0), (10, 784, 78, 1024), (70, 128, 9, 512)])
+@pytest.mark.parametrize("dtypes", [(np.int32, np.int32, np.float32), (np.int64, np.int64, np.float64)])
+def test_streamed_host_iteration_matches_reference(ctx, K, p, m, chunk, dtypes):
+    """skm_lloyd_step_host (X in host memory, chunks over PCIe) == resident path == oracle."""
+    from sparsifiedkmeans_b200 import lloyd_step_host
+    X, c, gamma = make_sparsified(p=p, n=5000, m=m, K=K, seed=K + 3, kind="mixture", ragged=(K == 5))
+    n = X.shape[1]
+    jt, it, vt = dtypes
+    newc, a, d, st = lloyd_step_host(p, n, X.indptr.astype(jt), X.indices.astype(it), X.data.astype(vt), c, gamma, gamma,
+                                     True, chunk_cols=chunk, want_dist=True, ctx=ctx)
+    wa, wd, _ = host_ref.find_cluster_assignments(X, c, gamma)
+    assert np.array_equal(a, wa)
+    np.testing.assert_allclose(d, wd, rtol=2e-5, atol=1e-30)
+    want, _, _, counts = cport.centroid_update(p, n, K, X.indptr, X.indices, X.data, wa, gamma, c, True)
+    scale = np.max(np.abs(want))
+    assert np.max(np.abs(newc - want)) <= CENTROID_RTOL * scale
+    assert st.n_points == n and st.n_empty == int(np.sum(counts == 0))
+    np.testing.assert_allclose(st.dff, np.linalg.norm(c - want, "fro"), rtol=1e-9)
+
+
+def test_streamed_rejects_bad_rows(ctx):
+    from sparsifiedkmeans_b200 import lloyd_step_host
+    from sparsifiedkmeans_b200._lib import SkmError
+    with pytest.raises(SkmError):
+        lloyd_step_host(4, 2, np.array([0, 2, 3]), np.array([0, 9, 1]), np.array([1.0, 2.0, 3.0]), np.ones((4, 2)),
+                        None, 1.0, ctx=ctx)
