@@ -163,6 +163,23 @@ class Dataset:
             SKM_F32 if store == "f32" else SKM_F64, 1, C.byref(h)))
         return cls(ctx, h)
 
+    @classmethod
+    def from_fwht_sample(cls, p2: int, n: int, m: int, x_ptr: int, signs_ptr: int, rows_ptr: int,
+                         ctx: Context | None = None):
+        """Fused precondition + row sample on the device (skm_fwht_sample_f32): x is a dense
+        p2 x n float32 column-major device matrix, signs float32[p2], rows int32[m*n] (column j
+        keeps rows[m*j:m*j+m]).  The result is resident and ready for Lloyd iterations."""
+        ctx = ctx or default_context()
+        h = C.c_void_p()
+        check(ctx._lib.skm_fwht_sample_f32(ctx.handle, p2, n, m, x_ptr, signs_ptr, rows_ptr, C.byref(h)))
+        return cls(ctx, h)
+
+    def to_scipy(self):
+        """Download as a scipy CSC matrix (float64 values) -- for tests and small data."""
+        import scipy.sparse as sp
+        cols = [self.get_column(j) for j in range(self.n)]
+        return sp.csc_matrix(np.stack(cols, axis=1)) if cols else sp.csc_matrix((self.p, 0))
+
     @property
     def handle(self):
         if self._h is None:
@@ -375,3 +392,26 @@ def lloyd_step_host(p: int, n: int, jc, ir, val, centers, gamma_dist, gamma_upda
         float(gamma_dist if gamma_dist is not None else 0.0), float(gamma_update), int(ml_correction),
         int(chunk_cols), _ptr(out_c), _ptr(a), _ptr(d), C.byref(st)))
     return out_c.reshape(K, p).T.copy(), a, d, Lloyd._stats(st)
+
+
+def mix_hadamard(X, signs, compute: str = "f64", ctx: Context | None = None) -> np.ndarray:
+    """mix(X) = hadamard(D*[X;0])/sqrt(p2) on the GPU (kmeans_sparsified.m:238-248,286-295).
+    X is dense p x n (host), signs has p2 = 2^nextpow2(p) entries; returns p2 x n float64."""
+    ctx = ctx or default_context()
+    X = np.asarray(X, dtype=np.float64)
+    if X.ndim == 1:
+        X = X.reshape(-1, 1)
+    p, n = X.shape
+    d = np.ascontiguousarray(signs, dtype=np.float64).reshape(-1)
+    p2 = d.shape[0]
+    Xf = np.ascontiguousarray(X.T).reshape(-1)
+    out = np.empty(p2 * n, dtype=np.float64)
+    check(ctx._lib.skm_mix_hadamard(ctx.handle, p, p2, n, _ptr(Xf), _ptr(d),
+                                    SKM_F64 if compute == "f64" else SKM_F32, _ptr(out)))
+    return out.reshape(n, p2).T
+
+
+def fwht_f32_inplace(p2: int, n: int, x_ptr: int, signs_ptr: int | None, ctx: Context | None = None):
+    """In-place device FWHT of a dense p2 x n float32 matrix: sign flip, transform, /sqrt(p2)."""
+    ctx = ctx or default_context()
+    check(ctx._lib.skm_fwht_f32_inplace(ctx.handle, p2, n, x_ptr, signs_ptr))

@@ -191,13 +191,8 @@ def kmeans_sparsified(X=None, K=None, **opts):
     def mix(A):                                                                       # :295
         if d is None:
             return np.asarray(A, dtype=np.float64)
-        A = np.asarray(A, dtype=np.float64)
-        Af = np.ascontiguousarray(A.T).reshape(-1)
-        out = np.empty(p2 * A.shape[1], dtype=np.float64)
-        from ._lib import SKM_F32, SKM_F64, check
-        check(ctx._lib.skm_mix_hadamard(ctx.handle, A.shape[0], p2, A.shape[1], Af.ctypes.data, d.ctypes.data,
-                                        SKM_F64 if o["MixDtype"] == "f64" else SKM_F32, out.ctypes.data))
-        return out.reshape(A.shape[1], p2).T
+        from .engine import mix_hadamard
+        return mix_hadamard(A, d, o["MixDtype"], ctx)
 
     def unmix(C):                                                                     # :296
         if d is None:

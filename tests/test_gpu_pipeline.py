@@ -1,0 +1,165 @@
+"""GPU tests of the stages either side of the Lloyd loop: precondition (mix / fused sample),
+k-means++ and the kmeans_sparsified entry point, against the oracle's restatement of the
+reference's host logic on identical explicit random draws."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import host_ref
+from tests.util import make_sparsified, sample_rows
+
+pytestmark = pytest.mark.gpu
+
+
+def _signs(rng, p2):
+    d = np.sign(rng.standard_normal(p2))
+    d[d == 0] = 1.0
+    return d
+
+
+@pytest.mark.parametrize("p,n", [(8, 5), (50, 40), (512, 33), (784, 16), (4096, 6)])
+def test_mix_hadamard_fp64_is_bit_exact(ctx, p, n):
+    from sparsifiedkmeans_b200 import mix_hadamard
+    rng = np.random.default_rng(p)
+    X = rng.standard_normal((p, n))
+    d = _signs(rng, host_ref.nextpow2_size(p))
+    got = mix_hadamard(X, d, "f64", ctx)
+    want = host_ref.mix_hadamard(X, d)                     # hadamard(DD*upsample(X))/sqrt(p2), kmeans_sparsified.m:295
+    assert got.shape == want.shape and np.array_equal(got, want)
+    # fp32 fast path: tolerance (relative to the column norm; the transform is orthonormal)
+    got32 = mix_hadamard(X, d, "f32", ctx)
+    assert np.max(np.abs(got32 - want)) <= 2e-6 * np.max(np.linalg.norm(X, axis=0)) * np.log2(d.shape[0])
+
+
+@pytest.mark.parametrize("p2,n,m", [(64, 200, 3), (512, 300, 26), (4096, 40, 205), (32768, 6, 1638)])
+def test_fused_fwht_sample_matches_reference_pipeline(ctx, p2, n, m):
+    """K4 fused: sign flip + FWHT + /sqrt(p2) + fixed-count row sample + /(m/p2), on the device."""
+    import torch
+    from sparsifiedkmeans_b200 import Dataset
+    rng = np.random.default_rng(p2 + n)
+    X = rng.standard_normal((p2, n)).astype(np.float32)
+    d = _signs(rng, p2)
+    rows = sample_rows(rng, p2, n, m)                                          # (m, n) sorted distinct
+    perm = rng.permuted(rows, axis=0)                                          # any order is accepted
+    dev = torch.device("cuda:0")
+    xd = torch.from_numpy(np.ascontiguousarray(X.T)).to(dev)                   # column-major p2 x n
+    sd = torch.from_numpy(d.astype(np.float32)).to(dev)
+    rd = torch.from_numpy(np.ascontiguousarray(perm.T).astype(np.int32)).to(dev)
+    ds = Dataset.from_fwht_sample(p2, n, m, xd.data_ptr(), sd.data_ptr(), rd.data_ptr(), ctx=ctx)
+    assert ds.nnz == n * m and ds.max_col_nnz == m
+    want = host_ref.sample_fixed_entries(host_ref.mix_hadamard(X.astype(np.float64), d), rows)
+    got = ds.to_scipy()
+    assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+    scale = np.max(np.abs(want.data))
+    assert np.max(np.abs(got.data - want.data)) <= 3e-6 * scale * np.log2(p2)
+    # the resident result runs the Lloyd path directly
+    c = rng.standard_normal((p2, 3))
+    a, _ = ds.assign(c, m / p2)
+    wa, _, _ = host_ref.find_cluster_assignments(got, c, m / p2)
+    assert np.array_equal(a, wa)
+    ds.close()
+
+
+def test_fwht_inplace_involution(ctx):
+    import torch
+    from sparsifiedkmeans_b200 import fwht_f32_inplace
+    x = torch.randn(7, 2048, device="cuda:0")
+    y = x.clone()
+    fwht_f32_inplace(2048, 7, y.data_ptr(), None, ctx)
+    fwht_f32_inplace(2048, 7, y.data_ptr(), None, ctx)      # H/sqrt(p) twice = identity (hadamard.c:18-24)
+    ctx.synchronize()
+    assert torch.allclose(x, y, rtol=0, atol=2e-5)
+
+
+def test_arthur_initialization_matches_reference(ctx):
+    from sparsifiedkmeans_b200 import Arthur_initialization, Dataset
+    X, _, gamma = make_sparsified(p=64, n=1200, m=8, K=6, seed=51, kind="mixture")
+    u = np.random.default_rng(7).random(4000)
+    want, _ = host_ref.arthur_initialization(X, 6, gamma, first=17, uniforms=iter(u))
+    ds = Dataset.from_scipy(X, store="f32", ctx=ctx)
+    got = Arthur_initialization(ds, 6, gamma, first=17, uniforms=iter(u))
+    assert np.array_equal(got, want)
+    ds.close()
+
+
+def _mixture(n=600, p=64, K=4, seed=0):
+    rng = np.random.default_rng(seed)
+    mu = rng.standard_normal((K, p))
+    lab = np.arange(n) % K
+    return mu[lab] + 0.1 * rng.standard_normal((n, p)), lab, mu
+
+
+@pytest.mark.parametrize("start", ["matrix", "indices"])
+def test_kmeans_sparsified_matches_reference_run(ctx, start):
+    """Whole entry point on explicit draws (signs, row sample, start) vs the oracle's restatement."""
+    from sparsifiedkmeans_b200 import kmeans_sparsified
+    Xr, lab, mu = _mixture()
+    n, p = Xr.shape
+    rng = np.random.default_rng(3)
+    d = _signs(rng, p)
+    m = max(1, host_ref.matlab_round(0.125 * p))
+    rows = sample_rows(rng, p, n, m)
+    opts = dict(Sparsify=True, SparsityLevel=0.125, SketchType="Hadamard", Signs=d, SampleRows=rows, MaxIter=25,
+                Store="f32", Context=ctx)
+    # oracle side
+    Xm = host_ref.mix_hadamard(Xr.T * (1 + 2 * np.finfo(float).eps), d)
+    Xs = host_ref.sample_fixed_entries(Xm, rows)
+    gamma = m / p
+    if start == "matrix":
+        st = mu + 0.05 * rng.standard_normal(mu.shape)
+        ref = host_ref.lloyd(Xs, host_ref.mix_hadamard(st.T, d), gamma, max_iter=25, tol=1e-6)
+        IDX, C, SUMD, D, OUT = kmeans_sparsified(Xr, 4, Start=st, **opts)
+    else:
+        ind = np.array([0, 1, 2, 3])
+        ref = host_ref.lloyd(Xs, np.asarray(Xs[:, ind].todense()), gamma, max_iter=25, tol=1e-6, centers_sparse=True)
+        IDX, C, SUMD, D, OUT = kmeans_sparsified(Xr, 4, Start="sample", StartIndices=ind, **opts)
+    assert OUT["iterations"][0] == ref.iterations
+    assert np.array_equal(IDX, ref.assignments)
+    np.testing.assert_allclose(D, ref.distances, rtol=2e-5, atol=1e-12)
+    want_C = host_ref.unmix_hadamard(ref.centers, d, p).T
+    np.testing.assert_allclose(C, want_C, rtol=1e-6, atol=1e-6 * np.max(np.abs(want_C)))
+    np.testing.assert_allclose(OUT["objectives"][0], ref.objective, rtol=1e-5)
+    assert SUMD.shape == (4,) and C.shape == (4, p)
+
+
+def test_kmeans_sparsified_recovers_planted_partition(ctx):
+    """example_sparseKMeans.m: well-separated Gaussian blobs are recovered up to relabelling."""
+    from sparsifiedkmeans_b200 import kmeans_sparsified
+    Xr, lab, mu = _mixture(n=2000, p=128, K=5, seed=4)
+    IDX, C, SUMD, D, OUT = kmeans_sparsified(Xr, 5, Sparsify=True, SparsityLevel=0.1, SketchType="Hadamard",
+                                             Replicates=3, Seed=0, Context=ctx)
+    for k in range(5):
+        assert len(set(IDX[lab == k].tolist())) == 1
+    assert len(set(IDX.tolist())) == 5
+    order = [int(IDX[lab == k][0]) - 1 for k in range(5)]
+    assert np.max(np.abs(C[order] - mu)) < 0.1              # centres within sampling error of the truth
+    assert set(OUT) >= {"iterations", "stoppingDiff", "objectives", "TimeToSketch", "TimeToSample", "TimeOverall"}
+
+
+def test_kmeans_sparsified_empty_actions(ctx):
+    from sparsifiedkmeans_b200 import KMeansError, kmeans_sparsified
+    Xr, lab, mu = _mixture(n=300, p=32, K=3, seed=5)
+    st = np.vstack([mu, 50.0 + np.zeros((1, 32))])          # 4th start centre attracts nobody
+    common = dict(Sparsify=True, SparsityLevel=0.25, SketchType="Hadamard", Seed=1, MaxIter=10, Context=ctx)
+    with pytest.warns(UserWarning):
+        IDX, C, *_ = kmeans_sparsified(Xr, 4, Start=st, EmptyAction="singleton", **common)
+    assert C.shape == (4, 32)
+    with pytest.raises(KMeansError), pytest.warns(UserWarning):
+        kmeans_sparsified(Xr, 4, Start=st, EmptyAction="error", **common)
+    with pytest.warns(UserWarning):
+        IDX, C, *_ = kmeans_sparsified(Xr, 4, Start=st, EmptyAction="drop", **common)
+    assert C.shape[0] == 3
+
+
+def test_sharded_driver_on_one_gpu_equals_plain_loop(ctx):
+    from sparsifiedkmeans_b200 import Dataset
+    from sparsifiedkmeans_b200.distributed import CudaShardEngine, ShardedLloyd
+    X, c, gamma = make_sparsified(p=64, n=3000, m=8, K=5, seed=61, kind="mixture")
+    ref = host_ref.lloyd(X, c, gamma, max_iter=20, tol=1e-6)
+    ds = Dataset.from_scipy(X, store="f32", ctx=ctx)
+    eng = CudaShardEngine(ds, 5)
+    its, st = ShardedLloyd(eng).run(c, gamma, gamma, max_iter=20, tol=1e-6)
+    a, _ = eng.assignments()
+    assert its == ref.iterations and np.array_equal(a, ref.assignments)
+    np.testing.assert_allclose(eng.get_centers(), ref.centers, rtol=1e-6, atol=1e-9)
+    eng.close(); ds.close()
