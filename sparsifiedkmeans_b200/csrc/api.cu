@@ -346,8 +346,8 @@ static ExactArgs exact_args(const skm_dataset *ds, int64_t K, const double *ct)
 extern "C" void skm_lloyd_destroy(skm_lloyd *L)
 {
     if (!L) return;
-    cudaSetDevice(L->ds->ctx->device);
-    cudaStreamSynchronize(L->ds->ctx->stream);
+    cudaSetDevice(L->ctx->device);
+    cudaStreamSynchronize(L->ctx->stream);
     cudaFree(L->centers); cudaFree(L->centers_old); cudaFree(L->cscaled_t); cudaFree(L->table);
     cudaFree(L->assign_c);
     cudaFree(L->cmax); cudaFree(L->assign); cudaFree(L->dist_f32); cudaFree(L->dist_f64);
@@ -374,7 +374,7 @@ static int skm_lloyd_create_ex(skm_dataset *ds, int64_t K, int want_f64_dist, sk
     skm_lloyd *L = new (std::nothrow) skm_lloyd();
     if (!L) { skm_set_error("out of host memory"); return SKM_ERR_NOMEM; }
     memset(L, 0, sizeof *L);
-    L->ds = ds; L->K = K;
+    L->ds = ds; L->ctx = ds->ctx; L->K = K;
     const int64_t p = ds->p, n = ds->n;
     int rc = SKM_OK;
     do {

@@ -133,6 +133,7 @@ struct skm_dataset {
 
 struct skm_lloyd {
     skm_dataset *ds;
+    skm_ctx     *ctx;        // kept separately so destroy never touches a dataset that is gone
     int64_t  K;
     double  *centers;        // [p*K] column-major, current centres (unscaled)
     double  *centers_old;    // [p*K]

@@ -5,6 +5,7 @@ module only marshals numpy buffers (host) or raw device pointers.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from dataclasses import dataclass
 
 import numpy as np
@@ -114,6 +115,7 @@ class Dataset:
         self.ctx = ctx
         self._lib = ctx._lib
         self._h = handle
+        self._children = weakref.WeakSet()       # Lloyd states bound to this dataset
         info = _lib.DatasetInfo()
         check(self._lib.skm_dataset_get_info(handle, C.byref(info)))
         self.p, self.n, self.nnz = int(info.p), int(info.n), int(info.nnz)
@@ -188,6 +190,8 @@ class Dataset:
 
     def close(self):
         if self._h is not None:
+            for child in list(self._children):   # a Lloyd state must not outlive its dataset
+                child.close()
             self._lib.skm_dataset_destroy(self._h)
             self._h = None
 
@@ -258,6 +262,7 @@ class Lloyd:
         h = C.c_void_p()
         check(self._lib.skm_lloyd_create(ds.handle, self.K, C.byref(h)))
         self._h = h
+        ds._children.add(self)
 
     @property
     def handle(self):

@@ -228,6 +228,7 @@ def kmeans_sparsified(X=None, K=None, **opts):
                   replicateTimes=np.zeros(R), replicateTimesJustInitialization=np.zeros(R))
     best = dict(obj=math.inf)
     distances = None
+    L = None
     try:
         for trial in range(R):
             t1 = time.perf_counter()
@@ -328,6 +329,8 @@ def kmeans_sparsified(X=None, K=None, **opts):
                 print("Trial %3d of %3d total, objective %.2e%s" % (trial + 1, R, obj, tail))
             L.close()
     finally:
+        if L is not None:
+            L.close()
         ds.close()
     if "assignments" not in best:
         raise KMeansError("no replicate produced a finite objective")
