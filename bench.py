@@ -361,7 +361,8 @@ def run_ours(args):
         def e2e_step():
             # stateless call: X in pinned host memory, streamed over PCIe in column chunks
             newc, a, _, st2 = lloyd_step_host(p, n_e2e, hj, hi, hv, start, gamma, gamma, True,
-                                              want_assign=True, want_dist=False, ctx=ctx)
+                                              want_assign=True, want_dist=False, ctx=ctx,
+                                              reduce=(lambda t: dist.all_reduce(t)) if world > 1 else None)
             return a, newc
         e2e_step()
         fence()

@@ -209,12 +209,16 @@ void *skm_lloyd_dist_ptr(skm_lloyd *L, int *dtype);
  * end.  Same arithmetic and exactness guarantee as skm_lloyd_assign/accumulate/finalize on an
  * SKM_F32 dataset.  Pinned host buffers overlap best.  assign_out (1-based) / dist_out may be
  * NULL; centers_out receives the updated centres (empty clusters keep their input column). */
+/* `reduce` (may be NULL) is called once, after the last chunk, with the device buffer
+ * [S | N | counts | sumsq] and the compute stream: a multi-GPU caller all-reduces it there
+ * (asynchronously on that stream) and returns 0. */
+typedef int (*skm_reduce_fn)(void *partials_dev, int64_t n_doubles, void *cuda_stream, void *user);
 int   skm_lloyd_step_host(skm_ctx *ctx, int64_t p, int64_t n, const void *jc, int jc_type,
                           const void *ir, int ir_type, const void *val, int val_type,
                           const double *centers, int64_t K, int has_gamma, double gamma_dist,
                           double gamma_update, int ml_correction, int64_t chunk_cols,
                           double *centers_out, int32_t *assign_out, double *dist_out,
-                          skm_iter_stats *stats);
+                          skm_iter_stats *stats, skm_reduce_fn reduce, void *reduce_user);
 
 /* k-means++ support (private/Arthur_initialization.m:39-53): fold the masked
  * distance to ONE new centre into the running minimum kept on the device.

@@ -31,6 +31,9 @@ class SkmError(RuntimeError):
         self.message = message
 
 
+REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
+
+
 class DatasetInfo(C.Structure):
     _fields_ = [("p", _i64), ("n", _i64), ("nnz", _i64), ("max_col_nnz", _i64),
                 ("store_dtype", C.c_int32), ("reserved", C.c_int32),
@@ -84,7 +87,7 @@ SIGNATURES = {
     "skm_lloyd_assign_ptr": (_vp, [_vp]),
     "skm_lloyd_dist_ptr": (_vp, [_vp, C.POINTER(_int)]),
     "skm_lloyd_step_host": (_int, [_vp, _i64, _i64, _vp, _int, _vp, _int, _vp, _int, _vp, _i64, _int, _dbl, _dbl,
-                                   _int, _i64, _vp, _vp, _vp, C.POINTER(IterStats)]),
+                                   _int, _i64, _vp, _vp, _vp, C.POINTER(IterStats), _vp, _vp]),
     "skm_kpp_update": (_int, [_vp, _vp, _int, _dbl, _int, C.POINTER(_dbl)]),
     "skm_kpp_pick": (_int, [_vp, _dbl, C.POINTER(_i64)]),
     "skm_kpp_get_mindist": (_int, [_vp, _vp]),

@@ -191,6 +191,7 @@ extern "C" void skm_dataset_destroy(skm_dataset *ds)
     cudaFree(ds->rowptr);
     cudaFree(ds->unit_row);
     cudaFree(ds->unit_start);
+    cudaFree(ds->unit_counter);
     free(ds->h_rowptr);
     delete ds;
 }

@@ -319,9 +319,10 @@ int skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const
             case 12: rc = launch_fast<12, 256, 4>(ctx, P, pl.smem); break;
             case 16: rc = launch_fast<16, 256, 4>(ctx, P, pl.smem); break;
             case 24: rc = launch_fast<24, 256, 3>(ctx, P, pl.smem); break;
-            case 32: rc = launch_fast<32, 256, 2>(ctx, P, pl.smem); break;
-            case 48: rc = launch_fast<48, 256, 2>(ctx, P, pl.smem); break;
-            case 64: rc = launch_fast<64, 256, 2>(ctx, P, pl.smem); break;
+            // a table above ~110 KB leaves room for one CTA per SM: use a wide CTA to keep 16 warps resident
+            case 32: rc = pl.smem > 110 * 1024 ? launch_fast<32, 512, 1>(ctx, P, pl.smem) : launch_fast<32, 256, 2>(ctx, P, pl.smem); break;
+            case 48: rc = pl.smem > 110 * 1024 ? launch_fast<48, 512, 1>(ctx, P, pl.smem) : launch_fast<48, 256, 2>(ctx, P, pl.smem); break;
+            case 64: rc = pl.smem > 110 * 1024 ? launch_fast<64, 512, 1>(ctx, P, pl.smem) : launch_fast<64, 256, 2>(ctx, P, pl.smem); break;
             default: skm_set_error("assign_fast: unsupported chunk %d", pl.kc); return SKM_ERR_UNSUPPORTED;
         }
         if (rc != SKM_OK) return rc;

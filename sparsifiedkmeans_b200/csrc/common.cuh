@@ -125,6 +125,7 @@ struct skm_dataset {
     int32_t *unit_row;
     int64_t *unit_start;                // [2*nunits]: starts then ends; a unit never crosses a row
     int64_t  nunits;
+    unsigned long long *unit_counter;   // device counter K2 pulls work units from
     // k-means++ running minimum distance (allocated on first use)
     double  *kpp_mind;                  // [n]
     double  *kpp_cum;                   // [n] inclusive scan of mind^2

@@ -78,6 +78,7 @@ int skm_build_csr(skm_dataset *ds)
     ds->h_rowptr = nullptr;
     ds->unit_row = nullptr;
     ds->unit_start = nullptr;
+    ds->unit_counter = nullptr;
     ds->nunits = 0;
     if (n == 0 || p == 0 || nnz == 0 || ds->store_dtype != SKM_F32) return SKM_OK;
     if (n >= 2147483647LL) { skm_set_error("a shard may hold at most 2^31-1 columns"); return SKM_ERR_UNSUPPORTED; }
@@ -119,8 +120,10 @@ int skm_build_csr(skm_dataset *ds)
     SKM_CUDA(cudaStreamSynchronize(ctx->stream));
 
     // work list: rows cut into chunks sized so every resident warp gets several units
-    int64_t chunk = nnz / ((int64_t)ctx->sm_count * 64);
-    chunk = chunk < 2048 ? 2048 : (chunk > 65536 ? 65536 : chunk);
+    // (about 8 units per resident warp keeps the tail of the last wave short; K2 pulls units
+    // from an atomic counter, so long and short rows balance out)
+    int64_t chunk = nnz / ((int64_t)ctx->sm_count * 64 * 8);
+    chunk = chunk < 1024 ? 1024 : (chunk > 16384 ? 16384 : chunk);
     chunk = (chunk + 31) & ~(int64_t)31;
     std::vector<int32_t> urow;
     std::vector<int64_t> ustart;
@@ -138,6 +141,7 @@ int skm_build_csr(skm_dataset *ds)
         uend[u] = e2 < re ? e2 : re;
     }
     if (ds->nunits > 0) {
+        SKM_CUDA(cudaMalloc((void **)&ds->unit_counter, sizeof(unsigned long long)));
         SKM_CUDA(cudaMalloc((void **)&ds->unit_row, sizeof(int32_t) * ds->nunits));
         SKM_CUDA(cudaMalloc((void **)&ds->unit_start, sizeof(int64_t) * 2 * ds->nunits));
         SKM_CUDA(cudaMemcpyAsync(ds->unit_row, urow.data(), sizeof(int32_t) * ds->nunits, cudaMemcpyHostToDevice, ctx->stream));

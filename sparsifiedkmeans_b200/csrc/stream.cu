@@ -47,7 +47,7 @@ extern "C" int skm_lloyd_step_host(skm_ctx *ctx, int64_t p, int64_t n, const voi
                                    const double *centers, int64_t K, int has_gamma, double gamma_dist,
                                    double gamma_update, int ml_correction, int64_t chunk_cols,
                                    double *centers_out, int32_t *assign_out, double *dist_out,
-                                   skm_iter_stats *stats)
+                                   skm_iter_stats *stats, skm_reduce_fn reduce, void *reduce_user)
 {
     SKM_REQUIRE(ctx && jc && centers && centers_out, "NULL argument");
     SKM_CUDA(cudaSetDevice(ctx->device));
@@ -217,6 +217,11 @@ extern "C" int skm_lloyd_step_host(skm_ctx *ctx, int64_t p, int64_t n, const voi
         rechecked += nf;
     }
 
+    // ---- multi-GPU: the caller sums the partials over ranks on the compute stream ----
+    if (reduce) {
+        const int rrc = reduce(partials.ptr, npart, (void *)cs, reduce_user);
+        if (rrc != 0) { skm_set_error("skm_lloyd_step_host: the reduce callback failed (%d)", rrc); return SKM_ERR_CUDA; }
+    }
     // ---- K3 ----
     SKM_TRY(skm_launch_finalize(ctx, p, K, partials.as<double>(), gamma_update, ml_correction, dcen.as<double>(),
                                 dold.as<double>(), dstats.as<double>()));

@@ -93,16 +93,18 @@ template <typename AT>
 __global__ void k_accumulate_csr(int64_t p, int k0, int kb, int64_t nunits,
                                  const int32_t *__restrict__ unit_row, const int64_t *__restrict__ unit_start,
                                  const int2 *__restrict__ csr, const AT *__restrict__ assign_c,
-                                 double *__restrict__ S, double *__restrict__ N)
+                                 double *__restrict__ S, double *__restrict__ N, unsigned long long *__restrict__ next_unit)
 {
     extern __shared__ __align__(16) unsigned char acc_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     double *binS = reinterpret_cast<double *>(acc_raw) + (size_t)warp * kb * 32;
     int *binN = reinterpret_cast<int *>(reinterpret_cast<double *>(acc_raw) + (size_t)nw * kb * 32) + (size_t)warp * kb * 32;
     const int64_t *unit_end = unit_start + nunits;
-    int64_t u = (int64_t)blockIdx.x * nw + warp;
-    const int64_t ustride = (int64_t)gridDim.x * nw;
-    for (; u < nunits; u += ustride) {
+    for (;;) {
+        unsigned long long uu = 0;
+        if (lane == 0) uu = atomicAdd(next_unit, 1ULL);          // dynamic schedule: one unit per fetch
+        const int64_t u = (int64_t)__shfl_sync(0xffffffffu, uu, 0);
+        if (u >= nunits) break;
         for (int k = 0; k < kb; ++k) { binS[k * 32 + lane] = 0.0; binN[k * 32 + lane] = 0; }
         const int64_t r = unit_row[u], s = unit_start[u], e = unit_end[u];
         int64_t i = s + lane;
@@ -294,8 +296,9 @@ static int accumulate_csr(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const 
     if (blocks > need) blocks = need;
     for (int64_t k0 = 0; k0 < K; k0 += kb) {
         const int kbb = (int)((K - k0) < kb ? (K - k0) : kb);
+        SKM_CUDA(cudaMemsetAsync(ds->unit_counter, 0, sizeof(unsigned long long), ctx->stream));
         kern<<<(unsigned)blocks, warps * 32, smem, ctx->stream>>>(p, (int)k0, kbb, ds->nunits, ds->unit_row, ds->unit_start,
-                                                               ds->csr, (const AT *)assign_c, S, N);
+                                                               ds->csr, (const AT *)assign_c, S, N, ds->unit_counter);
         SKM_CHECK_LAUNCH(ctx);
     }
     return SKM_OK;

@@ -372,10 +372,12 @@ class Lloyd:
 
 def lloyd_step_host(p: int, n: int, jc, ir, val, centers, gamma_dist, gamma_update: float,
                     ml_correction: bool = True, chunk_cols: int = 0, want_assign: bool = True,
-                    want_dist: bool = False, ctx: Context | None = None):
+                    want_dist: bool = False, ctx: Context | None = None, reduce=None):
     """One Lloyd iteration with X in HOST memory, streamed over PCIe in column chunks
     (skm_lloyd_step_host).  jc/ir/val are numpy arrays (int32/int64, float32/float64; pinned
-    memory overlaps best).  Returns (new_centers, assign 1-based or None, dist or None, IterStats)."""
+    memory overlaps best).  `reduce(tensor)` (optional) receives the partials as a torch float64
+    device tensor with the library stream current, for the multi-GPU all-reduce.
+    Returns (new_centers, assign 1-based or None, dist or None, IterStats)."""
     ctx = ctx or default_context()
     jc = np.ascontiguousarray(jc)
     ir = np.ascontiguousarray(ir)
@@ -391,11 +393,30 @@ def lloyd_step_host(p: int, n: int, jc, ir, val, centers, gamma_dist, gamma_upda
     a = np.empty(n, dtype=np.int32) if want_assign else None
     d = np.empty(n, dtype=np.float64) if want_dist else None
     st = _lib.IterStats()
+    cb = None
+    if reduce is not None:
+        import torch
+
+        def _cb(ptr, count, stream, _user):
+            try:
+                class _Raw:
+                    __cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False),
+                                                "version": 2, "strides": None}
+                t = torch.as_tensor(_Raw(), device=f"cuda:{ctx.device}")
+                with torch.cuda.stream(torch.cuda.ExternalStream(int(stream), device=f"cuda:{ctx.device}")):
+                    reduce(t)
+                return 0
+            except Exception:                      # never unwind through the C frame
+                import traceback
+                traceback.print_exc()
+                return 1
+        cb = _lib.REDUCE_FN(_cb)
     check(ctx._lib.skm_lloyd_step_host(
         ctx.handle, p, n, _ptr(jc), _NP_INDEX[jc.dtype], _ptr(ir), _NP_INDEX[ir.dtype], _ptr(val),
         _NP_VALUE[val.dtype], _ptr(c), K, int(gamma_dist is not None),
         float(gamma_dist if gamma_dist is not None else 0.0), float(gamma_update), int(ml_correction),
-        int(chunk_cols), _ptr(out_c), _ptr(a), _ptr(d), C.byref(st)))
+        int(chunk_cols), _ptr(out_c), _ptr(a), _ptr(d), C.byref(st),
+        C.cast(cb, C.c_void_p) if cb is not None else None, None))
     return out_c.reshape(K, p).T.copy(), a, d, Lloyd._stats(st)
 
 
