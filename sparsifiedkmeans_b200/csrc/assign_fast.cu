@@ -251,7 +251,8 @@ bool skm_fast_plan(const skm_ctx *ctx, int64_t p, int64_t K, FastPlan *plan)
 {
     const size_t budget = (size_t)ctx->smem_optin - 1024;
     int best = -1;
-    // smallest chunk that covers K in one launch and fits; else the largest that fits
+    // largest chunk whose table fits; then the smallest chunk that needs no more launches
+    // (K=64 with room for 48 centres takes two launches of 32, not 48 + 16)
     for (int kc : kKcOptions) {
         size_t bytes = (size_t)(p + 1) * stride_for(kc) * sizeof(float);
         if (bytes > budget) break;
@@ -259,6 +260,10 @@ bool skm_fast_plan(const skm_ctx *ctx, int64_t p, int64_t K, FastPlan *plan)
         if (kc >= K) break;
     }
     if (best < 0) return false;
+    const int launches = (int)((K + best - 1) / best);
+    for (int kc : kKcOptions) {
+        if ((K + kc - 1) / kc <= launches) { best = kc; break; }
+    }
     plan->kc = best;
     plan->ks = stride_for(best);
     plan->nchunks = (int)((K + best - 1) / best);

@@ -8,12 +8,14 @@
 // 1-byte assignment of each entry's column.
 //
 // Layout: csr[rowptr[r] .. rowptr[r+1]) holds (column, value-bits) pairs of row r, ordered by
-// column tile (tiles of CSR_TILE consecutive columns; order inside a tile is unspecified).
+// column tile (tiles of CSR_TILE = 512 consecutive columns; order inside a tile is unspecified).
 #include "common.cuh"
 #include <cub/device/device_scan.cuh>
 #include <vector>
 
-#define CSR_TILE 4096
+// small tiles keep a row's entries nearly column-sorted, so the 32 assignment gathers of a
+// warp in K2 touch a handful of cache lines instead of up to 32
+#define CSR_TILE 512
 
 namespace {
 

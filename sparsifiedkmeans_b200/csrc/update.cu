@@ -84,12 +84,13 @@ __global__ void k_count_sumsq(int64_t n, int64_t K, const int32_t *__restrict__ 
     }
 }
 
-// K2 over the row-major image: one warp per work unit (a run of one row's entries).  Every lane
-// owns a private column of bins [cluster][lane] in shared memory (fp64 sums, int counts), so
-// the read-modify-writes are conflict-free and need no atomics; the bins are folded across
-// lanes with a rotated read (also conflict-free) and leave the SM as one fp64 atomic per
-// (row, cluster, unit).
-template <typename AT>
+// K2 over the row-major image: one warp per work unit (a run of one row's entries).  Lanes own
+// private bin columns [cluster][BW] in shared memory (fp64 sums, int counts): with BW = 32
+// every lane has its own column and the read-modify-writes are conflict-free without atomics;
+// for larger K the columns are shared by 32/BW lanes, which take turns (BW shrinks so that
+// enough warps stay resident to hide the stream/gather latency).  The bins are folded across
+// columns with a rotated read and leave the SM as one fp64 atomic per (row, cluster, unit).
+template <typename AT, int BW>
 __global__ void k_accumulate_csr(int64_t p, int k0, int kb, int64_t nunits,
                                  const int32_t *__restrict__ unit_row, const int64_t *__restrict__ unit_start,
                                  const int2 *__restrict__ csr, const AT *__restrict__ assign_c,
@@ -97,30 +98,49 @@ __global__ void k_accumulate_csr(int64_t p, int k0, int kb, int64_t nunits,
 {
     extern __shared__ __align__(16) unsigned char acc_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    double *binS = reinterpret_cast<double *>(acc_raw) + (size_t)warp * kb * 32;
-    int *binN = reinterpret_cast<int *>(reinterpret_cast<double *>(acc_raw) + (size_t)nw * kb * 32) + (size_t)warp * kb * 32;
+    double *binS = reinterpret_cast<double *>(acc_raw) + (size_t)warp * kb * BW;
+    int *binN = reinterpret_cast<int *>(reinterpret_cast<double *>(acc_raw) + (size_t)nw * kb * BW) + (size_t)warp * kb * BW;
     const int64_t *unit_end = unit_start + nunits;
+    const int col = lane & (BW - 1);
+    constexpr int PHASES = 32 / BW;
+    const int my_phase = lane / BW;
+
+    auto add = [&](int a, int xbits) {
+        if (PHASES == 1) {
+            if ((unsigned)a < (unsigned)kb) { binS[a * BW + col] += (double)__int_as_float(xbits); binN[a * BW + col] += 1; }
+        } else {
+#pragma unroll
+            for (int ph = 0; ph < PHASES; ++ph) {
+                if (my_phase == ph && (unsigned)a < (unsigned)kb) {
+                    binS[a * BW + col] += (double)__int_as_float(xbits);
+                    binN[a * BW + col] += 1;
+                }
+                __syncwarp();
+            }
+        }
+    };
+
     for (;;) {
         unsigned long long uu = 0;
         if (lane == 0) uu = atomicAdd(next_unit, 1ULL);          // dynamic schedule: one unit per fetch
         const int64_t u = (int64_t)__shfl_sync(0xffffffffu, uu, 0);
         if (u >= nunits) break;
-        for (int k = 0; k < kb; ++k) { binS[k * 32 + lane] = 0.0; binN[k * 32 + lane] = 0; }
+        for (int i = lane; i < kb * BW; i += 32) { binS[i] = 0.0; binN[i] = 0; }
+        __syncwarp();
         const int64_t r = unit_row[u], s = unit_start[u], e = unit_end[u];
-        int64_t i = s + lane;
-        for (; i + 96 < e; i += 128) {
+        int64_t base = s;                                        // warp-uniform trip counts throughout
+        for (; base + 128 <= e; base += 128) {
+            const int64_t i = base + lane;
             const int2 q0 = __ldcs(csr + i), q1 = __ldcs(csr + i + 32), q2 = __ldcs(csr + i + 64), q3 = __ldcs(csr + i + 96);
             const int a0 = (int)__ldg(assign_c + q0.x) - k0, a1 = (int)__ldg(assign_c + q1.x) - k0;
             const int a2 = (int)__ldg(assign_c + q2.x) - k0, a3 = (int)__ldg(assign_c + q3.x) - k0;
-            if ((unsigned)a0 < (unsigned)kb) { binS[a0 * 32 + lane] += (double)__int_as_float(q0.y); binN[a0 * 32 + lane] += 1; }
-            if ((unsigned)a1 < (unsigned)kb) { binS[a1 * 32 + lane] += (double)__int_as_float(q1.y); binN[a1 * 32 + lane] += 1; }
-            if ((unsigned)a2 < (unsigned)kb) { binS[a2 * 32 + lane] += (double)__int_as_float(q2.y); binN[a2 * 32 + lane] += 1; }
-            if ((unsigned)a3 < (unsigned)kb) { binS[a3 * 32 + lane] += (double)__int_as_float(q3.y); binN[a3 * 32 + lane] += 1; }
+            add(a0, q0.y); add(a1, q1.y); add(a2, q2.y); add(a3, q3.y);
         }
-        for (; i < e; i += 32) {
-            const int2 q = __ldcs(csr + i);
-            const int a = (int)__ldg(assign_c + q.x) - k0;
-            if ((unsigned)a < (unsigned)kb) { binS[a * 32 + lane] += (double)__int_as_float(q.y); binN[a * 32 + lane] += 1; }
+        for (; base < e; base += 32) {
+            const int64_t ii = base + lane;
+            int a = -1, xb = 0;
+            if (ii < e) { const int2 q = __ldcs(csr + ii); a = (int)__ldg(assign_c + q.x) - k0; xb = q.y; }
+            add(a, xb);
         }
         __syncwarp();
         for (int kblk = 0; kblk < kb; kblk += 32) {
@@ -129,8 +149,8 @@ __global__ void k_accumulate_csr(int64_t p, int k0, int kb, int64_t nunits,
             int cnt = 0;
             if (k < kb) {
 #pragma unroll 8
-                for (int t = 0; t < 32; ++t) {
-                    const int idx = k * 32 + ((t + lane) & 31);
+                for (int t = 0; t < BW; ++t) {
+                    const int idx = k * BW + ((t + lane) & (BW - 1));
                     sum += binS[idx];
                     cnt += binN[idx];
                 }
@@ -264,6 +284,9 @@ __global__ void k_argmax_final(int nb, const double *__restrict__ bval, const in
 }  // namespace
 
 template <typename AT>
+static int accumulate_csr_bins(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const AT *assign_c, double *S, double *N);
+
+template <typename AT>
 static int accumulate_csr(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const int32_t *assign, void *assign_c,
                           const float *dist32, const double *dist64, double *partials)
 {
@@ -278,15 +301,22 @@ static int accumulate_csr(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const 
         k_count_sumsq<AT><<<(unsigned)blocks, 256, sm, ctx->stream>>>(n, K, assign, dist32, dist64, (AT *)assign_c, counts, sumsq);
         SKM_CHECK_LAUNCH(ctx);
     }
-    // bins: 12 bytes x 32 lanes per cluster per warp
+    return accumulate_csr_bins<AT>(ctx, ds, K, (const AT *)assign_c, S, N);
+}
+
+template <typename AT, int BW>
+static int launch_csr_bw(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const AT *assign_c, double *S, double *N)
+{
+    // bins: 12 bytes x BW columns per cluster per warp
+    const int64_t p = ds->p;
     const size_t budget = (size_t)ctx->smem_optin - 2048;
+    const size_t per_k = (size_t)12 * BW;
     int warps = 8;
-    while (warps > 1 && (size_t)warps * 384 * (size_t)(K < 32 ? K : 32) > budget) warps >>= 1;
-    int64_t kb = (int64_t)(budget / ((size_t)warps * 384));
+    while (warps > 1 && (size_t)warps * per_k * (size_t)(K < 32 ? K : 32) > budget) warps >>= 1;
+    int64_t kb = (int64_t)(budget / ((size_t)warps * per_k));
     if (kb > K) kb = K;
-    // prefer several resident blocks when the bins are small
-    const size_t smem = (size_t)warps * kb * 384;
-    auto kern = k_accumulate_csr<AT>;
+    const size_t smem = (size_t)warps * kb * per_k;
+    auto kern = k_accumulate_csr<AT, BW>;
     SKM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     SKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
@@ -298,10 +328,20 @@ static int accumulate_csr(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const 
         const int kbb = (int)((K - k0) < kb ? (K - k0) : kb);
         SKM_CUDA(cudaMemsetAsync(ds->unit_counter, 0, sizeof(unsigned long long), ctx->stream));
         kern<<<(unsigned)blocks, warps * 32, smem, ctx->stream>>>(p, (int)k0, kbb, ds->nunits, ds->unit_row, ds->unit_start,
-                                                               ds->csr, (const AT *)assign_c, S, N, ds->unit_counter);
+                                                               ds->csr, assign_c, S, N, ds->unit_counter);
         SKM_CHECK_LAUNCH(ctx);
     }
     return SKM_OK;
+}
+
+template <typename AT>
+static int accumulate_csr_bins(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const AT *assign_c, double *S, double *N)
+{
+    // shrink the bin width until roughly 32 warps fit on an SM
+    if (K <= 16) return launch_csr_bw<AT, 32>(ctx, ds, K, assign_c, S, N);
+    if (K <= 32) return launch_csr_bw<AT, 16>(ctx, ds, K, assign_c, S, N);
+    if (K <= 64) return launch_csr_bw<AT, 8>(ctx, ds, K, assign_c, S, N);
+    return launch_csr_bw<AT, 4>(ctx, ds, K, assign_c, S, N);
 }
 
 int skm_launch_accumulate(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const int32_t *assign, void *assign_c,
