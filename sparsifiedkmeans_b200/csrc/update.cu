@@ -129,6 +129,46 @@ __global__ void k_accumulate_csr(int64_t p, int k0, int kb, int64_t nunits,
         __syncwarp();
         const int64_t r = unit_row[u], s = unit_start[u], e = unit_end[u];
         int64_t base = s;                                        // warp-uniform trip counts throughout
+        if (PHASES == 1 && base + 128 <= e) {
+            // software pipeline: the next 4 stream loads are in flight while the current 4 entries
+            // are gathered and binned; entries of one lane that hit the same bin are merged in
+            // registers first, so the 4 read-modify-writes are independent (loads, adds, stores)
+            int2 n0 = __ldcs(csr + base + lane), n1 = __ldcs(csr + base + lane + 32);
+            int2 n2 = __ldcs(csr + base + lane + 64), n3 = __ldcs(csr + base + lane + 96);
+            for (; base + 128 <= e; base += 128) {
+                const int2 q0 = n0, q1 = n1, q2 = n2, q3 = n3;
+                int a0 = (int)__ldg(assign_c + q0.x) - k0, a1 = (int)__ldg(assign_c + q1.x) - k0;
+                int a2 = (int)__ldg(assign_c + q2.x) - k0, a3 = (int)__ldg(assign_c + q3.x) - k0;
+                if (base + 256 <= e) {
+                    const int64_t i2 = base + 128 + lane;
+                    n0 = __ldcs(csr + i2); n1 = __ldcs(csr + i2 + 32); n2 = __ldcs(csr + i2 + 64); n3 = __ldcs(csr + i2 + 96);
+                }
+                double x0 = (double)__int_as_float(q0.y), x1 = (double)__int_as_float(q1.y);
+                double x2 = (double)__int_as_float(q2.y), x3 = (double)__int_as_float(q3.y);
+                int c0 = 1, c1 = 1, c2 = 1, c3 = 1;
+                if ((unsigned)a0 >= (unsigned)kb) a0 = -1;
+                if ((unsigned)a1 >= (unsigned)kb) a1 = -1;
+                if ((unsigned)a2 >= (unsigned)kb) a2 = -1;
+                if ((unsigned)a3 >= (unsigned)kb) a3 = -1;
+                if (a3 >= 0 && a3 == a2) { x2 += x3; c2 += c3; a3 = -1; }
+                if (a3 >= 0 && a3 == a1) { x1 += x3; c1 += c3; a3 = -1; }
+                if (a3 >= 0 && a3 == a0) { x0 += x3; c0 += c3; a3 = -1; }
+                if (a2 >= 0 && a2 == a1) { x1 += x2; c1 += c2; a2 = -1; }
+                if (a2 >= 0 && a2 == a0) { x0 += x2; c0 += c2; a2 = -1; }
+                if (a1 >= 0 && a1 == a0) { x0 += x1; c0 += c1; a1 = -1; }
+                const int i0 = a0 * BW + col, i1 = a1 * BW + col, i2b = a2 * BW + col, i3 = a3 * BW + col;
+                double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+                int m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+                if (a0 >= 0) { s0 = binS[i0]; m0 = binN[i0]; }
+                if (a1 >= 0) { s1 = binS[i1]; m1 = binN[i1]; }
+                if (a2 >= 0) { s2 = binS[i2b]; m2 = binN[i2b]; }
+                if (a3 >= 0) { s3 = binS[i3]; m3 = binN[i3]; }
+                if (a0 >= 0) { binS[i0] = s0 + x0; binN[i0] = m0 + c0; }
+                if (a1 >= 0) { binS[i1] = s1 + x1; binN[i1] = m1 + c1; }
+                if (a2 >= 0) { binS[i2b] = s2 + x2; binN[i2b] = m2 + c2; }
+                if (a3 >= 0) { binS[i3] = s3 + x3; binN[i3] = m3 + c3; }
+            }
+        }
         for (; base + 128 <= e; base += 128) {
             const int64_t i = base + lane;
             const int2 q0 = __ldcs(csr + i), q1 = __ldcs(csr + i + 32), q2 = __ldcs(csr + i + 64), q3 = __ldcs(csr + i + 96);
