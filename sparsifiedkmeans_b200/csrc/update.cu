@@ -129,7 +129,7 @@ __global__ void k_accumulate_csr(int64_t p, int k0, int kb, int64_t nunits,
         __syncwarp();
         const int64_t r = unit_row[u], s = unit_start[u], e = unit_end[u];
         int64_t base = s;                                        // warp-uniform trip counts throughout
-        if (PHASES == 1 && base + 128 <= e) {
+        if (base + 128 <= e) {
             // software pipeline: the next 4 stream loads are in flight while the current 4 entries
             // are gathered and binned; entries of one lane that hit the same bin are merged in
             // registers first, so the 4 read-modify-writes are independent (loads, adds, stores)
@@ -157,16 +157,22 @@ __global__ void k_accumulate_csr(int64_t p, int k0, int kb, int64_t nunits,
                 if (a2 >= 0 && a2 == a0) { x0 += x2; c0 += c2; a2 = -1; }
                 if (a1 >= 0 && a1 == a0) { x0 += x1; c0 += c1; a1 = -1; }
                 const int i0 = a0 * BW + col, i1 = a1 * BW + col, i2b = a2 * BW + col, i3 = a3 * BW + col;
-                double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-                int m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-                if (a0 >= 0) { s0 = binS[i0]; m0 = binN[i0]; }
-                if (a1 >= 0) { s1 = binS[i1]; m1 = binN[i1]; }
-                if (a2 >= 0) { s2 = binS[i2b]; m2 = binN[i2b]; }
-                if (a3 >= 0) { s3 = binS[i3]; m3 = binN[i3]; }
-                if (a0 >= 0) { binS[i0] = s0 + x0; binN[i0] = m0 + c0; }
-                if (a1 >= 0) { binS[i1] = s1 + x1; binN[i1] = m1 + c1; }
-                if (a2 >= 0) { binS[i2b] = s2 + x2; binN[i2b] = m2 + c2; }
-                if (a3 >= 0) { binS[i3] = s3 + x3; binN[i3] = m3 + c3; }
+#pragma unroll
+                for (int ph = 0; ph < PHASES; ++ph) {               // lanes sharing a bin column take turns
+                    if (PHASES == 1 || my_phase == ph) {
+                        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+                        int m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+                        if (a0 >= 0) { s0 = binS[i0]; m0 = binN[i0]; }
+                        if (a1 >= 0) { s1 = binS[i1]; m1 = binN[i1]; }
+                        if (a2 >= 0) { s2 = binS[i2b]; m2 = binN[i2b]; }
+                        if (a3 >= 0) { s3 = binS[i3]; m3 = binN[i3]; }
+                        if (a0 >= 0) { binS[i0] = s0 + x0; binN[i0] = m0 + c0; }
+                        if (a1 >= 0) { binS[i1] = s1 + x1; binN[i1] = m1 + c1; }
+                        if (a2 >= 0) { binS[i2b] = s2 + x2; binN[i2b] = m2 + c2; }
+                        if (a3 >= 0) { binS[i3] = s3 + x3; binN[i3] = m3 + c3; }
+                    }
+                    if (PHASES > 1) __syncwarp();
+                }
             }
         }
         for (; base + 128 <= e; base += 128) {

@@ -1,0 +1,127 @@
+#!/usr/bin/env python
+"""Stage benchmarks beside bench.py's headline: K4 (FWHT, FWHT+sample) over p (BASELINE.json
+configs[3]), K5 (k-means++ rounds, configs[4] shape), and dataset upload.  CUDA events on the
+library stream; CPU numbers are the reference's own hadamard.c / hadamard_pthreads.c
+(oracle/_ref) on a bounded sample.  Prints one JSON object per stage.
+
+    python tools/bench_stages.py [--quick]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def timed(ctx, ext, fn, reps):
+    import torch
+    fn()
+    ctx.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for _ in range(reps):
+        fn()
+    e1.record(ext)
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    import torch
+    from sparsifiedkmeans_b200 import Context, Dataset, fwht_f32_inplace
+    from sparsifiedkmeans_b200._lib import SKM_F32, SKM_I32, SKM_I64
+    dev = torch.device("cuda:0")
+    ctx = Context(0)
+    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    pk = peak()
+    budget = (1 if args.quick else 8) * (1 << 30)          # bytes of dense input per measurement
+
+    # ---- K4: FWHT in place and FWHT + fixed-count row sample, gamma = 0.05 ----
+    for p2 in (512, 4096, 32768):
+        n = min(1_000_000, budget // (4 * p2))
+        x = torch.randn(n, p2, device=dev)                  # column-major p2 x n
+        signs = torch.sign(torch.randn(p2, device=dev))
+        signs[signs == 0] = 1
+        ms = timed(ctx, ext, lambda: fwht_f32_inplace(p2, n, x.data_ptr(), signs.data_ptr(), ctx), 5)
+        gb = 2 * 4 * p2 * n / 1e9
+        out = {"stage": "K4 fwht_f32_inplace", "p2": p2, "n": n, "ms": ms, "GBps": gb / ms * 1e3, "frac_of_hbm_peak": gb / ms * 1e3 / pk,
+               "algorithmic_bytes": "read 4*p2 + write 4*p2 per column"}
+        print(json.dumps(out), flush=True)
+        m = max(1, int(round(0.05 * p2)))
+        keys = torch.rand(min(n, 200_000), p2, device=dev)
+        rows1 = keys.topk(m, dim=1, largest=False).indices.to(torch.int32)
+        del keys
+        rows = rows1.repeat((n + rows1.shape[0] - 1) // rows1.shape[0], 1)[:n].contiguous()
+        x.normal_()
+        holder = {}
+
+        def fused():
+            if "ds" in holder:
+                holder["ds"].close()
+            holder["ds"] = Dataset.from_fwht_sample(p2, n, m, x.data_ptr(), signs.data_ptr(), rows.data_ptr(), ctx=ctx)
+        t0 = time.perf_counter()
+        fused()
+        ctx.synchronize()
+        t_all = (time.perf_counter() - t0) * 1e3
+        ctx.timing_enable(True); ctx.timing_read()
+        fused(); ctx.synchronize()
+        ctx.timing_enable(False)
+        gb = (4 * p2 + 8 * m + 4 * m) * n / 1e9              # dense read + (row,val) write + sampled-row list read
+        out = {"stage": "K4 fwht_sample (incl. building the resident images)", "p2": p2, "n": n, "m": m, "ms_total_call": t_all,
+               "GBps_total_call": gb / t_all * 1e3}
+        print(json.dumps(out), flush=True)
+        holder["ds"].close()
+        del x, rows, rows1
+        torch.cuda.empty_cache()
+        if not args.no_cpu:
+            from oracle import refmex
+            ncpu = max(1, min(n, (256 << 20) // (8 * p2)))
+            xc = np.random.default_rng(0).standard_normal((p2, ncpu))
+            t0 = time.perf_counter(); refmex.hadamard(xc); t_ser = time.perf_counter() - t0
+            nthr = max([v for v in refmex.pthreads_variants() if v <= (os.cpu_count() or 1)] or [4])
+            t0 = time.perf_counter(); refmex.hadamard_pthreads(xc, nthr); t_par = time.perf_counter() - t0
+            gbc = 2 * 8 * p2 * ncpu / 1e9
+            print(json.dumps({"stage": "CPU reference hadamard.c / hadamard_pthreads.c (fp64)", "p2": p2, "n": ncpu,
+                              "serial_GBps": gbc / t_ser, "pthreads_GBps": gbc / t_par, "NTHREADS": nthr,
+                              "host_cores": os.cpu_count()}), flush=True)
+
+    # ---- K5: k-means++ rounds on configs[4]'s shape (n per GPU = 1e7/8, p=784, m=78) ----
+    sys.path.insert(0, ROOT)
+    import bench
+    n = 250_000 if args.quick else 1_250_000
+    colptr, rowidx, val, mu, start = bench.gen_shard_device(dev, n, 784, 78, 100, col0=0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ds = Dataset.from_device_csc(784, n, colptr.data_ptr(), SKM_I64, rowidx.data_ptr(), SKM_I32, val.data_ptr(), SKM_F32,
+                                 store="f32", ctx=ctx)
+    ctx.synchronize()
+    t_up = (time.perf_counter() - t0) * 1e3
+    print(json.dumps({"stage": "dataset build from device CSC (SELL banked + CSR)", "n": n, "nnz": n * 78, "ms": t_up,
+                      "M_entries_per_s": n * 78 / t_up / 1e3}), flush=True)
+    c = ds.get_column(0)
+    ms = timed(ctx, ext, lambda: ds.kpp_update(c, 78 / 784, first=False), 5)
+    print(json.dumps({"stage": "K5 kpp_update (one k-means++ round incl. D^2 block sums + host read-back)", "n": n, "ms": ms,
+                      "points_per_s": n / ms * 1e3, "GBps": n * (78 * 8 + 16) / 1e9 / ms * 1e3,
+                      "reference_cost": "round k recomputes k centre-passes (Arthur_initialization.m:39); here 1 per round"}), flush=True)
+    ds.close()
+
+
+if __name__ == "__main__":
+    main()
