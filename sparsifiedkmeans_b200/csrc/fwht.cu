@@ -122,12 +122,165 @@ int fwht_any(skm_ctx *ctx, int64_t m, int64_t n, T *x, const T *signs, T divide_
     return SKM_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// fp32 fast path.  Index bits of a column of length p2 = 32*E*W are split as
+//   [ warp w : log2 W | register slot j : log2 E | lane : 5 ]
+// so every global and shared access of a warp is 32 consecutive words (coalesced, conflict-free).
+// Stages over the j bits run in registers, stages over the lane bits with warp shuffles, and the
+// stages over the warp bits after ONE exchange through shared memory.  The stage order differs
+// from the reference's (1,2,4,...), which only matters for rounding: this path is compared to the
+// reference to tolerance; the fp64 path above is the bit-exact one.
+// ---------------------------------------------------------------------------------------------
+template <int E>
+__device__ __forceinline__ void wht_regs_and_lanes(float (&v)[E], int lane)
+{
+#pragma unroll
+    for (int h = 1; h < E; h <<= 1) {
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            if (!(j & h)) { const float a = v[j], b = v[j + h]; v[j] = a + b; v[j + h] = a - b; }
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const float other = __shfl_xor_sync(0xffffffffu, v[j], o);
+            v[j] = up ? other - v[j] : v[j] + other;
+        }
+    }
+}
+
+// one warp per column, p2 = 32*E
+template <int E>
+__global__ void __launch_bounds__(256) k_fwht_warp(int64_t n, float *__restrict__ x, const float *__restrict__ signs, float inv_scale_div)
+{
+    const int lane = threadIdx.x & 31;
+    int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t ncol_stride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    constexpr int P2 = 32 * E;
+    for (; col < n; col += ncol_stride) {
+        float *g = x + col * P2;
+        float v[E];
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const int idx = (j << 5) | lane;
+            float t = __ldcs(g + idx);
+            if (signs) t *= __ldg(signs + idx);
+            v[j] = t;
+        }
+        wht_regs_and_lanes<E>(v, lane);
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            float t = v[j];
+            if (inv_scale_div != 0.f) t = __fdiv_rn(t, inv_scale_div);
+            __stcs(g + ((j << 5) | lane), t);
+        }
+    }
+}
+
+// W warps per column (W = 2..32), p2 = 1024*W, one CTA works on one column at a time
+template <int W>
+__global__ void __launch_bounds__(32 * W) k_fwht_cta(int64_t n, float *__restrict__ x, const float *__restrict__ signs, float divide_by)
+{
+    extern __shared__ __align__(16) unsigned char fc_raw[];
+    float *s = reinterpret_cast<float *>(fc_raw);
+    constexpr int T = 32 * W, P2 = 1024 * W, G = 32 / W;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int64_t col = blockIdx.x; col < n; col += gridDim.x) {
+        float *g = x + col * P2;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int idx = (w << 10) | (j << 5) | lane;
+            float t = __ldcs(g + idx);
+            if (signs) t *= __ldg(signs + idx);
+            v[j] = t;
+        }
+        wht_regs_and_lanes<32>(v, lane);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s[(w << 10) | (j << 5) | lane] = v[j];
+        __syncthreads();
+        // stages over the warp bits: thread handles G groups of W elements 1024 apart
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+#pragma unroll
+            for (int jw = 0; jw < W; ++jw) v[i * W + jw] = s[(jw << 10) | (i * T + threadIdx.x)];
+        }
+#pragma unroll
+        for (int h = 1; h < W; h <<= 1) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                if (!((q % W) & h)) { const float a = v[q], b = v[q + h]; v[q] = a + b; v[q + h] = a - b; }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+#pragma unroll
+            for (int jw = 0; jw < W; ++jw) {
+                float t = v[i * W + jw];
+                if (divide_by != 0.f) t = __fdiv_rn(t, divide_by);
+                __stcs(g + ((jw << 10) | (i * T + threadIdx.x)), t);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int E>
+int launch_fwht_warp(skm_ctx *ctx, int64_t n, float *x, const float *signs, float divide_by)
+{
+    int64_t blocks = (n * 32 + 255) / 256;
+    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    k_fwht_warp<E><<<(unsigned)blocks, 256, 0, ctx->stream>>>(n, x, signs, divide_by);
+    SKM_CHECK_LAUNCH(ctx);
+    return SKM_OK;
+}
+
+template <int W>
+int launch_fwht_cta(skm_ctx *ctx, int64_t n, float *x, const float *signs, float divide_by)
+{
+    const size_t smem = (size_t)1024 * W * sizeof(float);
+    auto kern = k_fwht_cta<W>;
+    SKM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    SKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * W, smem));
+    if (per_sm < 1) per_sm = 1;
+    int64_t blocks = (int64_t)ctx->sm_count * per_sm;
+    if (blocks > n) blocks = n;
+    kern<<<(unsigned)blocks, 32 * W, smem, ctx->stream>>>(n, x, signs, divide_by);
+    SKM_CHECK_LAUNCH(ctx);
+    return SKM_OK;
+}
+
+// returns SKM_ERR_UNSUPPORTED when the size has no fast kernel (caller falls back)
+int fwht_f32_fast(skm_ctx *ctx, int64_t m, int64_t n, float *x, const float *signs, float divide_by)
+{
+    switch (m) {
+        case 32: return launch_fwht_warp<1>(ctx, n, x, signs, divide_by);
+        case 64: return launch_fwht_warp<2>(ctx, n, x, signs, divide_by);
+        case 128: return launch_fwht_warp<4>(ctx, n, x, signs, divide_by);
+        case 256: return launch_fwht_warp<8>(ctx, n, x, signs, divide_by);
+        case 512: return launch_fwht_warp<16>(ctx, n, x, signs, divide_by);
+        case 1024: return launch_fwht_warp<32>(ctx, n, x, signs, divide_by);
+        case 2048: return launch_fwht_cta<2>(ctx, n, x, signs, divide_by);
+        case 4096: return launch_fwht_cta<4>(ctx, n, x, signs, divide_by);
+        case 8192: return launch_fwht_cta<8>(ctx, n, x, signs, divide_by);
+        case 16384: return launch_fwht_cta<16>(ctx, n, x, signs, divide_by);
+        case 32768: return launch_fwht_cta<32>(ctx, n, x, signs, divide_by);
+        default: return SKM_ERR_UNSUPPORTED;
+    }
+}
+
 // One CTA per column: sign flip, full FWHT in shared memory, then keep exactly m_keep rows
 // (ascending) with value (h / sqrt(p2)) / (m_keep / p2).
 __global__ void k_fwht_sample(int64_t p2, int64_t n, int m_keep, const float *__restrict__ x,
                               const float *__restrict__ signs, const int32_t *__restrict__ rows,
                               int64_t *__restrict__ colptr, int32_t *__restrict__ rowidx,
-                              float *__restrict__ val)
+                              float *__restrict__ val, int *__restrict__ bad_flag)
 {
     extern __shared__ __align__(16) unsigned char fs_raw[];
     float *s = reinterpret_cast<float *>(fs_raw);
@@ -147,7 +300,8 @@ __global__ void k_fwht_sample(int64_t p2, int64_t n, int m_keep, const float *__
         const int32_t *rr = rows + col * (int64_t)m_keep;
         for (int i = threadIdx.x; i < m_keep; i += blockDim.x) {
             const int r = rr[i];
-            atomicOr(&bits[r >> 5], 1u << (r & 31));
+            if ((unsigned)r < (unsigned)P2) atomicOr(&bits[r >> 5], 1u << (r & 31));
+            else *bad_flag = 1;                        // reported by the caller; never corrupts memory
         }
         __syncthreads();
         // ordered compaction of the set bits
@@ -190,6 +344,11 @@ int skm_launch_fwht_f64(skm_ctx *ctx, int64_t m, int64_t n, double *x, const dou
 
 int skm_launch_fwht_f32(skm_ctx *ctx, int64_t m, int64_t n, float *x, const float *signs, float divide_by)
 {
+    if (n > 0) {
+        SkmTimed t(ctx, SKM_T_FWHT);
+        const int rc = fwht_f32_fast(ctx, m, n, x, signs, divide_by);
+        if (rc != SKM_ERR_UNSUPPORTED) return rc;
+    }
     return fwht_any<float>(ctx, m, n, x, signs, divide_by);
 }
 
@@ -215,8 +374,15 @@ int skm_launch_fwht_sample_f32(skm_ctx *ctx, int64_t p2, int64_t n, int64_t m, c
     if (per_sm < 1) per_sm = 1;
     int64_t blocks = (int64_t)ctx->sm_count * per_sm;
     if (blocks > n) blocks = n;
+    SKM_CUDA(cudaMemsetAsync(ctx->d_flag + 8, 0, sizeof(int), ctx->stream));
     k_fwht_sample<<<(unsigned)blocks, threads, smem, ctx->stream>>>(p2, n, (int)m, x, signs, rows, colptr,
-                                                                   rowidx, val);
+                                                                   rowidx, val, ctx->d_flag + 8);
     SKM_CHECK_LAUNCH(ctx);
+    SKM_CUDA(cudaMemcpyAsync(ctx->h_flag + 8, ctx->d_flag + 8, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SKM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_flag[8]) {
+        skm_set_error("fwht_sample: a sampled row index is outside [0, p2) (or rows repeat within a column)");
+        return SKM_ERR_INVALID;
+    }
     return SKM_OK;
 }

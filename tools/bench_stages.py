@@ -59,6 +59,7 @@ def main():
         x = torch.randn(n, p2, device=dev)                  # column-major p2 x n
         signs = torch.sign(torch.randn(p2, device=dev))
         signs[signs == 0] = 1
+        torch.cuda.synchronize()
         ms = timed(ctx, ext, lambda: fwht_f32_inplace(p2, n, x.data_ptr(), signs.data_ptr(), ctx), 5)
         gb = 2 * 4 * p2 * n / 1e9
         out = {"stage": "K4 fwht_f32_inplace", "p2": p2, "n": n, "ms": ms, "GBps": gb / ms * 1e3, "frac_of_hbm_peak": gb / ms * 1e3 / pk,
@@ -70,6 +71,7 @@ def main():
         del keys
         rows = rows1.repeat((n + rows1.shape[0] - 1) // rows1.shape[0], 1)[:n].contiguous()
         x.normal_()
+        torch.cuda.synchronize()                            # torch's stream and the library's are independent
         holder = {}
 
         def fused():
