@@ -271,6 +271,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"           # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     cfg = CONFIGS[args.config]
     n, p, K, m = (args.n or cfg["n"]), cfg["p"], cfg["K"], cfg["m"]

@@ -62,6 +62,8 @@ extern "C" int skm_ctx_create(int device, void *cuda_stream, skm_ctx **out)
     ctx->d_flag = nullptr;
     ctx->h_flag = nullptr;
     ctx->timing = false;
+    ctx->stream_cache = nullptr;
+    ctx->stream_cache_free = nullptr;
     ctx->ev = nullptr;
     memset(ctx->ev_count, 0, sizeof ctx->ev_count);
     if (cudaMalloc((void **)&ctx->d_flag, 16 * sizeof(int)) != cudaSuccess ||
@@ -79,6 +81,7 @@ extern "C" void skm_ctx_destroy(skm_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream_cache && ctx->stream_cache_free) ctx->stream_cache_free(ctx->stream_cache);
     if (ctx->d_flag) cudaFree(ctx->d_flag);
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
     if (ctx->ev) {

@@ -62,6 +62,8 @@ struct skm_ctx {
     bool         timing;
     cudaEvent_t (*ev)[SKM_T_RING][2];   // [SKM_T_SLOTS][SKM_T_RING][2], created lazily
     int          ev_count[SKM_T_SLOTS];
+    void        *stream_cache;              // staging buffers of skm_lloyd_step_host, reused across calls
+    void       (*stream_cache_free)(void *);
 };
 
 // RAII: records a start event now and a stop event at scope exit when timing is enabled

@@ -375,6 +375,7 @@ int skm_launch_fwht_sample_f32(skm_ctx *ctx, int64_t p2, int64_t n, int64_t m, c
     int64_t blocks = (int64_t)ctx->sm_count * per_sm;
     if (blocks > n) blocks = n;
     SKM_CUDA(cudaMemsetAsync(ctx->d_flag + 8, 0, sizeof(int), ctx->stream));
+    SkmTimed timed(ctx, SKM_T_FWHT);
     k_fwht_sample<<<(unsigned)blocks, threads, smem, ctx->stream>>>(p2, n, (int)m, x, signs, rows, colptr,
                                                                    rowidx, val, ctx->d_flag + 8);
     SKM_CHECK_LAUNCH(ctx);

@@ -9,6 +9,7 @@
 // end.  Results are identical to the resident path's (same kernels, same exactness guard).
 #include "common.cuh"
 #include <algorithm>
+#include <new>
 #include <vector>
 
 namespace {
@@ -32,6 +33,19 @@ __global__ void k_publish(int64_t n, const int32_t *__restrict__ a, const float 
         if (d64) d64[j] = (double)d[j];
     }
 }
+
+// everything skm_lloyd_step_host allocates, kept in the context between calls (cudaMalloc /
+// cudaFree of gigabytes per call is slow and synchronises the device)
+struct StreamCache {
+    int64_t p = -1, K = -1, chunk_cols = -1, cap_nnz = -1, cap_sell = -1;
+    int jc_type = -1, ir_type = -1, val_type = -1, want_assign = -1, want_dist = -1, table_floats = -1;
+    DevBuf dcen, dold, ct, table, cmax, partials, dstats, best2;
+    Slot slots[2];
+    cudaStream_t copy_stream = nullptr;
+    ~StreamCache() { if (copy_stream) cudaStreamDestroy(copy_stream); }
+};
+
+void free_stream_cache(void *p) { delete (StreamCache *)p; }
 
 size_t tsize(int t) { return (t == SKM_F32 || t == SKM_I32) ? 4 : 8; }
 
@@ -71,46 +85,67 @@ extern "C" int skm_lloyd_step_host(skm_ctx *ctx, int64_t p, int64_t n, const voi
     chunk_cols = (chunk_cols + 31) & ~(int64_t)31;
     const int64_t cap_nnz = (int64_t)(avg * chunk_cols * 1.5) + 4096;
     const int64_t cap_sell = cap_nnz / 2 + 32 * (chunk_cols / 32 + 1) * 2;      // int4 units
+    (void)0;
 
-    // ---- per-call device state ----
+    // ---- device state: reused from the previous call when the shapes match ----
     const int64_t npart = 2 * p * K + K + 1;
-    DevBuf dcen, dold, ct, table, cmax, partials, dstats, best2;
-    SKM_TRY(dcen.alloc(sizeof(double) * p * K));
-    SKM_TRY(dold.alloc(sizeof(double) * p * K));
-    SKM_TRY(ct.alloc(sizeof(double) * (p + 1) * K));
-    SKM_TRY(table.alloc(sizeof(float) * (size_t)(p + 1) * pl.ks * pl.nchunks));
-    SKM_TRY(cmax.alloc(16));
-    SKM_TRY(partials.alloc(sizeof(double) * npart));
-    SKM_TRY(dstats.alloc(sizeof(double) * 8));
-    if (pl.nchunks > 1) SKM_TRY(best2.alloc(sizeof(float) * 2 * chunk_cols));
-    cudaStream_t copy_stream;
-    SKM_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-    struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sg{copy_stream};
-
-    Slot slots[2];
-    const int64_t nsl = chunk_cols / 32 + 1;
-    for (Slot &s : slots) {
-        if (jc_type != SKM_I64 || true) SKM_TRY(s.raw_jc.alloc(tsize(jc_type) * (chunk_cols + 1)));
-        if (ir_type != SKM_I32) SKM_TRY(s.raw_ir.alloc(tsize(ir_type) * cap_nnz));
-        if (val_type != SKM_F32) SKM_TRY(s.raw_val.alloc(tsize(val_type) * cap_nnz));
-        SKM_TRY(s.colptr.alloc(sizeof(int64_t) * (chunk_cols + 1)));
-        SKM_TRY(s.rowidx.alloc(sizeof(int32_t) * cap_nnz));
-        SKM_TRY(s.val.alloc(sizeof(float) * cap_nnz));
-        SKM_TRY(s.sell.alloc(sizeof(int4) * cap_sell));
-        SKM_TRY(s.slice_ptr.alloc(sizeof(int64_t) * (nsl + 1)));
-        SKM_TRY(s.w2.alloc(sizeof(int32_t) * (nsl + 1)));
-        SKM_TRY(s.elems.alloc(sizeof(int64_t) * (nsl + 1)));
-        SKM_TRY(s.cub_tmp.alloc(skm_sell_scan_tmp_bytes(nsl) + 256));
-        SKM_TRY(s.assign.alloc(sizeof(int32_t) * chunk_cols));
-        SKM_TRY(s.dist.alloc(sizeof(float) * chunk_cols));
-        SKM_TRY(s.flagged.alloc(sizeof(int32_t) * chunk_cols));
-        SKM_TRY(s.nflag.alloc(16));
-        SKM_TRY(s.flags.alloc(16));
-        if (assign_out) SKM_TRY(s.out_assign.alloc(sizeof(int32_t) * chunk_cols));
-        if (dist_out) SKM_TRY(s.out_dist.alloc(sizeof(double) * chunk_cols));
-        SKM_CUDA(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
-        SKM_CUDA(cudaEventCreateWithFlags(&s.free_ev, cudaEventDisableTiming));
+    const int table_floats = (int)((p + 1) * pl.ks * pl.nchunks);
+    StreamCache *sc = (StreamCache *)ctx->stream_cache;
+    const bool reuse = sc && sc->p == p && sc->K == K && sc->chunk_cols == chunk_cols && sc->cap_nnz >= cap_nnz &&
+                       sc->cap_sell >= cap_sell && sc->jc_type == jc_type && sc->ir_type == ir_type &&
+                       sc->val_type == val_type && sc->want_assign >= (assign_out != nullptr) &&
+                       sc->want_dist >= (dist_out != nullptr) && sc->table_floats == table_floats;
+    if (!reuse) {
+        if (sc) { SKM_CUDA(cudaStreamSynchronize(ctx->stream)); delete sc; ctx->stream_cache = nullptr; }
+        sc = new (std::nothrow) StreamCache();
+        if (!sc) { skm_set_error("out of host memory"); return SKM_ERR_NOMEM; }
+        ctx->stream_cache = sc;
+        ctx->stream_cache_free = free_stream_cache;
+        int rc = SKM_OK;
+        do {
+            if ((rc = sc->dcen.alloc(sizeof(double) * p * K))) break;
+            if ((rc = sc->dold.alloc(sizeof(double) * p * K))) break;
+            if ((rc = sc->ct.alloc(sizeof(double) * (p + 1) * K))) break;
+            if ((rc = sc->table.alloc(sizeof(float) * (size_t)table_floats))) break;
+            if ((rc = sc->cmax.alloc(16))) break;
+            if ((rc = sc->partials.alloc(sizeof(double) * npart))) break;
+            if ((rc = sc->dstats.alloc(sizeof(double) * 8))) break;
+            if (pl.nchunks > 1 && (rc = sc->best2.alloc(sizeof(float) * 2 * chunk_cols))) break;
+            if (cudaStreamCreateWithFlags(&sc->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = SKM_ERR_CUDA; skm_set_error("cudaStreamCreate failed"); break; }
+            const int64_t nsl = chunk_cols / 32 + 1;
+            for (Slot &s : sc->slots) {
+                if ((rc = s.raw_jc.alloc(tsize(jc_type) * (chunk_cols + 1)))) break;
+                if (ir_type != SKM_I32 && (rc = s.raw_ir.alloc(tsize(ir_type) * cap_nnz))) break;
+                if (val_type != SKM_F32 && (rc = s.raw_val.alloc(tsize(val_type) * cap_nnz))) break;
+                if ((rc = s.colptr.alloc(sizeof(int64_t) * (chunk_cols + 1)))) break;
+                if ((rc = s.rowidx.alloc(sizeof(int32_t) * cap_nnz))) break;
+                if ((rc = s.val.alloc(sizeof(float) * cap_nnz))) break;
+                if ((rc = s.sell.alloc(sizeof(int4) * cap_sell))) break;
+                if ((rc = s.slice_ptr.alloc(sizeof(int64_t) * (nsl + 1)))) break;
+                if ((rc = s.w2.alloc(sizeof(int32_t) * (nsl + 1)))) break;
+                if ((rc = s.elems.alloc(sizeof(int64_t) * (nsl + 1)))) break;
+                if ((rc = s.cub_tmp.alloc(skm_sell_scan_tmp_bytes(nsl) + 256))) break;
+                if ((rc = s.assign.alloc(sizeof(int32_t) * chunk_cols))) break;
+                if ((rc = s.dist.alloc(sizeof(float) * chunk_cols))) break;
+                if ((rc = s.flagged.alloc(sizeof(int32_t) * chunk_cols))) break;
+                if ((rc = s.nflag.alloc(16))) break;
+                if ((rc = s.flags.alloc(16))) break;
+                if (assign_out && (rc = s.out_assign.alloc(sizeof(int32_t) * chunk_cols))) break;
+                if (dist_out && (rc = s.out_dist.alloc(sizeof(double) * chunk_cols))) break;
+                if (cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&s.free_ev, cudaEventDisableTiming) != cudaSuccess) { rc = SKM_ERR_CUDA; skm_set_error("cudaEventCreate failed"); break; }
+            }
+        } while (0);
+        if (rc != SKM_OK) { delete sc; ctx->stream_cache = nullptr; return rc; }
+        sc->p = p; sc->K = K; sc->chunk_cols = chunk_cols; sc->cap_nnz = cap_nnz; sc->cap_sell = cap_sell;
+        sc->jc_type = jc_type; sc->ir_type = ir_type; sc->val_type = val_type;
+        sc->want_assign = assign_out != nullptr; sc->want_dist = dist_out != nullptr; sc->table_floats = table_floats;
     }
+    DevBuf &dcen = sc->dcen, &dold = sc->dold, &ct = sc->ct, &table = sc->table, &cmax = sc->cmax,
+           &partials = sc->partials, &dstats = sc->dstats, &best2 = sc->best2;
+    Slot *slots = sc->slots;
+    cudaStream_t copy_stream = sc->copy_stream;
+    slots[0].used = slots[1].used = false;
 
     cudaStream_t cs = ctx->stream;
     SKM_CUDA(cudaMemcpyAsync(dcen.ptr, centers, sizeof(double) * p * K, cudaMemcpyHostToDevice, cs));

@@ -84,10 +84,12 @@ def main():
         t_all = (time.perf_counter() - t0) * 1e3
         ctx.timing_enable(True); ctx.timing_read()
         fused(); ctx.synchronize()
+        k_ms = ctx.timing_read()["fwht"][0]
         ctx.timing_enable(False)
         gb = (4 * p2 + 8 * m + 4 * m) * n / 1e9              # dense read + (row,val) write + sampled-row list read
         out = {"stage": "K4 fwht_sample (incl. building the resident images)", "p2": p2, "n": n, "m": m, "ms_total_call": t_all,
-               "GBps_total_call": gb / t_all * 1e3}
+               "kernel_ms": k_ms, "kernel_GBps": gb / k_ms * 1e3 if k_ms else None, "kernel_frac_of_hbm_peak": gb / k_ms * 1e3 / pk if k_ms else None,
+               "algorithmic_bytes": "4*p2 read + 12*m (row list in, (row,val) out) per column"}
         print(json.dumps(out), flush=True)
         holder["ds"].close()
         del x, rows, rows1
