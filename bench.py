@@ -355,32 +355,42 @@ def run_ours(args):
     e2e = None
     if args.e2e_steps > 0:
         hj, hi, hv = h_colptr.numpy(), h_rowidx.numpy(), h_val.numpy()
-        h2d = hj.nbytes + hi.nbytes + hv.nbytes + start.nbytes
-        d2h = n_e2e * 4 + start.nbytes
-
         from sparsifiedkmeans_b200 import lloyd_step_host
+        # the same host matrix with 2-byte row indices (p <= 65536): the most compact format the ABI accepts
+        h_row16 = torch.empty(n_e2e * m, dtype=torch.uint16, pin_memory=True) if p <= 65536 else None
+        if h_row16 is not None:
+            h_row16.copy_(h_rowidx.to(torch.uint16))
+        red = (lambda t: dist.all_reduce(t)) if world > 1 else None
 
-        def e2e_step():
-            # stateless call: X in pinned host memory, streamed over PCIe in column chunks
-            newc, a, _, st2 = lloyd_step_host(p, n_e2e, hj, hi, hv, start, gamma, gamma, True,
-                                              want_assign=True, want_dist=False, ctx=ctx,
-                                              reduce=(lambda t: dist.all_reduce(t)) if world > 1 else None)
-            return a, newc
-        e2e_step()
-        fence()
-        ev0.record(ext)
-        for _ in range(args.e2e_steps):
+        def measure(rows_np, label):
+            def e2e_step():
+                # stateless call: X in pinned host memory, streamed over PCIe in column chunks
+                newc, a, _, st2 = lloyd_step_host(p, n_e2e, hj, rows_np, hv, start, gamma, gamma, True,
+                                                  want_assign=True, want_dist=False, ctx=ctx, reduce=red)
+                return a, newc
             e2e_step()
-        ev1.record(ext)
-        fence()
-        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e_ms = float(t.item()) / args.e2e_steps
-        e2e = {"value": world * n_e2e / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": e_ms, "columns_per_step": n_e2e,
-               "what": "lloyd_step_host: pinned host CSC (int64 colptr, int32 rows, fp32 values) streamed in chunks "
-                       "+ K1/K2/K3 + assignments and centres read back, every step"}
+            fence()
+            ev0.record(ext)
+            for _ in range(args.e2e_steps):
+                e2e_step()
+            ev1.record(ext)
+            fence()
+            tt = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e_ms = float(tt.item()) / args.e2e_steps
+            h2d = hj.nbytes + rows_np.nbytes + hv.nbytes + start.nbytes
+            d2h = n_e2e * 4 + start.nbytes
+            return {"value": world * n_e2e / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e_ms, "columns_per_step": n_e2e,
+                    "what": "lloyd_step_host: X in pinned host memory (int64 colptr, %s rows, fp32 values) streamed over "
+                            "PCIe in chunks + K1/K2/K3 + assignments and centres read back, every step" % label}
+        e2e_i32 = measure(hi, "int32")
+        if h_row16 is not None:
+            e2e = measure(h_row16.numpy(), "uint16")
+            e2e["int32_rows_variant"] = {k: e2e_i32[k] for k in ("value", "ms_per_step", "h2d_bytes_per_step")}
+        else:
+            e2e = e2e_i32
 
     if rank == 0:
         cpu = None

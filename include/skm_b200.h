@@ -58,6 +58,7 @@ extern "C" {
 #define SKM_F64 1
 #define SKM_I32 2
 #define SKM_I64 3   /* also used for MATLAB mwIndex (uint64 < 2^63) */
+#define SKM_U16 4   /* row indices only (p <= 65536): 2 bytes per entry over PCIe */
 
 typedef struct skm_ctx     skm_ctx;
 typedef struct skm_dataset skm_dataset;
@@ -123,7 +124,7 @@ typedef struct skm_dataset_info {
 } skm_dataset_info;
 
 /* Upload a p x n CSC matrix.  jc has n+1 entries of type jc_type (SKM_I32/SKM_I64),
- * ir has nnz entries of type ir_type, val has nnz entries of type val_type
+ * ir has nnz entries of type ir_type (SKM_I32/SKM_I64/SKM_U16), val has nnz entries of type val_type
  * (SKM_F32/SKM_F64).  on_device != 0: the three pointers are device pointers on
  * ctx's device (used when the data was produced on the GPU).
  * store_dtype SKM_F64 keeps doubles and every operation is bit-exact with the

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_lib", "libskm_b200.so")
 
 SKM_OK, SKM_ERR_INVALID, SKM_ERR_CUDA, SKM_ERR_NOMEM, SKM_ERR_UNSUPPORTED, SKM_ERR_STATE = range(6)
-SKM_F32, SKM_F64, SKM_I32, SKM_I64 = range(4)
+SKM_F32, SKM_F64, SKM_I32, SKM_I64, SKM_U16 = range(5)
 
 _i64 = C.c_int64
 _vp = C.c_void_p

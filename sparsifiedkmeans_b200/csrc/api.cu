@@ -176,7 +176,7 @@ static int d2h_sync(skm_ctx *ctx, void *dst, const void *src, size_t bytes)
 // ---------------------------------------------------------------------------
 // datasets
 // ---------------------------------------------------------------------------
-static size_t type_size(int t) { return (t == SKM_F32 || t == SKM_I32) ? 4 : 8; }
+static size_t type_size(int t) { return t == SKM_U16 ? 2 : ((t == SKM_F32 || t == SKM_I32) ? 4 : 8); }
 
 extern "C" void skm_dataset_destroy(skm_dataset *ds)
 {
@@ -224,7 +224,8 @@ extern "C" int skm_dataset_create_csc(skm_ctx *ctx, int64_t p, int64_t n, const 
     SKM_REQUIRE(p < 2147483647LL, "p must be below 2^31-1");
     SKM_REQUIRE(jc, "jc is NULL");
     SKM_REQUIRE(jc_type == SKM_I32 || jc_type == SKM_I64, "jc_type must be SKM_I32 or SKM_I64");
-    SKM_REQUIRE(ir_type == SKM_I32 || ir_type == SKM_I64, "ir_type must be SKM_I32 or SKM_I64");
+    SKM_REQUIRE(ir_type == SKM_I32 || ir_type == SKM_I64 || ir_type == SKM_U16, "ir_type must be SKM_I32, SKM_I64 or SKM_U16");
+    SKM_REQUIRE(ir_type != SKM_U16 || p <= 65536, "SKM_U16 row indices need p <= 65536");
     SKM_REQUIRE(val_type == SKM_F32 || val_type == SKM_F64, "val_type must be SKM_F32 or SKM_F64");
     SKM_REQUIRE(store_dtype == SKM_F32 || store_dtype == SKM_F64, "store_dtype must be SKM_F32 or SKM_F64");
 

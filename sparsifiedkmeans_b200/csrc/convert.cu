@@ -281,8 +281,11 @@ int skm_launch_convert_index(skm_ctx *ctx, const void *src, int src_type, int64_
     } else if (src_type == SKM_I32) {
         return dst_is_i64 ? convert<int32_t, int64_t>(ctx, src, dst, count)
                           : convert<int32_t, int32_t>(ctx, src, dst, count);
+    } else if (src_type == SKM_U16) {
+        return dst_is_i64 ? convert<uint16_t, int64_t>(ctx, src, dst, count)
+                          : convert<uint16_t, int32_t>(ctx, src, dst, count);
     }
-    skm_set_error("index type must be SKM_I32 or SKM_I64");
+    skm_set_error("index type must be SKM_I32, SKM_I64 or SKM_U16");
     return SKM_ERR_INVALID;
 }
 

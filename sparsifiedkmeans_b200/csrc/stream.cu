@@ -47,7 +47,7 @@ struct StreamCache {
 
 void free_stream_cache(void *p) { delete (StreamCache *)p; }
 
-size_t tsize(int t) { return (t == SKM_F32 || t == SKM_I32) ? 4 : 8; }
+size_t tsize(int t) { return t == SKM_U16 ? 2 : ((t == SKM_F32 || t == SKM_I32) ? 4 : 8); }
 
 int64_t host_index(const void *a, int type, int64_t i)
 {
@@ -67,7 +67,8 @@ extern "C" int skm_lloyd_step_host(skm_ctx *ctx, int64_t p, int64_t n, const voi
     SKM_CUDA(cudaSetDevice(ctx->device));
     SKM_REQUIRE(p >= 1 && n >= 0 && K >= 1, "bad dimensions");
     SKM_REQUIRE(jc_type == SKM_I32 || jc_type == SKM_I64, "jc_type must be SKM_I32 or SKM_I64");
-    SKM_REQUIRE(ir_type == SKM_I32 || ir_type == SKM_I64, "ir_type must be SKM_I32 or SKM_I64");
+    SKM_REQUIRE(ir_type == SKM_I32 || ir_type == SKM_I64 || ir_type == SKM_U16, "ir_type must be SKM_I32, SKM_I64 or SKM_U16");
+    SKM_REQUIRE(ir_type != SKM_U16 || p <= 65536, "SKM_U16 row indices need p <= 65536");
     SKM_REQUIRE(val_type == SKM_F32 || val_type == SKM_F64, "val_type must be SKM_F32 or SKM_F64");
     const int64_t nnz = host_index(jc, jc_type, n);
     SKM_REQUIRE(nnz >= 0 && host_index(jc, jc_type, 0) == 0, "invalid CSC column pointers");

@@ -11,10 +11,11 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import SKM_F32, SKM_F64, SKM_I32, SKM_I64, check
+from ._lib import SKM_F32, SKM_F64, SKM_I32, SKM_I64, SKM_U16, check
 
 _NP_INDEX = {np.dtype(np.int32): SKM_I32, np.dtype(np.int64): SKM_I64, np.dtype(np.uint64): SKM_I64}
 _NP_VALUE = {np.dtype(np.float32): SKM_F32, np.dtype(np.float64): SKM_F64}
+_NP_ROWS = {**_NP_INDEX, np.dtype(np.uint16): SKM_U16}      # row indices may also be uint16 (p <= 65536)
 
 
 def _ptr(a) -> int:
@@ -134,7 +135,7 @@ class Dataset:
         val = np.ascontiguousarray(val)
         if jc.dtype not in _NP_INDEX:
             jc = jc.astype(np.int64)
-        if ir.dtype not in _NP_INDEX:
+        if ir.dtype not in _NP_ROWS:
             ir = ir.astype(np.int64)
         if val.dtype not in _NP_VALUE:
             val = val.astype(np.float64)
@@ -142,7 +143,7 @@ class Dataset:
             raise ValueError("jc must have n+1 entries")
         h = C.c_void_p()
         check(ctx._lib.skm_dataset_create_csc(
-            ctx.handle, p, n, _ptr(jc), _NP_INDEX[jc.dtype], _ptr(ir), _NP_INDEX[ir.dtype],
+            ctx.handle, p, n, _ptr(jc), _NP_INDEX[jc.dtype], _ptr(ir), _NP_ROWS[ir.dtype],
             _ptr(val), _NP_VALUE[val.dtype], SKM_F32 if store == "f32" else SKM_F64, 0, C.byref(h)))
         return cls(ctx, h)
 
@@ -384,7 +385,7 @@ def lloyd_step_host(p: int, n: int, jc, ir, val, centers, gamma_dist, gamma_upda
     val = np.ascontiguousarray(val)
     if jc.dtype not in _NP_INDEX:
         jc = jc.astype(np.int64)
-    if ir.dtype not in _NP_INDEX:
+    if ir.dtype not in _NP_ROWS:
         ir = ir.astype(np.int64)
     if val.dtype not in _NP_VALUE:
         val = val.astype(np.float64)
@@ -412,7 +413,7 @@ def lloyd_step_host(p: int, n: int, jc, ir, val, centers, gamma_dist, gamma_upda
                 return 1
         cb = _lib.REDUCE_FN(_cb)
     check(ctx._lib.skm_lloyd_step_host(
-        ctx.handle, p, n, _ptr(jc), _NP_INDEX[jc.dtype], _ptr(ir), _NP_INDEX[ir.dtype], _ptr(val),
+        ctx.handle, p, n, _ptr(jc), _NP_INDEX[jc.dtype], _ptr(ir), _NP_ROWS[ir.dtype], _ptr(val),
         _NP_VALUE[val.dtype], _ptr(c), K, int(gamma_dist is not None),
         float(gamma_dist if gamma_dist is not None else 0.0), float(gamma_update), int(ml_correction),
         int(chunk_cols), _ptr(out_c), _ptr(a), _ptr(d), C.byref(st),

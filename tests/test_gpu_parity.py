@@ -243,7 +243,8 @@ def test_kpp_running_min_matches_reference(ctx):
 
 # ------------------------------------------------------------ streamed -----
 @pytest.mark.parametrize("K,p,m,chunk", [(5, 64, 8, 0), (10, 784, 78, 1024), (70, 128, 9, 512)])
-@pytest.mark.parametrize("dtypes", [(np.int32, np.int32, np.float32), (np.int64, np.int64, np.float64)])
+@pytest.mark.parametrize("dtypes", [(np.int32, np.int32, np.float32), (np.int64, np.int64, np.float64),
+                                    (np.int64, np.uint16, np.float32)])
 def test_streamed_host_iteration_matches_reference(ctx, K, p, m, chunk, dtypes):
     """skm_lloyd_step_host (X in host memory, chunks over PCIe) == resident path == oracle."""
     from sparsifiedkmeans_b200 import lloyd_step_host
@@ -268,3 +269,13 @@ def test_streamed_rejects_bad_rows(ctx):
     with pytest.raises(SkmError):
         lloyd_step_host(4, 2, np.array([0, 2, 3]), np.array([0, 9, 1]), np.array([1.0, 2.0, 3.0]), np.ones((4, 2)),
                         None, 1.0, ctx=ctx)
+
+
+def test_upload_accepts_uint16_rows(ctx):
+    from sparsifiedkmeans_b200 import Dataset
+    X, c, gamma = make_sparsified(p=300, n=700, m=20, K=4, seed=77)
+    ds = Dataset.from_csc(300, 700, X.indptr.astype(np.int32), X.indices.astype(np.uint16), X.data.astype(np.float32), ctx=ctx)
+    a, _ = ds.assign(c, gamma)
+    wa, _, _ = host_ref.find_cluster_assignments(X, c, gamma)
+    assert np.array_equal(a, wa)
+    ds.close()
