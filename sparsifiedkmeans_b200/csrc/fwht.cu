@@ -275,6 +275,187 @@ int fwht_f32_fast(skm_ctx *ctx, int64_t m, int64_t n, float *x, const float *sig
     }
 }
 
+// ---- fused precondition + row sample on the fast transform --------------------------------
+// After the transform the column sits in shared memory; the m sampled rows are marked in a
+// bitmap (one 32-bit word per lane / thread), an exclusive scan of the popcounts gives every
+// word its output offset, and the set bits are emitted in ascending row order as (row, value)
+// with value = (h / sqrt(p2)) / (m / p2)   (randsample_fixedNumberEntries.m:30-31,62).
+template <int E>
+__global__ void __launch_bounds__(256) k_fwht_sample_warp(int64_t n, int m_keep, const float *__restrict__ x,
+                                                          const float *__restrict__ signs, const int32_t *__restrict__ rows,
+                                                          int64_t *__restrict__ colptr, int32_t *__restrict__ rowidx,
+                                                          float *__restrict__ val, int *__restrict__ bad_flag)
+{
+    constexpr int P2 = 32 * E;
+    __shared__ float s_col[8][P2];
+    __shared__ uint32_t s_bits[8][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float *s = s_col[wib];
+    uint32_t *bits = s_bits[wib];
+    int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float root = sqrtf((float)P2), level = __fdiv_rn((float)m_keep, (float)P2);
+    for (; col < n; col += stride) {
+        const float *g = x + col * P2;
+        float v[E];
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const int idx = (j << 5) | lane;
+            v[j] = __ldcs(g + idx) * __ldg(signs + idx);
+        }
+        wht_regs_and_lanes<E>(v, lane);
+#pragma unroll
+        for (int j = 0; j < E; ++j) s[(j << 5) | lane] = v[j];
+        bits[lane] = 0u;
+        __syncwarp();
+        const int32_t *rr = rows + col * (int64_t)m_keep;
+        for (int i = lane; i < m_keep; i += 32) {
+            const int r = rr[i];
+            if ((unsigned)r < (unsigned)P2) atomicOr(&bits[r >> 5], 1u << (r & 31));
+            else *bad_flag = 1;
+        }
+        __syncwarp();
+        uint32_t b = lane < E ? bits[lane] : 0u;
+        const int cnt = __popc(b);
+        int off = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, off, o); if (lane >= o) off += t; }
+        const int total = __shfl_sync(0xffffffffu, off, 31);
+        if (total != m_keep) *bad_flag = 1;                 // repeated rows inside a column
+        int64_t out = col * (int64_t)m_keep + (off - cnt);
+        while (b) {
+            const int bit = __ffs(b) - 1;
+            b &= b - 1;
+            const int r = (lane << 5) + bit;
+            rowidx[out] = r;
+            val[out] = __fdiv_rn(__fdiv_rn(s[r], root), level);
+            ++out;
+        }
+        if (lane == 0) { colptr[col] = col * (int64_t)m_keep; if (col == n - 1) colptr[n] = n * (int64_t)m_keep; }
+        __syncwarp();
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(32 * W) k_fwht_sample_cta(int64_t n, int m_keep, const float *__restrict__ x,
+                                                            const float *__restrict__ signs, const int32_t *__restrict__ rows,
+                                                            int64_t *__restrict__ colptr, int32_t *__restrict__ rowidx,
+                                                            float *__restrict__ val, int *__restrict__ bad_flag)
+{
+    extern __shared__ __align__(16) unsigned char fsc_raw[];
+    constexpr int T = 32 * W, P2 = 1024 * W, G = 32 / W;
+    float *s = reinterpret_cast<float *>(fsc_raw);
+    uint32_t *bits = reinterpret_cast<uint32_t *>(s + P2);          // [T] one word per thread
+    int *wsum = reinterpret_cast<int *>(bits + T);                  // [W] warp totals
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const float root = sqrtf((float)P2), level = __fdiv_rn((float)m_keep, (float)P2);
+    for (int64_t col = blockIdx.x; col < n; col += gridDim.x) {
+        const float *g = x + col * P2;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int idx = (w << 10) | (j << 5) | lane;
+            v[j] = __ldcs(g + idx) * __ldg(signs + idx);
+        }
+        wht_regs_and_lanes<32>(v, lane);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s[(w << 10) | (j << 5) | lane] = v[j];
+        bits[threadIdx.x] = 0u;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+#pragma unroll
+            for (int jw = 0; jw < W; ++jw) v[i * W + jw] = s[(jw << 10) | (i * T + threadIdx.x)];
+        }
+#pragma unroll
+        for (int h = 1; h < W; h <<= 1) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                if (!((q % W) & h)) { const float a = v[q], b = v[q + h]; v[q] = a + b; v[q + h] = a - b; }
+            }
+        }
+        __syncthreads();                                            // everyone has read the old contents
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+#pragma unroll
+            for (int jw = 0; jw < W; ++jw) s[(jw << 10) | (i * T + threadIdx.x)] = v[i * W + jw];
+        }
+        const int32_t *rr = rows + col * (int64_t)m_keep;
+        for (int i = threadIdx.x; i < m_keep; i += T) {
+            const int r = rr[i];
+            if ((unsigned)r < (unsigned)P2) atomicOr(&bits[r >> 5], 1u << (r & 31));
+            else *bad_flag = 1;
+        }
+        __syncthreads();
+        uint32_t b = bits[threadIdx.x];
+        const int cnt = __popc(b);
+        int off = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, off, o); if (lane >= o) off += t; }
+        if (lane == 31) wsum[w] = off;
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int q = 0; q < W; ++q) { const int t = wsum[q]; if (q < w) before += t; total += t; }
+        if (threadIdx.x == 0 && total != m_keep) *bad_flag = 1;
+        int64_t out = col * (int64_t)m_keep + before + (off - cnt);
+        while (b) {
+            const int bit = __ffs(b) - 1;
+            b &= b - 1;
+            const int r = ((int)threadIdx.x << 5) + bit;
+            rowidx[out] = r;
+            val[out] = __fdiv_rn(__fdiv_rn(s[r], root), level);
+            ++out;
+        }
+        if (threadIdx.x == 0) { colptr[col] = col * (int64_t)m_keep; if (col == n - 1) colptr[n] = n * (int64_t)m_keep; }
+        __syncthreads();
+    }
+}
+
+template <int E>
+int launch_sample_warp(skm_ctx *ctx, int64_t n, int m, const float *x, const float *signs, const int32_t *rows,
+                       int64_t *colptr, int32_t *rowidx, float *val, int *bad)
+{
+    int64_t blocks = (n * 32 + 255) / 256;
+    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    k_fwht_sample_warp<E><<<(unsigned)blocks, 256, 0, ctx->stream>>>(n, m, x, signs, rows, colptr, rowidx, val, bad);
+    SKM_CHECK_LAUNCH(ctx);
+    return SKM_OK;
+}
+
+template <int W>
+int launch_sample_cta(skm_ctx *ctx, int64_t n, int m, const float *x, const float *signs, const int32_t *rows,
+                      int64_t *colptr, int32_t *rowidx, float *val, int *bad)
+{
+    const size_t smem = (size_t)1024 * W * sizeof(float) + (size_t)32 * W * 4 + (size_t)W * 4 + 16;
+    auto kern = k_fwht_sample_cta<W>;
+    SKM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    SKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * W, smem));
+    if (per_sm < 1) per_sm = 1;
+    int64_t blocks = (int64_t)ctx->sm_count * per_sm;
+    if (blocks > n) blocks = n;
+    kern<<<(unsigned)blocks, 32 * W, smem, ctx->stream>>>(n, m, x, signs, rows, colptr, rowidx, val, bad);
+    SKM_CHECK_LAUNCH(ctx);
+    return SKM_OK;
+}
+
+int fwht_sample_fast(skm_ctx *ctx, int64_t p2, int64_t n, int m, const float *x, const float *signs, const int32_t *rows,
+                     int64_t *colptr, int32_t *rowidx, float *val, int *bad)
+{
+#define SKM_SW(E) return launch_sample_warp<E>(ctx, n, m, x, signs, rows, colptr, rowidx, val, bad)
+#define SKM_SC(W) return launch_sample_cta<W>(ctx, n, m, x, signs, rows, colptr, rowidx, val, bad)
+    switch (p2) {
+        case 32: SKM_SW(1); case 64: SKM_SW(2); case 128: SKM_SW(4); case 256: SKM_SW(8); case 512: SKM_SW(16);
+        case 1024: SKM_SW(32);
+        case 2048: SKM_SC(2); case 4096: SKM_SC(4); case 8192: SKM_SC(8); case 16384: SKM_SC(16); case 32768: SKM_SC(32);
+        default: return SKM_ERR_UNSUPPORTED;
+    }
+#undef SKM_SW
+#undef SKM_SC
+}
+
 // One CTA per column: sign flip, full FWHT in shared memory, then keep exactly m_keep rows
 // (ascending) with value (h / sqrt(p2)) / (m_keep / p2).
 __global__ void k_fwht_sample(int64_t p2, int64_t n, int m_keep, const float *__restrict__ x,
@@ -375,10 +556,15 @@ int skm_launch_fwht_sample_f32(skm_ctx *ctx, int64_t p2, int64_t n, int64_t m, c
     int64_t blocks = (int64_t)ctx->sm_count * per_sm;
     if (blocks > n) blocks = n;
     SKM_CUDA(cudaMemsetAsync(ctx->d_flag + 8, 0, sizeof(int), ctx->stream));
-    SkmTimed timed(ctx, SKM_T_FWHT);
-    k_fwht_sample<<<(unsigned)blocks, threads, smem, ctx->stream>>>(p2, n, (int)m, x, signs, rows, colptr,
-                                                                   rowidx, val, ctx->d_flag + 8);
-    SKM_CHECK_LAUNCH(ctx);
+    {
+        SkmTimed timed(ctx, SKM_T_FWHT);
+        int rc = fwht_sample_fast(ctx, p2, n, (int)m, x, signs, rows, colptr, rowidx, val, ctx->d_flag + 8);
+        if (rc == SKM_ERR_UNSUPPORTED) {
+            k_fwht_sample<<<(unsigned)blocks, threads, smem, ctx->stream>>>(p2, n, (int)m, x, signs, rows, colptr,
+                                                                           rowidx, val, ctx->d_flag + 8);
+            SKM_CHECK_LAUNCH(ctx);
+        } else if (rc != SKM_OK) return rc;
+    }
     SKM_CUDA(cudaMemcpyAsync(ctx->h_flag + 8, ctx->d_flag + 8, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     SKM_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->h_flag[8]) {
