@@ -239,13 +239,19 @@ int   skm_mix_hadamard(skm_ctx *ctx, int64_t p, int64_t p2, int64_t n, const dou
                        const double *signs, int compute_dtype, double *y);
 
 /* Fused precondition + row sample, all on device, producing a resident dataset:
- * column j of the result keeps rows `rows[m*j .. m*j+m)` (0-based, distinct; any
- * order, sorted internally) of hadamard(D*x_j)/sqrt(p2), each divided by
- * (m/p2) (private/randsample_fixedNumberEntries.m:30-31,62).  x_dev is a device
- * pointer to a dense p2 x n float matrix (column-major); rows_dev a device
- * pointer to int32[m*n].  Exact zeros are kept as stored entries with value 0. */
+ * column j of the result keeps m distinct rows of hadamard(D*x_j)/sqrt(p2), each divided by
+ * (m/p2) (private/randsample_fixedNumberEntries.m:30-31,62).  x_dev is a device pointer to a
+ * dense p2 x n float matrix (column-major).  rows_dev: device int32[m*n], column j keeps
+ * rows[m*j .. m*j+m) (0-based, distinct, any order) -- or NULL, and the rows are drawn on the
+ * device: uniform without replacement (the contract of private/randsample_block.m:44-84) from
+ * Philox4x32-10 keyed by `seed` and counted by the GLOBAL column index col0 + j, so a column's
+ * sample does not depend on the sharding.  Exact zeros are kept as stored entries with value 0. */
 int   skm_fwht_sample_f32(skm_ctx *ctx, int64_t p2, int64_t n, int64_t m, const float *x_dev,
-                          const float *signs_dev, const int32_t *rows_dev, skm_dataset **out);
+                          const float *signs_dev, const int32_t *rows_dev, uint64_t seed, int64_t col0,
+                          skm_dataset **out);
+/* The row sets skm_fwht_sample_f32 draws for (seed, col0): rows_dev int32[m*n], ascending per column. */
+int   skm_sample_rows(skm_ctx *ctx, int64_t p2, int64_t n, int64_t m, uint64_t seed, int64_t col0,
+                      int32_t *rows_dev);
 /* In-place device FWHT of a dense p2 x n float matrix with sign flip and 1/sqrt(p2). */
 int   skm_fwht_f32_inplace(skm_ctx *ctx, int64_t p2, int64_t n, float *x_dev,
                            const float *signs_dev);

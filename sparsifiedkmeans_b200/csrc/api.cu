@@ -861,11 +861,22 @@ extern "C" int skm_fwht_f32_inplace(skm_ctx *ctx, int64_t p2, int64_t n, float *
     return skm_launch_fwht_f32(ctx, p2, n, x_dev, signs_dev, sqrtf((float)p2));
 }
 
-extern "C" int skm_fwht_sample_f32(skm_ctx *ctx, int64_t p2, int64_t n, int64_t m, const float *x_dev,
-                                   const float *signs_dev, const int32_t *rows_dev, skm_dataset **out)
+extern "C" int skm_sample_rows(skm_ctx *ctx, int64_t p2, int64_t n, int64_t m, uint64_t seed, int64_t col0,
+                               int32_t *rows_dev)
 {
     SKM_TRY(enter(ctx));
-    SKM_REQUIRE(x_dev && signs_dev && rows_dev && out, "NULL argument");
+    SKM_REQUIRE(rows_dev, "NULL argument");
+    SKM_TRY(skm_launch_sample_rows(ctx, p2, n, m, seed, col0, rows_dev));
+    SKM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SKM_OK;
+}
+
+extern "C" int skm_fwht_sample_f32(skm_ctx *ctx, int64_t p2, int64_t n, int64_t m, const float *x_dev,
+                                   const float *signs_dev, const int32_t *rows_dev, uint64_t seed, int64_t col0,
+                                   skm_dataset **out)
+{
+    SKM_TRY(enter(ctx));
+    SKM_REQUIRE(x_dev && signs_dev && out, "NULL argument");
     *out = nullptr;
     skm_dataset *ds = new (std::nothrow) skm_dataset();
     if (!ds) { skm_set_error("out of host memory"); return SKM_ERR_NOMEM; }
@@ -879,7 +890,7 @@ extern "C" int skm_fwht_sample_f32(skm_ctx *ctx, int64_t p2, int64_t n, int64_t 
         if ((rc = dev_alloc((void **)&ds->rowidx, sizeof(int32_t) * ds->nnz, "rowidx"))) break;
         if ((rc = dev_alloc(&ds->val, sizeof(float) * ds->nnz, "val"))) break;
         if (n == 0) { if ((rc = (cudaMemsetAsync(ds->colptr, 0, sizeof(int64_t), ctx->stream) == cudaSuccess) ? SKM_OK : SKM_ERR_CUDA)) break; }
-        if ((rc = skm_launch_fwht_sample_f32(ctx, p2, n, m, x_dev, signs_dev, rows_dev, ds->colptr, ds->rowidx,
+        if ((rc = skm_launch_fwht_sample_f32(ctx, p2, n, m, x_dev, signs_dev, rows_dev, seed, col0, ds->colptr, ds->rowidx,
                                              (float *)ds->val))) break;
         rc = dataset_finish(ds);
     } while (0);

@@ -230,8 +230,10 @@ int skm_launch_fwht_f64(skm_ctx *ctx, int64_t m, int64_t n, double *x_inplace,
 int skm_launch_fwht_f32(skm_ctx *ctx, int64_t m, int64_t n, float *x_inplace,
                         const float *signs /* nullable */, float divide_by /* 0 = none */);
 int skm_launch_fwht_sample_f32(skm_ctx *ctx, int64_t p2, int64_t n, int64_t m, const float *x,
-                               const float *signs, const int32_t *rows, int64_t *colptr,
-                               int32_t *rowidx, float *val);
+                               const float *signs, const int32_t *rows /* nullable: sample on device */,
+                               uint64_t seed, int64_t col0, int64_t *colptr, int32_t *rowidx, float *val);
+int skm_launch_sample_rows(skm_ctx *ctx, int64_t p2, int64_t n, int64_t m, uint64_t seed, int64_t col0,
+                           int32_t *rows_out);
 
 // kpp.cu
 int skm_launch_kpp_update(skm_ctx *ctx, const skm_dataset *ds, const double *c_scaled /* dev [p] */,

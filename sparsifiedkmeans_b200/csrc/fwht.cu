@@ -275,6 +275,88 @@ int fwht_f32_fast(skm_ctx *ctx, int64_t m, int64_t n, float *x, const float *sig
     }
 }
 
+// ---- on-device row sampler -------------------------------------------------------------------
+// Contract of private/randsample_fixedNumberEntries.m:44-63 / randsample_block.m:44-84: every
+// column keeps exactly m distinct rows, uniformly among all m-subsets.  MATLAB's generator is
+// closed source, so the draws come from Philox4x32-10 keyed by the seed and counted by
+// (global column, draw index, attempt): the sample of a column does not depend on how columns
+// are sharded over GPUs or scheduled over threads.
+__device__ __forceinline__ uint32_t philox_draw(uint64_t seed, uint64_t col, uint32_t draw, uint32_t attempt)
+{
+    uint32_t c0 = draw, c1 = attempt, c2 = (uint32_t)col, c3 = (uint32_t)(col >> 32);
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return c0;
+}
+
+// Marks m distinct uniformly random rows of [0, P2) in `bits` (P2/32 words, already zero).
+// `owner` is scratch of P2 ints shared by the T cooperating threads; barrier_any(pred) must
+// synchronise those T threads and return whether pred holds for any of them.  Draw i proposes
+// philox(seed; col, i, attempt) mod P2; among the draws proposing the same free row in a round
+// the smallest i wins, the others redraw -- a pure function of (seed, col), whatever the timing.
+template <class BarrierAny>
+__device__ __forceinline__ void mark_random_rows(uint32_t *bits, int *owner, int P2, int m, uint64_t seed, int64_t col,
+                                                 int tid, int T, BarrierAny barrier_any)
+{
+    for (int i = tid; i < P2; i += T) owner[i] = 0x7fffffff;
+    int draw = tid;
+    uint32_t attempt = 0;
+    bool pending = draw < m;
+    while (barrier_any(pending)) {
+        int r = -1;
+        if (pending) {
+            r = (int)(philox_draw(seed, (uint64_t)col, (uint32_t)draw, attempt) & (uint32_t)(P2 - 1));
+            if ((bits[r >> 5] >> (r & 31)) & 1u) { r = -1; ++attempt; }     // taken in an earlier round
+            else atomicMin(&owner[r], draw);
+        }
+        barrier_any(false);
+        if (pending && r >= 0) {
+            if (owner[r] == draw) {
+                atomicOr(&bits[r >> 5], 1u << (r & 31));
+                draw += T; attempt = 0; pending = draw < m;
+            } else ++attempt;
+        }
+    }
+}
+
+struct WarpBarrierAny { __device__ bool operator()(bool p) const { return __any_sync(0xffffffffu, p); } };
+struct CtaBarrierAny { __device__ bool operator()(bool p) const { return __syncthreads_or(p) != 0; } };
+
+// rows_out[col*m .. +m) = the sampled rows of global column col0+col, ascending
+__global__ void k_sample_rows(int P2, int64_t n, int m, uint64_t seed, int64_t col0, int32_t *__restrict__ rows_out)
+{
+    extern __shared__ __align__(16) unsigned char sr_raw[];
+    int *owner = reinterpret_cast<int *>(sr_raw);
+    const int nwords = P2 >> 5;
+    uint32_t *bits = reinterpret_cast<uint32_t *>(owner + P2);
+    int *scan = reinterpret_cast<int *>(bits + nwords);
+    const int T = blockDim.x;
+    for (int64_t col = blockIdx.x; col < n; col += gridDim.x) {
+        for (int w = threadIdx.x; w < nwords; w += T) bits[w] = 0u;
+        __syncthreads();
+        mark_random_rows(bits, owner, P2, m, seed, col0 + col, threadIdx.x, T, CtaBarrierAny());
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int run = 0;
+            for (int w = 0; w < nwords; ++w) { scan[w] = run; run += __popc(bits[w]); }
+        }
+        __syncthreads();
+        for (int w = threadIdx.x; w < nwords; w += T) {
+            uint32_t b = bits[w];
+            int64_t out = col * (int64_t)m + scan[w];
+            while (b) { const int bit = __ffs(b) - 1; b &= b - 1; rows_out[out++] = (w << 5) + bit; }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- fused precondition + row sample on the fast transform --------------------------------
 // After the transform the column sits in shared memory; the m sampled rows are marked in a
 // bitmap (one 32-bit word per lane / thread), an exclusive scan of the popcounts gives every
@@ -283,6 +365,7 @@ int fwht_f32_fast(skm_ctx *ctx, int64_t m, int64_t n, float *x, const float *sig
 template <int E>
 __global__ void __launch_bounds__(256) k_fwht_sample_warp(int64_t n, int m_keep, const float *__restrict__ x,
                                                           const float *__restrict__ signs, const int32_t *__restrict__ rows,
+                                                          uint64_t seed, int64_t col0,
                                                           int64_t *__restrict__ colptr, int32_t *__restrict__ rowidx,
                                                           float *__restrict__ val, int *__restrict__ bad_flag)
 {
@@ -296,6 +379,20 @@ __global__ void __launch_bounds__(256) k_fwht_sample_warp(int64_t n, int m_keep,
     const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const float root = sqrtf((float)P2), level = __fdiv_rn((float)m_keep, (float)P2);
     for (; col < n; col += stride) {
+        // the sample does not depend on the data: mark it first, while the column buffer is free
+        bits[lane] = 0u;
+        __syncwarp();
+        if (rows) {
+            const int32_t *rr = rows + col * (int64_t)m_keep;
+            for (int i = lane; i < m_keep; i += 32) {
+                const int r = rr[i];
+                if ((unsigned)r < (unsigned)P2) atomicOr(&bits[r >> 5], 1u << (r & 31));
+                else *bad_flag = 1;
+            }
+        } else {
+            mark_random_rows(bits, reinterpret_cast<int *>(s), P2, m_keep, seed, col0 + col, lane, 32, WarpBarrierAny());
+        }
+        __syncwarp();
         const float *g = x + col * P2;
         float v[E];
 #pragma unroll
@@ -306,14 +403,6 @@ __global__ void __launch_bounds__(256) k_fwht_sample_warp(int64_t n, int m_keep,
         wht_regs_and_lanes<E>(v, lane);
 #pragma unroll
         for (int j = 0; j < E; ++j) s[(j << 5) | lane] = v[j];
-        bits[lane] = 0u;
-        __syncwarp();
-        const int32_t *rr = rows + col * (int64_t)m_keep;
-        for (int i = lane; i < m_keep; i += 32) {
-            const int r = rr[i];
-            if ((unsigned)r < (unsigned)P2) atomicOr(&bits[r >> 5], 1u << (r & 31));
-            else *bad_flag = 1;
-        }
         __syncwarp();
         uint32_t b = lane < E ? bits[lane] : 0u;
         const int cnt = __popc(b);
@@ -339,6 +428,7 @@ __global__ void __launch_bounds__(256) k_fwht_sample_warp(int64_t n, int m_keep,
 template <int W>
 __global__ void __launch_bounds__(32 * W) k_fwht_sample_cta(int64_t n, int m_keep, const float *__restrict__ x,
                                                             const float *__restrict__ signs, const int32_t *__restrict__ rows,
+                                                            uint64_t seed, int64_t col0,
                                                             int64_t *__restrict__ colptr, int32_t *__restrict__ rowidx,
                                                             float *__restrict__ val, int *__restrict__ bad_flag)
 {
@@ -350,6 +440,19 @@ __global__ void __launch_bounds__(32 * W) k_fwht_sample_cta(int64_t n, int m_kee
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const float root = sqrtf((float)P2), level = __fdiv_rn((float)m_keep, (float)P2);
     for (int64_t col = blockIdx.x; col < n; col += gridDim.x) {
+        bits[threadIdx.x] = 0u;
+        __syncthreads();
+        if (rows) {
+            const int32_t *rr = rows + col * (int64_t)m_keep;
+            for (int i = threadIdx.x; i < m_keep; i += T) {
+                const int r = rr[i];
+                if ((unsigned)r < (unsigned)P2) atomicOr(&bits[r >> 5], 1u << (r & 31));
+                else *bad_flag = 1;
+            }
+        } else {
+            mark_random_rows(bits, reinterpret_cast<int *>(s), P2, m_keep, seed, col0 + col, threadIdx.x, T, CtaBarrierAny());
+        }
+        __syncthreads();
         const float *g = x + col * P2;
         float v[32];
 #pragma unroll
@@ -360,7 +463,6 @@ __global__ void __launch_bounds__(32 * W) k_fwht_sample_cta(int64_t n, int m_kee
         wht_regs_and_lanes<32>(v, lane);
 #pragma unroll
         for (int j = 0; j < 32; ++j) s[(w << 10) | (j << 5) | lane] = v[j];
-        bits[threadIdx.x] = 0u;
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < G; ++i) {
@@ -379,12 +481,6 @@ __global__ void __launch_bounds__(32 * W) k_fwht_sample_cta(int64_t n, int m_kee
         for (int i = 0; i < G; ++i) {
 #pragma unroll
             for (int jw = 0; jw < W; ++jw) s[(jw << 10) | (i * T + threadIdx.x)] = v[i * W + jw];
-        }
-        const int32_t *rr = rows + col * (int64_t)m_keep;
-        for (int i = threadIdx.x; i < m_keep; i += T) {
-            const int r = rr[i];
-            if ((unsigned)r < (unsigned)P2) atomicOr(&bits[r >> 5], 1u << (r & 31));
-            else *bad_flag = 1;
         }
         __syncthreads();
         uint32_t b = bits[threadIdx.x];
@@ -414,19 +510,19 @@ __global__ void __launch_bounds__(32 * W) k_fwht_sample_cta(int64_t n, int m_kee
 
 template <int E>
 int launch_sample_warp(skm_ctx *ctx, int64_t n, int m, const float *x, const float *signs, const int32_t *rows,
-                       int64_t *colptr, int32_t *rowidx, float *val, int *bad)
+                       uint64_t seed, int64_t col0, int64_t *colptr, int32_t *rowidx, float *val, int *bad)
 {
     int64_t blocks = (n * 32 + 255) / 256;
     const int64_t cap = (int64_t)ctx->sm_count * 8;
     if (blocks > cap) blocks = cap;
-    k_fwht_sample_warp<E><<<(unsigned)blocks, 256, 0, ctx->stream>>>(n, m, x, signs, rows, colptr, rowidx, val, bad);
+    k_fwht_sample_warp<E><<<(unsigned)blocks, 256, 0, ctx->stream>>>(n, m, x, signs, rows, seed, col0, colptr, rowidx, val, bad);
     SKM_CHECK_LAUNCH(ctx);
     return SKM_OK;
 }
 
 template <int W>
 int launch_sample_cta(skm_ctx *ctx, int64_t n, int m, const float *x, const float *signs, const int32_t *rows,
-                      int64_t *colptr, int32_t *rowidx, float *val, int *bad)
+                      uint64_t seed, int64_t col0, int64_t *colptr, int32_t *rowidx, float *val, int *bad)
 {
     const size_t smem = (size_t)1024 * W * sizeof(float) + (size_t)32 * W * 4 + (size_t)W * 4 + 16;
     auto kern = k_fwht_sample_cta<W>;
@@ -436,16 +532,16 @@ int launch_sample_cta(skm_ctx *ctx, int64_t n, int m, const float *x, const floa
     if (per_sm < 1) per_sm = 1;
     int64_t blocks = (int64_t)ctx->sm_count * per_sm;
     if (blocks > n) blocks = n;
-    kern<<<(unsigned)blocks, 32 * W, smem, ctx->stream>>>(n, m, x, signs, rows, colptr, rowidx, val, bad);
+    kern<<<(unsigned)blocks, 32 * W, smem, ctx->stream>>>(n, m, x, signs, rows, seed, col0, colptr, rowidx, val, bad);
     SKM_CHECK_LAUNCH(ctx);
     return SKM_OK;
 }
 
 int fwht_sample_fast(skm_ctx *ctx, int64_t p2, int64_t n, int m, const float *x, const float *signs, const int32_t *rows,
-                     int64_t *colptr, int32_t *rowidx, float *val, int *bad)
+                     uint64_t seed, int64_t col0, int64_t *colptr, int32_t *rowidx, float *val, int *bad)
 {
-#define SKM_SW(E) return launch_sample_warp<E>(ctx, n, m, x, signs, rows, colptr, rowidx, val, bad)
-#define SKM_SC(W) return launch_sample_cta<W>(ctx, n, m, x, signs, rows, colptr, rowidx, val, bad)
+#define SKM_SW(E) return launch_sample_warp<E>(ctx, n, m, x, signs, rows, seed, col0, colptr, rowidx, val, bad)
+#define SKM_SC(W) return launch_sample_cta<W>(ctx, n, m, x, signs, rows, seed, col0, colptr, rowidx, val, bad)
     switch (p2) {
         case 32: SKM_SW(1); case 64: SKM_SW(2); case 128: SKM_SW(4); case 256: SKM_SW(8); case 512: SKM_SW(16);
         case 1024: SKM_SW(32);
@@ -533,9 +629,27 @@ int skm_launch_fwht_f32(skm_ctx *ctx, int64_t m, int64_t n, float *x, const floa
     return fwht_any<float>(ctx, m, n, x, signs, divide_by);
 }
 
+int skm_launch_sample_rows(skm_ctx *ctx, int64_t p2, int64_t n, int64_t m, uint64_t seed, int64_t col0, int32_t *rows_out)
+{
+    if (p2 < 32 || (p2 & (p2 - 1)) != 0) { skm_set_error("sample_rows: p2 must be a power of two >= 32"); return SKM_ERR_INVALID; }
+    if (m < 1 || m > p2) { skm_set_error("sample_rows: need 1 <= m <= p2"); return SKM_ERR_INVALID; }
+    if (n == 0) return SKM_OK;
+    const int threads = (int)(p2 / 32 < 1024 ? (p2 / 32 < 32 ? 32 : p2 / 32) : 1024);
+    const size_t smem = (size_t)p2 * 4 + (size_t)(p2 / 32) * 8 + 16;
+    if (smem > (size_t)ctx->smem_optin) { skm_set_error("sample_rows: p2=%lld does not fit in shared memory", (long long)p2); return SKM_ERR_UNSUPPORTED; }
+    SKM_CUDA(cudaFuncSetAttribute(k_sample_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    SKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sample_rows, threads, smem));
+    int64_t blocks = (int64_t)ctx->sm_count * (per_sm < 1 ? 1 : per_sm);
+    if (blocks > n) blocks = n;
+    k_sample_rows<<<(unsigned)blocks, threads, smem, ctx->stream>>>((int)p2, n, (int)m, seed, col0, rows_out);
+    SKM_CHECK_LAUNCH(ctx);
+    return SKM_OK;
+}
+
 int skm_launch_fwht_sample_f32(skm_ctx *ctx, int64_t p2, int64_t n, int64_t m, const float *x,
-                               const float *signs, const int32_t *rows, int64_t *colptr,
-                               int32_t *rowidx, float *val)
+                               const float *signs, const int32_t *rows, uint64_t seed, int64_t col0,
+                               int64_t *colptr, int32_t *rowidx, float *val)
 {
     if (p2 < 2 || (p2 & (p2 - 1)) != 0) {
         skm_set_error("fwht_sample: p2 must be a power of two >= 2");
@@ -558,7 +672,11 @@ int skm_launch_fwht_sample_f32(skm_ctx *ctx, int64_t p2, int64_t n, int64_t m, c
     SKM_CUDA(cudaMemsetAsync(ctx->d_flag + 8, 0, sizeof(int), ctx->stream));
     {
         SkmTimed timed(ctx, SKM_T_FWHT);
-        int rc = fwht_sample_fast(ctx, p2, n, (int)m, x, signs, rows, colptr, rowidx, val, ctx->d_flag + 8);
+        int rc = fwht_sample_fast(ctx, p2, n, (int)m, x, signs, rows, seed, col0, colptr, rowidx, val, ctx->d_flag + 8);
+        if (rc == SKM_ERR_UNSUPPORTED && !rows) {
+            skm_set_error("fwht_sample: on-device row sampling needs 32 <= p2 <= 32768");
+            return SKM_ERR_UNSUPPORTED;
+        }
         if (rc == SKM_ERR_UNSUPPORTED) {
             k_fwht_sample<<<(unsigned)blocks, threads, smem, ctx->stream>>>(p2, n, (int)m, x, signs, rows, colptr,
                                                                            rowidx, val, ctx->d_flag + 8);

@@ -167,14 +167,16 @@ class Dataset:
         return cls(ctx, h)
 
     @classmethod
-    def from_fwht_sample(cls, p2: int, n: int, m: int, x_ptr: int, signs_ptr: int, rows_ptr: int,
-                         ctx: Context | None = None):
+    def from_fwht_sample(cls, p2: int, n: int, m: int, x_ptr: int, signs_ptr: int, rows_ptr: int | None,
+                         ctx: Context | None = None, seed: int = 0, col0: int = 0):
         """Fused precondition + row sample on the device (skm_fwht_sample_f32): x is a dense
         p2 x n float32 column-major device matrix, signs float32[p2], rows int32[m*n] (column j
-        keeps rows[m*j:m*j+m]).  The result is resident and ready for Lloyd iterations."""
+        keeps rows[m*j:m*j+m]); rows_ptr=None draws the rows on the device from (seed, col0 + j).
+        The result is resident and ready for Lloyd iterations."""
         ctx = ctx or default_context()
         h = C.c_void_p()
-        check(ctx._lib.skm_fwht_sample_f32(ctx.handle, p2, n, m, x_ptr, signs_ptr, rows_ptr, C.byref(h)))
+        check(ctx._lib.skm_fwht_sample_f32(ctx.handle, p2, n, m, x_ptr, signs_ptr, rows_ptr, int(seed), int(col0),
+                                           C.byref(h)))
         return cls(ctx, h)
 
     def to_scipy(self):
@@ -442,3 +444,9 @@ def fwht_f32_inplace(p2: int, n: int, x_ptr: int, signs_ptr: int | None, ctx: Co
     """In-place device FWHT of a dense p2 x n float32 matrix: sign flip, transform, /sqrt(p2)."""
     ctx = ctx or default_context()
     check(ctx._lib.skm_fwht_f32_inplace(ctx.handle, p2, n, x_ptr, signs_ptr))
+
+
+def sample_rows(p2: int, n: int, m: int, seed: int, col0: int, rows_ptr: int, ctx: Context | None = None):
+    """Write the row sets the on-device sampler draws for (seed, col0) into device int32[m*n]."""
+    ctx = ctx or default_context()
+    check(ctx._lib.skm_sample_rows(ctx.handle, p2, n, m, int(seed), int(col0), rows_ptr))

@@ -45,6 +45,7 @@ def test_fused_fwht_sample_matches_reference_pipeline(ctx, p2, n, m):
     xd = torch.from_numpy(np.ascontiguousarray(X.T)).to(dev)                   # column-major p2 x n
     sd = torch.from_numpy(d.astype(np.float32)).to(dev)
     rd = torch.from_numpy(np.ascontiguousarray(perm.T).astype(np.int32)).to(dev)
+    torch.cuda.synchronize()
     ds = Dataset.from_fwht_sample(p2, n, m, xd.data_ptr(), sd.data_ptr(), rd.data_ptr(), ctx=ctx)
     assert ds.nnz == n * m and ds.max_col_nnz == m
     want = host_ref.sample_fixed_entries(host_ref.mix_hadamard(X.astype(np.float64), d), rows)
@@ -163,3 +164,62 @@ def test_sharded_driver_on_one_gpu_equals_plain_loop(ctx):
     assert its == ref.iterations and np.array_equal(a, ref.assignments)
     np.testing.assert_allclose(eng.get_centers(), ref.centers, rtol=1e-6, atol=1e-9)
     eng.close(); ds.close()
+
+
+# ------------------------------------------------------------ on-device sampler ----
+@pytest.mark.parametrize("p2,m,n", [(64, 3, 4000), (512, 26, 3000), (1024, 102, 500), (4096, 205, 300), (32768, 1638, 40)])
+def test_device_row_sampler_contract(ctx, p2, m, n):
+    """randsample_block / randsample_fixedNumberEntries contract: exactly m distinct rows per column,
+    uniform over rows, reproducible from (seed, global column) whatever the sharding."""
+    import torch
+    from sparsifiedkmeans_b200 import sample_rows
+    dev = torch.device("cuda:0")
+    r = torch.empty(n * m, dtype=torch.int32, device=dev)
+    sample_rows(p2, n, m, seed=1234, col0=0, rows_ptr=r.data_ptr(), ctx=ctx)
+    rows = r.cpu().numpy().reshape(n, m)
+    assert rows.min() >= 0 and rows.max() < p2
+    assert np.all(np.diff(rows, axis=1) > 0)                         # ascending => distinct
+    # same seed again: identical; a shard starting at column 7 reproduces columns 7.. of the full run
+    r2 = torch.empty(n * m, dtype=torch.int32, device=dev)
+    sample_rows(p2, n, m, seed=1234, col0=0, rows_ptr=r2.data_ptr(), ctx=ctx)
+    assert torch.equal(r, r2)
+    k = min(20, n - 7)
+    r3 = torch.empty(k * m, dtype=torch.int32, device=dev)
+    sample_rows(p2, k, m, seed=1234, col0=7, rows_ptr=r3.data_ptr(), ctx=ctx)
+    assert np.array_equal(r3.cpu().numpy().reshape(k, m), rows[7:7 + k])
+    r4 = torch.empty(n * m, dtype=torch.int32, device=dev)
+    sample_rows(p2, n, m, seed=99, col0=0, rows_ptr=r4.data_ptr(), ctx=ctx)
+    assert not torch.equal(r, r4)
+    # uniformity: every row is kept with probability m/p2 (binomial tolerance, 6 sigma)
+    freq = np.bincount(rows.ravel(), minlength=p2)
+    mean = n * m / p2
+    assert np.max(np.abs(freq - mean)) < 6 * np.sqrt(mean * (1 - m / p2)) + 1
+    # two fixed rows co-occur like in a uniform m-subset: P(both) = m(m-1)/(p2(p2-1))
+    if p2 <= 512:
+        has0 = (rows == 0).any(axis=1)
+        has1 = (rows == 1).any(axis=1)
+        pboth = m * (m - 1) / (p2 * (p2 - 1))
+        assert abs(np.mean(has0 & has1) - pboth) < 6 * np.sqrt(pboth / n) + 2 / n
+
+
+def test_fused_sample_on_device_equals_explicit_rows(ctx):
+    import torch
+    from sparsifiedkmeans_b200 import Dataset, sample_rows
+    p2, n, m = 1024, 400, 51
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(8)
+    X = rng.standard_normal((p2, n)).astype(np.float32)
+    d = _signs(rng, p2)
+    xd = torch.from_numpy(np.ascontiguousarray(X.T)).to(dev)
+    sd = torch.from_numpy(d.astype(np.float32)).to(dev)
+    r = torch.empty(n * m, dtype=torch.int32, device=dev)
+    sample_rows(p2, n, m, seed=5, col0=100, rows_ptr=r.data_ptr(), ctx=ctx)
+    a = Dataset.from_fwht_sample(p2, n, m, xd.data_ptr(), sd.data_ptr(), None, ctx=ctx, seed=5, col0=100)
+    b = Dataset.from_fwht_sample(p2, n, m, xd.data_ptr(), sd.data_ptr(), r.data_ptr(), ctx=ctx)
+    A, B = a.to_scipy(), b.to_scipy()
+    assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices) and np.array_equal(A.data, B.data)
+    rows = r.cpu().numpy().reshape(n, m).T
+    want = host_ref.sample_fixed_entries(host_ref.mix_hadamard(X.astype(np.float64), d), rows)
+    assert np.array_equal(A.indices, want.indices)
+    assert np.max(np.abs(A.data - want.data)) <= 3e-5 * np.max(np.abs(want.data))
+    a.close(); b.close()
