@@ -252,6 +252,14 @@ int   skm_fwht_sample_f32(skm_ctx *ctx, int64_t p2, int64_t n, int64_t m, const 
 /* The row sets skm_fwht_sample_f32 draws for (seed, col0): rows_dev int32[m*n], ascending per column. */
 int   skm_sample_rows(skm_ctx *ctx, int64_t p2, int64_t n, int64_t m, uint64_t seed, int64_t col0,
                       int32_t *rows_dev);
+/* The whole precondition + sample stage of kmeans_sparsified.m:286-334 from a dense HOST matrix
+ * x (p x n column-major, x_type SKM_F32/SKM_F64, points are columns): column chunks cross PCIe
+ * on a copy stream, are zero-padded to p2 rows, scaled by (1+2*eps) (:292), cast to fp32 and run
+ * through the fused sign-flip + FWHT + /sqrt(p2) + on-device row sample (m rows, divided by
+ * m/p2) straight into a resident SKM_F32 dataset.  signs: host double[p2] of +-1. */
+int   skm_dataset_from_dense_host(skm_ctx *ctx, int64_t p, int64_t p2, int64_t n, const void *x, int x_type,
+                                  const double *signs, int64_t m, uint64_t seed, int64_t col0,
+                                  int64_t chunk_cols, skm_dataset **out);
 /* In-place device FWHT of a dense p2 x n float matrix with sign flip and 1/sqrt(p2). */
 int   skm_fwht_f32_inplace(skm_ctx *ctx, int64_t p2, int64_t n, float *x_dev,
                            const float *signs_dev);

@@ -93,6 +93,8 @@ SIGNATURES = {
     "skm_kpp_get_mindist": (_int, [_vp, _vp]),
     "skm_mix_hadamard": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _int, _vp]),
     "skm_fwht_sample_f32": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, C.c_uint64, _i64, C.POINTER(_vp)]),
+    "skm_dataset_from_dense_host": (_int, [_vp, _i64, _i64, _i64, _vp, _int, _vp, _i64, C.c_uint64, _i64, _i64,
+                                           C.POINTER(_vp)]),
     "skm_sample_rows": (_int, [_vp, _i64, _i64, _i64, C.c_uint64, _i64, _vp]),
     "skm_fwht_f32_inplace": (_int, [_vp, _i64, _i64, _vp, _vp]),
 }

@@ -899,6 +899,102 @@ extern "C" int skm_fwht_sample_f32(skm_ctx *ctx, int64_t p2, int64_t n, int64_t 
     return SKM_OK;
 }
 
+
+namespace {
+template <typename T>
+__global__ void k_pad_cast_scaled(int64_t p, int64_t p2, int64_t n, const T *__restrict__ x, double scale, float *__restrict__ y)
+{
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; idx < p2 * n; idx += stride) {
+        const int64_t col = idx / p2, r = idx % p2;
+        y[idx] = r < p ? (float)((double)x[col * p + r] * scale) : 0.f;
+    }
+}
+__global__ void k_fill_colptr(int64_t n, int64_t m, int64_t *__restrict__ colptr)
+{
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; j <= n; j += stride) colptr[j] = j * m;
+}
+}  // namespace
+
+// Whole precondition + sample pipeline from a dense HOST matrix (p x n column-major, points are
+// columns): chunks cross PCIe, are zero-padded to p2 rows, multiplied by (1+2*eps)
+// (kmeans_sparsified.m:292) and cast to fp32, then run through the fused sign-flip + FWHT +
+// on-device row sample kernel straight into the resident dataset.
+extern "C" int skm_dataset_from_dense_host(skm_ctx *ctx, int64_t p, int64_t p2, int64_t n, const void *x, int x_type,
+                                           const double *signs, int64_t m, uint64_t seed, int64_t col0,
+                                           int64_t chunk_cols, skm_dataset **out)
+{
+    SKM_TRY(enter(ctx));
+    SKM_REQUIRE(x && signs && out, "NULL argument");
+    *out = nullptr;
+    SKM_REQUIRE(x_type == SKM_F32 || x_type == SKM_F64, "x_type must be SKM_F32 or SKM_F64");
+    SKM_REQUIRE(p2 >= 32 && p2 <= 32768 && (p2 & (p2 - 1)) == 0 && p >= 1 && p <= p2, "need a power of two 32 <= p2 <= 32768 and p <= p2");
+    SKM_REQUIRE(m >= 1 && m <= p2 && n >= 0, "need 1 <= m <= p2");
+    const size_t xs = x_type == SKM_F32 ? 4 : 8;
+    if (chunk_cols <= 0) chunk_cols = std::max<int64_t>(1, (int64_t)(512LL << 20) / (int64_t)(p2 * 4));
+    chunk_cols = std::min<int64_t>(chunk_cols, std::max<int64_t>(n, 1));
+    skm_dataset *ds = new (std::nothrow) skm_dataset();
+    if (!ds) { skm_set_error("out of host memory"); return SKM_ERR_NOMEM; }
+    memset(ds, 0, sizeof *ds);
+    ds->ctx = ctx; ds->p = p2; ds->n = n; ds->nnz = n * m; ds->store_dtype = SKM_F32;
+    int rc = SKM_OK;
+    do {
+        if ((rc = dev_alloc((void **)&ds->colptr, sizeof(int64_t) * (n + 1), "colptr"))) break;
+        if ((rc = dev_alloc((void **)&ds->rowidx, sizeof(int32_t) * ds->nnz, "rowidx"))) break;
+        if ((rc = dev_alloc(&ds->val, sizeof(float) * ds->nnz, "val"))) break;
+        DevBuf raw[2], dense, dsign, scratch_colptr;
+        std::vector<float> s32(p2);
+        for (int64_t i = 0; i < p2; ++i) s32[i] = (float)signs[i];
+        if ((rc = dsign.alloc(sizeof(float) * p2))) break;
+        if ((rc = h2d(ctx, dsign.ptr, s32.data(), sizeof(float) * p2))) break;
+        if ((rc = raw[0].alloc(xs * p * chunk_cols)) || (rc = raw[1].alloc(xs * p * chunk_cols))) break;
+        if ((rc = dense.alloc(sizeof(float) * p2 * chunk_cols))) break;
+        if ((rc = scratch_colptr.alloc(sizeof(int64_t) * (chunk_cols + 1)))) break;
+        cudaStream_t copy_stream;
+        if (cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = SKM_ERR_CUDA; skm_set_error("cudaStreamCreate failed"); break; }
+        cudaEvent_t up[2], freed[2];
+        for (int i = 0; i < 2; ++i) { cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&freed[i], cudaEventDisableTiming); }
+        const double scale = 1.0 + 2.0 * 2.220446049250313e-16;
+        const int64_t nchunks = (n + chunk_cols - 1) / chunk_cols;
+        auto issue = [&](int64_t c) {
+            const int64_t j0 = c * chunk_cols, nc = std::min(chunk_cols, n - j0);
+            if (c >= 2) cudaStreamWaitEvent(copy_stream, freed[c & 1], 0);
+            cudaMemcpyAsync(raw[c & 1].ptr, (const char *)x + (size_t)j0 * p * xs, xs * p * nc, cudaMemcpyHostToDevice, copy_stream);
+            cudaEventRecord(up[c & 1], copy_stream);
+        };
+        if (nchunks > 0) issue(0);
+        for (int64_t c = 0; c < nchunks && rc == SKM_OK; ++c) {
+            if (c + 1 < nchunks) issue(c + 1);
+            const int64_t j0 = c * chunk_cols, nc = std::min(chunk_cols, n - j0);
+            cudaStreamWaitEvent(ctx->stream, up[c & 1], 0);
+            const int64_t blocks = std::min<int64_t>((p2 * nc + 255) / 256, (int64_t)ctx->sm_count * 32);
+            if (x_type == SKM_F32)
+                k_pad_cast_scaled<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>(p, p2, nc, raw[c & 1].as<float>(), scale, dense.as<float>());
+            else
+                k_pad_cast_scaled<double><<<(unsigned)blocks, 256, 0, ctx->stream>>>(p, p2, nc, raw[c & 1].as<double>(), scale, dense.as<float>());
+            ctx->launches++;
+            cudaEventRecord(freed[c & 1], ctx->stream);
+            rc = skm_launch_fwht_sample_f32(ctx, p2, nc, m, dense.as<float>(), dsign.as<float>(), nullptr, seed, col0 + j0,
+                                            scratch_colptr.as<int64_t>(), ds->rowidx + j0 * m, (float *)ds->val + j0 * m);
+        }
+        cudaStreamSynchronize(copy_stream);
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(up[i]); cudaEventDestroy(freed[i]); }
+        cudaStreamDestroy(copy_stream);
+        if (rc != SKM_OK) break;
+        k_fill_colptr<<<(unsigned)std::min<int64_t>((n + 256) / 256, (int64_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(n, m, ds->colptr);
+        ctx->launches++;
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { skm_set_error("precondition pipeline failed: %s", cudaGetErrorString(e)); rc = SKM_ERR_CUDA; break; }
+        rc = dataset_finish(ds);
+    } while (0);
+    if (rc != SKM_OK) { skm_dataset_destroy(ds); return rc; }
+    *out = ds;
+    return SKM_OK;
+}
+
 // ---------------------------------------------------------------------------
 // k-means++
 // ---------------------------------------------------------------------------

@@ -179,6 +179,24 @@ class Dataset:
                                            C.byref(h)))
         return cls(ctx, h)
 
+    @classmethod
+    def from_dense_host(cls, X, signs, m: int, seed: int = 0, col0: int = 0, chunk_cols: int = 0,
+                        ctx: Context | None = None):
+        """Precondition + sample a dense host matrix X (p x n, points are columns; float32 or
+        float64) on the GPU: zero-pad to p2 = len(signs), *(1+2eps), sign flip, FWHT, /sqrt(p2),
+        keep m rows per column drawn on the device from (seed, col0 + j), divide by m/p2."""
+        ctx = ctx or default_context()
+        X = np.asarray(X)
+        if X.dtype not in _NP_VALUE:
+            X = X.astype(np.float64)
+        p, n = X.shape
+        Xf = np.ascontiguousarray(X.T).reshape(-1)                 # column-major p x n
+        d = np.ascontiguousarray(signs, dtype=np.float64).reshape(-1)
+        h = C.c_void_p()
+        check(ctx._lib.skm_dataset_from_dense_host(ctx.handle, p, d.shape[0], n, _ptr(Xf), _NP_VALUE[Xf.dtype], _ptr(d),
+                                                   int(m), int(seed), int(col0), int(chunk_cols), C.byref(h)))
+        return cls(ctx, h)
+
     def to_scipy(self):
         """Download as a scipy CSC matrix (float64 values) -- for tests and small data."""
         import scipy.sparse as sp

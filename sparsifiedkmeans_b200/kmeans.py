@@ -37,7 +37,7 @@ _DEFAULTS = dict(
     unbiasedInitialization=True, denseCenters=False,
 )
 _EXTRA = dict(Seed=None, Signs=None, SampleRows=None, StartIndices=None, Store="f32", Device=0,
-              MixDtype="f64", nargout=5, Context=None)
+              MixDtype="f64", nargout=5, Context=None, Pipeline="auto")
 
 
 class KMeansError(RuntimeError):
@@ -186,7 +186,7 @@ def kmeans_sparsified(X=None, K=None, **opts):
             raise ValueError("Signs must have 2^nextpow2(p) entries")
     else:
         d = None
-    Xd = Xd * (1 + 2 * np.finfo(np.float64).eps)                                      # :281 / :292
+    scale_eps = 1 + 2 * np.finfo(np.float64).eps                                      # :281 / :292 (applied below)
 
     def mix(A):                                                                       # :295
         if d is None:
@@ -200,26 +200,47 @@ def kmeans_sparsified(X=None, K=None, **opts):
         Y = ops.hadamard(C, ctx) / math.sqrt(p2)
         return (d.reshape(-1, 1) * Y)[:p, :]
 
-    t1 = time.perf_counter()
-    Xm = mix(Xd)
-    OUTPUT["TimeToSketch"] = time.perf_counter() - t1
-
     small_p = max(1, matlab_round(o["SparsityLevel"] * p2))                           # :325-331
     gamma = small_p / p
-    t1 = time.perf_counter()
-    rows = o["SampleRows"]
-    if rows is None:
-        rows = randsample_block(rng, p2, small_p, n)
-    Xs = randsample_fixedNumberEntries(Xm, small_p, np.asarray(rows))                 # :334
-    del Xm
-    OUTPUT["TimeToSample"] = time.perf_counter() - t1
     display = str(o["Display"]).lower() if o["Display"] else "off"
+    pipeline = str(o["Pipeline"]).lower()
+    if pipeline == "auto":
+        # all-GPU precondition + sample when nothing pins the random rows and the sizes allow it
+        pipeline = "device" if (d is not None and o["SampleRows"] is None and 32 <= p2 <= 32768
+                                and o["Store"] == "f32") else "host"
+    if pipeline == "device":
+        if d is None or o["SampleRows"] is not None:
+            raise ValueError("Pipeline='device' needs the Hadamard sketch and on-device row sampling")
+        t1 = time.perf_counter()
+        seed = int(rng.integers(0, 2 ** 63 - 1))
+        ds = Dataset.from_dense_host(Xd, d, small_p, seed=seed, ctx=ctx)          # applies *(1+2eps) itself
+        OUTPUT["TimeToSketch"] = time.perf_counter() - t1
+        OUTPUT["TimeToSample"] = 0.0                                                  # fused into the sketch
+        Xs = None
+    else:
+        t1 = time.perf_counter()
+        Xm = mix(Xd * scale_eps)
+        OUTPUT["TimeToSketch"] = time.perf_counter() - t1
+        t1 = time.perf_counter()
+        rows = o["SampleRows"]
+        if rows is None:
+            rows = randsample_block(rng, p2, small_p, n)
+        Xs = randsample_fixedNumberEntries(Xm, small_p, np.asarray(rows))             # :334
+        del Xm
+        OUTPUT["TimeToSample"] = time.perf_counter() - t1
+        ds = Dataset.from_scipy(Xs, store=o["Store"], ctx=ctx)
+    OUTPUT["Pipeline"] = pipeline
     if display in ("iter", "final"):
         print(f"Randomly mixing of type {sketch}")
         print("Randomly taking %.1f%% of the data; actual dataset is %.1f%% sparse"
-              % (100 * gamma, 100 * Xs.nnz / (Xs.shape[0] * Xs.shape[1])))
+              % (100 * gamma, 100 * ds.nnz / (ds.p * max(ds.n, 1))))
 
-    ds = Dataset.from_scipy(Xs, store=o["Store"], ctx=ctx)
+    def columns(ind):
+        """dense p2 x len(ind) matrix of the sparsified columns `ind` (X(:,ind) in the reference)"""
+        if Xs is not None:
+            return np.asarray(Xs[:, ind].todense())
+        return np.stack([ds.get_column(int(j)) for j in ind], axis=1)
+
     ml = bool(o["MLcorrection"])
     g_dist = gamma if o["unbiasedDistance"] else None                                 # :369-373
     start = o["Start"]
@@ -237,9 +258,11 @@ def kmeans_sparsified(X=None, K=None, **opts):
                 s = start.lower()
                 if s == "sample":
                     ind = rng.choice(n, size=K, replace=False) if o["StartIndices"] is None else np.asarray(o["StartIndices"])
-                    centers = np.asarray(Xs[:, ind].todense())
+                    centers = columns(ind)
                     centers_sparse = True
                 elif s == "uniform":
+                    if Xs is None:
+                        raise NotImplementedError("Start='uniform' needs Pipeline='host'")
                     mn, mx = float(Xs.min()), float(Xs.max())
                     centers = (mx - mn) * rng.random((p2, K)) - mn                     # :390 (sign as in the reference)
                 elif s in ("arthur", "++", "kmeans++", "k-means++", "k-means-++"):
@@ -247,7 +270,7 @@ def kmeans_sparsified(X=None, K=None, **opts):
                         ind = np.asarray(o["StartIndices"], dtype=np.int64)
                     else:
                         ind = Arthur_initialization(ds, K, gamma if o["unbiasedInitialization"] else None, rng)
-                    centers = np.asarray(Xs[:, ind].todense())
+                    centers = columns(ind)
                     centers_sparse = True
                 else:
                     raise KMeansError('cannot handle other types of "Start" values')

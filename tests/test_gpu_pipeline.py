@@ -223,3 +223,44 @@ def test_fused_sample_on_device_equals_explicit_rows(ctx):
     assert np.array_equal(A.indices, want.indices)
     assert np.max(np.abs(A.data - want.data)) <= 3e-5 * np.max(np.abs(want.data))
     a.close(); b.close()
+
+
+def test_dense_host_pipeline_matches_reference_pipeline(ctx):
+    """skm_dataset_from_dense_host (chunked upload, pad, *(1+2eps), sign, FWHT, on-device sample) against
+    the oracle's mix + sample_fixed_entries with the rows the device sampler reports."""
+    import torch
+    from sparsifiedkmeans_b200 import Dataset, sample_rows
+    p, p2, n, m = 50, 64, 777, 6
+    rng = np.random.default_rng(12)
+    X = rng.standard_normal((p, n))
+    d = _signs(rng, p2)
+    ds = Dataset.from_dense_host(X, d, m, seed=42, col0=0, chunk_cols=100, ctx=ctx)       # 8 chunks
+    r = torch.empty(n * m, dtype=torch.int32, device="cuda:0")
+    sample_rows(p2, n, m, seed=42, col0=0, rows_ptr=r.data_ptr(), ctx=ctx)
+    rows = r.cpu().numpy().reshape(n, m).T
+    want = host_ref.sample_fixed_entries(host_ref.mix_hadamard(X * (1 + 2 * np.finfo(float).eps), d), rows)
+    got = ds.to_scipy()
+    assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+    assert np.max(np.abs(got.data - want.data)) <= 3e-6 * np.max(np.abs(want.data)) * 6
+    ds32 = Dataset.from_dense_host(X.astype(np.float32), d, m, seed=42, ctx=ctx)          # single chunk, fp32 input
+    assert np.array_equal(ds32.to_scipy().indices, want.indices)
+    ds.close(); ds32.close()
+
+
+def test_kmeans_sparsified_device_pipeline_is_the_default_and_reproducible(ctx):
+    from sparsifiedkmeans_b200 import kmeans_sparsified
+    Xr, lab, mu = _mixture(n=1500, p=100, K=4, seed=9)          # p is not a power of two: rows are padded to 128
+    kw = dict(Sparsify=True, SparsityLevel=0.1, SketchType="Hadamard", Replicates=2, Seed=5, Context=ctx)
+    IDX, C, SUMD, D, OUT = kmeans_sparsified(Xr, 4, **kw)
+    assert OUT["Pipeline"] == "device"
+    IDX2, C2, *_ = kmeans_sparsified(Xr, 4, **kw)
+    assert np.array_equal(IDX, IDX2) and np.array_equal(C, C2)
+    for k in range(4):
+        assert len(set(IDX[lab == k].tolist())) == 1
+    # gamma uses the ORIGINAL p while the sampler scales by p2 (kmeans_sparsified.m:326-329): centres come out scaled by p2/p
+    order = [int(IDX[lab == k][0]) - 1 for k in range(4)]
+    assert np.max(np.abs(C[order] * (100 / 128) - mu)) < 0.15
+    IDXh, Ch, *_ , OUTh = kmeans_sparsified(Xr, 4, Pipeline="host", **kw)
+    assert OUTh["Pipeline"] == "host"
+    for k in range(4):
+        assert len(set(IDXh[lab == k].tolist())) == 1
