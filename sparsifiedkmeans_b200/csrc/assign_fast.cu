@@ -93,13 +93,20 @@ __device__ __forceinline__ void step(float (&acc)[KC], const float *tab, int ks,
     }
 }
 
-template <int KC, int THREADS, int MINB>
+// GTAB = true: the centroid table is too large for shared memory (e.g. p2 = 32768) and is gathered
+// from global memory instead (it stays L2-resident; the kernel is then L2-bound, not HBM-bound).
+template <int KC, int THREADS, int MINB, bool GTAB = false>
 __global__ void __launch_bounds__(THREADS, MINB) k_assign_fast(const FastParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
-    float *tab = reinterpret_cast<float *>(smem_raw);
-    tma_stage(tab, P.table, P.table_bytes, &bar);
+    const float *tab;
+    if (GTAB) tab = P.table;
+    else {
+        float *stab = reinterpret_cast<float *>(smem_raw);
+        tma_stage(stab, P.table, P.table_bytes, &bar);
+        tab = stab;
+    }
 
     const int lane = threadIdx.x & 31;
     const int64_t warps_total = ((int64_t)gridDim.x * THREADS) >> 5;
@@ -217,10 +224,10 @@ __global__ void k_build_table(int64_t p, int64_t K, const double *__restrict__ c
     if ((threadIdx.x & 31) == 0 && mi > 0) atomicMax(reinterpret_cast<int *>(cmax), mi);
 }
 
-template <int KC, int THREADS, int MINB>
+template <int KC, int THREADS, int MINB, bool GTAB = false>
 int launch_fast(skm_ctx *ctx, const FastParams &P, size_t smem)
 {
-    auto kern = k_assign_fast<KC, THREADS, MINB>;
+    auto kern = k_assign_fast<KC, THREADS, MINB, GTAB>;
     SKM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     SKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
@@ -259,7 +266,17 @@ bool skm_fast_plan(const skm_ctx *ctx, int64_t p, int64_t K, FastPlan *plan)
         best = kc;
         if (kc >= K) break;
     }
-    if (best < 0) return false;
+    plan->global_table = false;
+    if (best < 0) {
+        // no chunk fits in shared memory: gather from global memory (L2) with a 16-centre chunk
+        plan->global_table = true;
+        plan->kc = K <= 4 ? 4 : (K <= 8 ? 8 : 16);
+        plan->ks = stride_for(plan->kc);
+        plan->nchunks = (int)((K + plan->kc - 1) / plan->kc);
+        plan->smem = 0;
+        plan->threads = 256;
+        return true;
+    }
     const int launches = (int)((K + best - 1) / best);
     for (int kc : kKcOptions) {
         if ((K + kc - 1) / kc <= launches) { best = kc; break; }
@@ -318,6 +335,15 @@ int skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const
         P.first = (c == 0);
         P.last = (c == pl.nchunks - 1);
         int rc;
+        if (pl.global_table) {
+            switch (pl.kc) {
+                case 4:  rc = launch_fast<4, 256, 4, true>(ctx, P, 0); break;
+                case 8:  rc = launch_fast<8, 256, 4, true>(ctx, P, 0); break;
+                default: rc = launch_fast<16, 256, 4, true>(ctx, P, 0); break;
+            }
+            if (rc != SKM_OK) return rc;
+            continue;
+        }
         switch (pl.kc) {
             case 4:  rc = launch_fast<4, 256, 4>(ctx, P, pl.smem); break;
             case 8:  rc = launch_fast<8, 256, 4>(ctx, P, pl.smem); break;

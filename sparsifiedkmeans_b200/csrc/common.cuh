@@ -207,6 +207,7 @@ struct FastPlan {
     int nchunks;      // launches per assignment pass
     size_t smem;      // dynamic shared memory per block
     int threads;
+    bool global_table; // table gathered from global memory (too large for shared memory)
 };
 bool skm_fast_plan(const skm_ctx *ctx, int64_t p, int64_t K, FastPlan *plan);
 int  skm_launch_build_table(skm_ctx *ctx, int64_t p, int64_t K, const double *ct, const FastPlan &pl,

@@ -75,7 +75,7 @@ extern "C" int skm_lloyd_step_host(skm_ctx *ctx, int64_t p, int64_t n, const voi
     SKM_REQUIRE(nnz == 0 || (ir && val), "ir/val are NULL but nnz > 0");
     FastPlan pl;
     if (!skm_fast_plan(ctx, p, K, &pl)) {
-        skm_set_error("skm_lloyd_step_host: centroid table (p=%lld) does not fit in shared memory", (long long)p);
+        skm_set_error("skm_lloyd_step_host: no assignment plan for p=%lld K=%lld", (long long)p, (long long)K);
         return SKM_ERR_UNSUPPORTED;
     }
 

@@ -65,6 +65,10 @@ class CudaShardEngine:
         self.L.accumulate()
         return self.L.partials_tensor()
 
+    # k-means++ support
+    def kpp_update(self, center, gamma, first): return self.ds.kpp_update(center, gamma, first)
+    def kpp_pick(self, target): return self.ds.kpp_pick(target)
+
     def close(self):
         self.L.close()
 
@@ -155,3 +159,83 @@ class ShardedLloyd:
             if st.has_nan:
                 raise RuntimeError("Found NaN in centers")
         return its, st
+
+
+def sharded_arthur_initialization(engine, K: int, gamma, n_total: int, lo: int, first: int, uniforms, group=None):
+    """k-means++ (private/Arthur_initialization.m:24-69) over column shards.
+
+    Every rank passes the SAME `first` (global index of the first centre, :35) and the same
+    iterable of uniform numbers (one per randsample call, :50,:56).  Per round: each rank folds
+    the distance to the newest centre into its running minimum and returns its local sum of D^2;
+    the sums are all-gathered; the rank whose cumulative range contains u*total finds the local
+    index by a prefix search; it broadcasts the global index and the column.  Returns
+    (global indices int64[K], centres p x K) on every rank.  `engine` needs n_local, get_column,
+    kpp_update(center, gamma, first) -> local sum, kpp_pick(target) -> local index."""
+    import torch.distributed as dist
+    on = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    world = dist.get_world_size(group) if on else 1
+    me = dist.get_rank(group) if on else 0
+    bounds = [None] * world
+    if on:
+        dist.all_gather_object(bounds, (int(lo), int(lo + engine.n_local)), group=group)
+    else:
+        bounds[0] = (int(lo), int(lo + engine.n_local))
+
+    def owner_of(g):
+        for r, (a, b) in enumerate(bounds):
+            if a <= g < b:
+                return r
+        raise ValueError(f"global column {g} is owned by no rank")
+
+    def fetch(g):
+        r = owner_of(g)
+        col = engine.get_column(g - bounds[r][0]) if r == me else None
+        if on:
+            box = [col]
+            dist.broadcast_object_list(box, src=r, group=group)
+            col = box[0]
+        return col
+
+    it = iter(uniforms)
+    chosen = [int(first)]
+    cols = [fetch(chosen[0])]
+    for _ in range(K - 1):
+        local = engine.kpp_update(cols[-1], gamma, first=(len(chosen) == 1)) if engine.n_local else 0.0
+        sums = [None] * world
+        if on:
+            dist.all_gather_object(sums, float(local), group=group)
+        else:
+            sums[0] = float(local)
+        total = 0.0
+        prefix = []
+        for v in sums:                       # same summation order on every rank
+            prefix.append(total)
+            total += v
+
+        def pick():
+            u = float(next(it))
+            if not (total > 0):              # all distances zero: uniform (Arthur_initialization.m:44-48)
+                return min(int(u * n_total), n_total - 1)
+            target = u * total
+            q = world - 1
+            for r in range(world):
+                if target < prefix[r] + sums[r] and sums[r] > 0:
+                    q = r
+                    break
+            j = engine.kpp_pick(target - prefix[q]) if q == me else None
+            if on:
+                box = [j]
+                dist.broadcast_object_list(box, src=q, group=group)
+                j = box[0]
+            return bounds[q][0] + int(j)
+
+        g = pick()
+        counter = 1
+        while g in chosen and counter < 400:  # :54-61
+            g = pick()
+            counter += 1
+        if g in chosen:
+            raise RuntimeError("Cannot sample with replacement with this distribution")
+        chosen.append(g)
+        cols.append(fetch(g))
+    return np.asarray(chosen, dtype=np.int64), np.stack(cols, axis=1)

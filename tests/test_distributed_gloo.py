@@ -65,6 +65,17 @@ class OracleShardEngine:
     def set_center_column(self, k, col): self.C[:, k] = col
     def assignments(self): return self.a, self.d
 
+    def kpp_update(self, center, gamma, first):
+        from oracle import host_ref
+        c = np.asarray(center, dtype=np.float64).reshape(-1, 1)
+        _, dd, _ = host_ref.find_cluster_assignments(self.X, c, gamma)
+        self.mind = dd if first else np.minimum(self.mind, dd)
+        return float(np.sum(self.mind ** 2))
+
+    def kpp_pick(self, target):
+        cs = np.cumsum(self.mind ** 2)
+        return int(min(np.searchsorted(cs, target, side="right"), self.n_local - 1))
+
 
 def _worker(rank, world, port, case, out):
     sys.path.insert(0, ROOT)
@@ -86,6 +97,38 @@ def _worker(rank, world, port, case, out):
         out[rank] = dict(its=its, dff=st.dff, sumsq=st.sumsq, centers=eng.get_centers(), a=np.asarray(a), lo=lo, hi=hi)
     finally:
         dist.destroy_process_group()
+
+
+def _kpp_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from sparsifiedkmeans_b200.distributed import shard_bounds, sharded_arthur_initialization
+        from tests.util import make_sparsified
+        X, _, gamma = make_sparsified(p=64, n=1001, m=8, K=6, seed=71, kind="mixture")
+        lo, hi = shard_bounds(X.shape[1], world, rank)
+        eng = OracleShardEngine(X[:, lo:hi], 6)
+        u = np.random.default_rng(3).random(4000)
+        idx, cen = sharded_arthur_initialization(eng, 6, gamma, X.shape[1], lo, first=500, uniforms=iter(u))
+        out[rank] = dict(idx=idx, cen=cen)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_kmeanspp_equals_single_process():
+    from oracle import host_ref
+    from tests.util import make_sparsified
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_kpp_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    X, _, gamma = make_sparsified(p=64, n=1001, m=8, K=6, seed=71, kind="mixture")
+    u = np.random.default_rng(3).random(4000)
+    want, cen = host_ref.arthur_initialization(X, 6, gamma, first=500, uniforms=iter(u))
+    assert np.array_equal(out[0]["idx"], want) and np.array_equal(out[1]["idx"], want)
+    assert np.array_equal(out[0]["cen"], np.asarray(cen.todense()))
+    assert np.array_equal(out[0]["cen"], out[1]["cen"])
 
 
 def _free_port():

@@ -75,7 +75,8 @@ def test_hadamard_rejects_bad_sizes(ctx):
 @pytest.mark.parametrize("store", ["f64", "f32"])
 @pytest.mark.parametrize("kind", ["mixture", "unstructured"])
 @pytest.mark.parametrize("K,p,m", [(1, 32, 4), (2, 40, 6), (5, 64, 8), (10, 784, 78), (16, 128, 7),
-                                   (33, 100, 10), (64, 1024, 51), (100, 256, 13), (130, 64, 5)])
+                                   (33, 100, 10), (64, 1024, 51), (100, 256, 13), (130, 64, 5),
+                                   (16, 32768, 40), (5, 20000, 25)])       # tables too large for shared memory
 def test_assign_matches_reference(ctx, store, kind, K, p, m):
     from sparsifiedkmeans_b200 import Dataset
     X, c, gamma = make_sparsified(p=p, n=3000, m=m, K=K, seed=K * 7 + p, kind=kind, f32=True, ragged=(K % 2 == 1))

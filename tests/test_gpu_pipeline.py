@@ -264,3 +264,16 @@ def test_kmeans_sparsified_device_pipeline_is_the_default_and_reproducible(ctx):
     assert OUTh["Pipeline"] == "host"
     for k in range(4):
         assert len(set(IDXh[lab == k].tolist())) == 1
+
+
+def test_sharded_kmeanspp_on_one_gpu_matches_reference(ctx):
+    from sparsifiedkmeans_b200 import Dataset
+    from sparsifiedkmeans_b200.distributed import CudaShardEngine, sharded_arthur_initialization
+    X, _, gamma = make_sparsified(p=64, n=1200, m=8, K=6, seed=81, kind="mixture")
+    u = np.random.default_rng(4).random(4000)
+    want, cen = host_ref.arthur_initialization(X, 6, gamma, first=3, uniforms=iter(u))
+    ds = Dataset.from_scipy(X, store="f32", ctx=ctx)
+    eng = CudaShardEngine(ds, 6)
+    idx, C = sharded_arthur_initialization(eng, 6, gamma, X.shape[1], 0, first=3, uniforms=iter(u))
+    assert np.array_equal(idx, want) and np.array_equal(C, np.asarray(cen.todense()))
+    eng.close(); ds.close()
