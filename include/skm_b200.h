@@ -138,6 +138,14 @@ int  skm_dataset_create_csc(skm_ctx *ctx, int64_t p, int64_t n,
                             skm_dataset **out);
 void skm_dataset_destroy(skm_dataset *ds);
 int  skm_dataset_get_info(const skm_dataset *ds, skm_dataset_info *info);
+/* Verification / statistics of the streamed (SELL-32) image the fast assignment kernel reads.
+ * layout: -1 = check the current image, 0 / 1 = first re-order it for kernel family 0 (16-byte
+ * gathers, single table, greedy quarter-warp order) or 1 (8-byte gathers, dual table, exact
+ * edge-coloured half-warp order; needs columns of at most 254 entries).
+ * out[0] = columns whose image differs from the CSC matrix (must be 0), out[1] = gather steps,
+ * out[2] = shared-memory wavefronts those steps cost (== out[1] when conflict-free),
+ * out[3] = layout of the image. */
+int  skm_dataset_layout_check(skm_dataset *ds, int layout, int64_t out[4]);
 /* Densify column j (0-based) into out[p] (kmeans_sparsified.m:436, X(:,iMax)). */
 int  skm_dataset_get_column(skm_dataset *ds, int64_t j, double *out);
 

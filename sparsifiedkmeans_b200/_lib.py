@@ -66,6 +66,7 @@ SIGNATURES = {
     "skm_dataset_destroy": (None, [_vp]),
     "skm_dataset_get_info": (_int, [_vp, C.POINTER(DatasetInfo)]),
     "skm_dataset_get_column": (_int, [_vp, _i64, _vp]),
+    "skm_dataset_layout_check": (_int, [_vp, _int, _vp]),
     "skm_assign": (_int, [_vp, _vp, _i64, _int, _dbl, _vp, _vp]),
     "skm_assign_sparse_centers": (_int, [_vp, _vp, _i64, _int, _dbl, _vp, _vp]),
     "skm_masked_distances": (_int, [_vp, _vp, _i64, _vp]),

@@ -310,6 +310,17 @@ extern "C" int skm_dataset_get_info(const skm_dataset *ds, skm_dataset_info *inf
     return SKM_OK;
 }
 
+extern "C" int skm_dataset_layout_check(skm_dataset *ds, int layout, int64_t *out)
+{
+    SKM_REQUIRE(ds && out, "NULL argument");
+    SKM_TRY(enter(ds->ctx));
+    SKM_REQUIRE(layout >= -1 && layout <= 1, "layout must be -1 (current), 0 or 1");
+    if (layout >= 0 && ds->store_dtype == SKM_F32) SKM_TRY(skm_sell_ensure_layout(ds, layout));
+    SKM_TRY(skm_sell_check(ds, out));
+    out[3] = ds->sell_mode;
+    return SKM_OK;
+}
+
 extern "C" int skm_dataset_get_column(skm_dataset *ds, int64_t j, double *out)
 {
     SKM_REQUIRE(ds && out, "NULL argument");
@@ -396,8 +407,8 @@ static int skm_lloyd_create_ex(skm_dataset *ds, int64_t K, int want_f64_dist, sk
             if ((rc = dev_alloc((void **)&L->dist_f32, sizeof(float) * n, "dist"))) break;
             if ((rc = dev_alloc((void **)&L->flagged, sizeof(int32_t) * n, "flagged"))) break;
             FastPlan pl;
-            if (skm_fast_plan(ds->ctx, p, K, &pl)) {
-                if ((rc = dev_alloc((void **)&L->table, sizeof(float) * (size_t)(p + 1) * pl.ks * pl.nchunks, "table"))) break;
+            if (skm_fast_plan(ds->ctx, p, K, &pl, ds->max_col_nnz)) {
+                if ((rc = dev_alloc((void **)&L->table, sizeof(float) * skm_fast_table_floats(p, pl), "table"))) break;
                 if (pl.nchunks > 1 && (rc = dev_alloc((void **)&L->best2, sizeof(float) * 2 * n, "best2"))) break;
             }
         }
@@ -460,7 +471,8 @@ extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
     SKM_TRY(enter(ctx));
     SKM_REQUIRE(!has_gamma || gamma == gamma, "gamma is NaN");
     FastPlan pl;
-    const bool fast = ds->store_dtype == SKM_F32 && L->table && skm_fast_plan(ctx, ds->p, L->K, &pl);
+    const bool fast = ds->store_dtype == SKM_F32 && L->table && skm_fast_plan(ctx, ds->p, L->K, &pl, ds->max_col_nnz);
+    if (fast) SKM_TRY(skm_sell_ensure_layout(ds, pl.mode64 ? 1 : 0));   // entry order of the kernel family (one-off)
     {
         SkmTimed t(ctx, SKM_T_PREP);
         SKM_TRY(skm_launch_prep_centers(ctx, ds->p, L->K, L->centers, has_gamma, gamma, L->cscaled_t, nullptr, nullptr));

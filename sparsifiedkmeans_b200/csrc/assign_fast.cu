@@ -16,6 +16,7 @@
 // assignments equal the reference's bit for bit.
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -75,6 +76,65 @@ __device__ __forceinline__ void tma_stage(void *smem_dst, const void *gsrc, uint
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
             "selp.b32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(bar_a) : "memory");
+    }
+}
+
+// Per-column epilogue shared by the fast kernels: best / second best of this chunk, merge with
+// earlier chunks, exactness guard, results.
+template <int KC>
+__device__ __forceinline__ void finish_column(const FastParams &P, const float (&acc)[KC], int64_t slice, int lane)
+{
+        // ---- per-column epilogue: best / second best of this chunk ----
+    const float INF = __int_as_float(0x7f800000);
+    const float QNAN = __int_as_float(0x7fc00000);
+    float b1 = INF, b2 = INF;
+    int i1 = P.k0;
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        if (k < P.kvalid) {
+            const float v = acc[k];
+            if (!(v < INF)) bad = true;                    // NaN or overflow: cannot certify
+            if (v < b1) { b2 = b1; b1 = v; i1 = P.k0 + k; }
+            else if (v < b2) b2 = v;
+        }
+    }
+    if (bad) b2 = QNAN;
+
+    const int64_t j = slice * SKM_SLICE + lane;
+    if (j >= P.n) return;
+    if (!P.first) {                                        // merge with earlier chunks
+        const float2 r = P.best2[j];
+        const int ri = P.assign[j];
+        const bool nan2 = (r.y != r.y) || (b2 != b2);
+        if (b1 < r.x) { b2 = fminf(r.x, b2); }
+        else { b2 = fminf(r.y, b1); b1 = r.x; i1 = ri; }
+        if (nan2) b2 = QNAN;
+    }
+    if (!P.last) {
+        P.best2[j] = make_float2(b1, b2);
+        P.assign[j] = i1;
+        return;
+    }
+    // ---- guard: |fp32 sum - exact sum| <= E(s) = ga*s + gb*sqrt(s) + ge   ----
+    const float cm = *P.cmax;
+    float ga = P.ga, gbu = P.gb_unit, geu = P.ge_unit;
+    if (P.m_dev) {                                          // same constants, rounded up in fp32
+        const float U = 5.9604644775390625e-08f, mm = (float)max(*P.m_dev, 1);
+        ga = 1.02f * (mm + 5.f) * U; gbu = 2.04f * U * sqrtf(mm); geu = 2.2f * U * U * mm;
+    }
+    const float gb = gbu * cm, ge = geu * cm * cm + 1e-37f;
+    bool certified;
+    if (P.ktotal == 1) certified = (b1 < INF);
+    else {
+        const float E = ga * (b1 + b2) + gb * (sqrtf(b1) + sqrtf(b2)) + 2.f * ge;
+        certified = (b2 - b1) > E;                         // false for NaN / inf
+    }
+    P.assign[j] = i1;
+    P.dist[j] = sqrtf(b1);
+    if (!certified) {
+        const int slot = atomicAdd(P.nflag, 1);
+        P.flagged[slot] = (int32_t)j;
     }
 }
 
@@ -145,74 +205,96 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assign_fast(const FastParams 
             step<KC>(acc, tab, ks, q.z, __int_as_float(q.w));
         }
 
-        // ---- per-column epilogue: best / second best of this chunk ----
-        const float INF = __int_as_float(0x7f800000);
-        const float QNAN = __int_as_float(0x7fc00000);
-        float b1 = INF, b2 = INF;
-        int i1 = P.k0;
-        bool bad = false;
-#pragma unroll
-        for (int k = 0; k < KC; ++k) {
-            if (k < P.kvalid) {
-                const float v = acc[k];
-                if (!(v < INF)) bad = true;                    // NaN or overflow: cannot certify
-                if (v < b1) { b2 = b1; b1 = v; i1 = P.k0 + k; }
-                else if (v < b2) b2 = v;
-            }
-        }
-        if (bad) b2 = QNAN;
-
-        const int64_t j = slice * SKM_SLICE + lane;
-        if (j >= P.n) continue;
-        if (!P.first) {                                        // merge with earlier chunks
-            const float2 r = P.best2[j];
-            const int ri = P.assign[j];
-            const bool nan2 = (r.y != r.y) || (b2 != b2);
-            if (b1 < r.x) { b2 = fminf(r.x, b2); }
-            else { b2 = fminf(r.y, b1); b1 = r.x; i1 = ri; }
-            if (nan2) b2 = QNAN;
-        }
-        if (!P.last) {
-            P.best2[j] = make_float2(b1, b2);
-            P.assign[j] = i1;
-            continue;
-        }
-        // ---- guard: |fp32 sum - exact sum| <= E(s) = ga*s + gb*sqrt(s) + ge   ----
-        const float cm = *P.cmax;
-        float ga = P.ga, gbu = P.gb_unit, geu = P.ge_unit;
-        if (P.m_dev) {                                          // same constants, rounded up in fp32
-            const float U = 5.9604644775390625e-08f, mm = (float)max(*P.m_dev, 1);
-            ga = 1.02f * (mm + 5.f) * U; gbu = 2.04f * U * sqrtf(mm); geu = 2.2f * U * U * mm;
-        }
-        const float gb = gbu * cm, ge = geu * cm * cm + 1e-37f;
-        bool certified;
-        if (P.ktotal == 1) certified = (b1 < INF);
-        else {
-            const float E = ga * (b1 + b2) + gb * (sqrtf(b1) + sqrtf(b2)) + 2.f * ge;
-            certified = (b2 - b1) > E;                         // false for NaN / inf
-        }
-        P.assign[j] = i1;
-        P.dist[j] = sqrtf(b1);
-        if (!certified) {
-            const int slot = atomicAdd(P.nflag, 1);
-            P.flagged[slot] = (int32_t)j;
-        }
+        finish_column<KC>(P, acc, slice, lane);
     }
 }
 
+// LDS.64 variant for K chunks with an odd number of 8-byte slots per table row (KC = 2, 6, 10, 14):
+// the row is exactly KC floats (K = 10: 40 bytes instead of the 48 the 16-byte variant gathers),
+// one LDS.64 per two centres.  A 64-bit shared load is served per half-warp; its 16 slots are
+// conflict-free iff the 16 rows differ mod 16 (slot = row * KC/2 + c, KC/2 odd).  The SELL image
+// built for this kernel (convert.cu, layout mode 1) guarantees that: the table is staged TWICE
+// (copy B starts at row `boff`, boff = 1 mod 16, so an entry can be served from bank class
+// row mod 16 or row + 1 mod 16), the per-class loads of every half-warp are balanced over the two
+// copies and the entries are then scheduled by an exact bipartite edge colouring.  The row field
+// of the image already holds the row of the copy to read; pad entries point at one of 16 zero rows.
+template <int KC>
+__device__ __forceinline__ void step64(float (&acc)[KC], const float *tab, int r, float x)
+{
+    const float2 *row = reinterpret_cast<const float2 *>(tab + (size_t)r * KC);
+#pragma unroll
+    for (int c = 0; c < KC / 2; ++c) {
+        const float2 v = row[c];
+        float d;
+        d = x - v.x; acc[2 * c + 0] = fmaf(d, d, acc[2 * c + 0]);
+        d = x - v.y; acc[2 * c + 1] = fmaf(d, d, acc[2 * c + 1]);
+    }
+}
+
+template <int KC, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_assign_fast64(const FastParams P)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    float *stab = reinterpret_cast<float *>(smem_raw);
+    tma_stage(stab, P.table, P.table_bytes, &bar);
+    const float *tab = stab;
+
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = ((int64_t)gridDim.x * THREADS) >> 5;
+    int64_t slice = ((int64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
+
+    for (; slice < P.nslices; slice += warps_total) {
+        int64_t base;
+        int w2;
+        if (P.uniform) { base = slice * (int64_t)P.width2 * 32; w2 = P.width2; }
+        else { base = P.slice_ptr[slice]; w2 = (int)((P.slice_ptr[slice + 1] - base) >> 5); }
+        const int4 *src = P.sell + base + lane;
+
+        float acc[KC];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) acc[k] = 0.f;
+
+        int t2 = 0;
+        for (; t2 + 4 <= w2; t2 += 4) {
+            const int4 q0 = __ldcs(src + (t2 + 0) * 32);
+            const int4 q1 = __ldcs(src + (t2 + 1) * 32);
+            const int4 q2 = __ldcs(src + (t2 + 2) * 32);
+            const int4 q3 = __ldcs(src + (t2 + 3) * 32);
+            step64<KC>(acc, tab, q0.x, __int_as_float(q0.y));
+            step64<KC>(acc, tab, q0.z, __int_as_float(q0.w));
+            step64<KC>(acc, tab, q1.x, __int_as_float(q1.y));
+            step64<KC>(acc, tab, q1.z, __int_as_float(q1.w));
+            step64<KC>(acc, tab, q2.x, __int_as_float(q2.y));
+            step64<KC>(acc, tab, q2.z, __int_as_float(q2.w));
+            step64<KC>(acc, tab, q3.x, __int_as_float(q3.y));
+            step64<KC>(acc, tab, q3.z, __int_as_float(q3.w));
+        }
+        for (; t2 < w2; ++t2) {
+            const int4 q = __ldcs(src + t2 * 32);
+            step64<KC>(acc, tab, q.x, __int_as_float(q.y));
+            step64<KC>(acc, tab, q.z, __int_as_float(q.w));
+        }
+        finish_column<KC>(P, acc, slice, lane);
+    }
+}
+
+// table rows: [0,p) the centres, [p,zrows_end) zeros, then (dual tables) a second copy at row boff
 __global__ void k_build_table(int64_t p, int64_t K, const double *__restrict__ ct, int kc, int ks,
-                              int nchunks, float *__restrict__ table, float *__restrict__ cmax)
+                              int nchunks, int64_t rows, int64_t boff, float *__restrict__ table,
+                              float *__restrict__ cmax)
 {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t per_chunk = (p + 1) * ks;
+    int64_t per_chunk = rows * ks;
     int64_t total = per_chunk * nchunks;
     float m = 0.f;
     if (idx < total) {
         int64_t c = idx / per_chunk, rem = idx % per_chunk;
         int64_t r = rem / ks, kk = rem % ks;
         int64_t k = c * kc + kk;
+        if (boff > 0 && r >= boff) r -= boff;              // second copy
         float v = 0.f;
-        if (kk < kc && k < K) v = (float)ct[r * K + k];
+        if (r < p && kk < kc && k < K) v = (float)ct[r * K + k];
         table[idx] = v;
         m = fabsf(v);
         if (v != v) m = __int_as_float(0x7fc00000);
@@ -244,6 +326,26 @@ int launch_fast(skm_ctx *ctx, const FastParams &P, size_t smem)
     return SKM_OK;
 }
 
+template <int KC, int THREADS, int MINB>
+int launch_fast64(skm_ctx *ctx, const FastParams &P, size_t smem)
+{
+    auto kern = k_assign_fast64<KC, THREADS, MINB>;
+    SKM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+    if (per_sm < 1) {
+        skm_set_error("assign_fast64<%d>: kernel does not fit on an SM (smem %zu)", KC, smem);
+        return SKM_ERR_UNSUPPORTED;
+    }
+    int64_t blocks = (int64_t)ctx->sm_count * per_sm;
+    int64_t need = (P.nslices * 32 + THREADS - 1) / THREADS;
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+    kern<<<(unsigned)blocks, THREADS, smem, ctx->stream>>>(P);
+    SKM_CHECK_LAUNCH(ctx);
+    return SKM_OK;
+}
+
 }  // namespace
 
 static const int kKcOptions[] = {4, 8, 12, 16, 24, 32, 48, 64};
@@ -254,9 +356,41 @@ static int stride_for(int kc)
     return 4 * (chunks | 1);          // odd number of 16-byte chunks per row spreads the banks
 }
 
-bool skm_fast_plan(const skm_ctx *ctx, int64_t p, int64_t K, FastPlan *plan)
+int64_t skm_dual_boff(int64_t p)
+{
+    // first row of the second table copy: leaves 16 zero rows [p, p+16) for pad entries and is
+    // 1 mod 16, so copy B of a row sits one bank class above copy A
+    const int64_t b = p + 16;
+    return b + (((1 - b) % 16) + 16) % 16;
+}
+
+bool skm_fast_plan(const skm_ctx *ctx, int64_t p, int64_t K, FastPlan *plan, int64_t max_col_nnz)
 {
     const size_t budget = (size_t)ctx->smem_optin - 1024;
+    plan->mode64 = false;
+    plan->boff = 0;
+    plan->rows = p + 1;
+    // LDS.64 kernel on a dual table: K <= 14 with an odd number of 8-byte slots per row, columns
+    // short enough for the byte-sized scheduler state (max_col_nnz < 0: caller cannot use it)
+    {
+        const int kc = (int)((K + 1) & ~(int64_t)1);
+        const int64_t boff = skm_dual_boff(p);
+        const size_t bytes = (size_t)(boff + p) * kc * sizeof(float);
+        static const bool off = getenv("SKM_NO_FAST64") != nullptr;
+        if (!off && K <= 14 && ((kc / 2) & 1) && max_col_nnz >= 0 && max_col_nnz <= 254 && p < (1 << 20) &&
+            bytes <= budget / 2) {
+            plan->mode64 = true;
+            plan->boff = (int)boff;
+            plan->rows = boff + p;
+            plan->kc = kc;
+            plan->ks = kc;
+            plan->nchunks = 1;
+            plan->smem = (bytes + 127) & ~(size_t)127;
+            plan->threads = 512;
+            plan->global_table = false;
+            return true;
+        }
+    }
     int best = -1;
     // largest chunk whose table fits; then the smallest chunk that needs no more launches
     // (K=64 with room for 48 centres takes two launches of 32, not 48 + 16)
@@ -289,13 +423,19 @@ bool skm_fast_plan(const skm_ctx *ctx, int64_t p, int64_t K, FastPlan *plan)
     return true;
 }
 
+size_t skm_fast_table_floats(int64_t p, const FastPlan &pl)
+{
+    (void)p;
+    return (size_t)pl.rows * pl.ks * pl.nchunks;
+}
+
 int skm_launch_build_table(skm_ctx *ctx, int64_t p, int64_t K, const double *ct, const FastPlan &pl,
                            float *table, float *cmax)
 {
     SKM_CUDA(cudaMemsetAsync(cmax, 0, sizeof(float), ctx->stream));
-    int64_t total = (p + 1) * pl.ks * (int64_t)pl.nchunks;
+    int64_t total = pl.rows * pl.ks * (int64_t)pl.nchunks;
     int64_t blocks = (total + 255) / 256;
-    k_build_table<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p, K, ct, pl.kc, pl.ks, pl.nchunks, table, cmax);
+    k_build_table<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p, K, ct, pl.kc, pl.ks, pl.nchunks, pl.rows, pl.boff, table, cmax);
     SKM_CHECK_LAUNCH(ctx);
     return SKM_OK;
 }
@@ -316,7 +456,7 @@ int skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const
     P.uniform = ds->uniform_width ? 1 : 0;
     P.width2 = ds->sell_width2;
     P.ks = pl.ks;
-    P.table_bytes = (uint32_t)((size_t)(ds->p + 1) * pl.ks * sizeof(float));
+    P.table_bytes = (uint32_t)((size_t)pl.rows * pl.ks * sizeof(float));
     P.ktotal = (int)K;
     P.ga = (float)(1.01 * (m + 5.0) * u);
     P.gb_unit = (float)(2.02 * u * sqrt(m));
@@ -329,12 +469,28 @@ int skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const
     P.flagged = flagged;
     P.nflag = nflag;
     for (int c = 0; c < pl.nchunks; ++c) {
-        P.table = table + (size_t)c * (ds->p + 1) * pl.ks;
+        P.table = table + (size_t)c * pl.rows * pl.ks;
         P.k0 = c * pl.kc;
         P.kvalid = (int)((K - P.k0) < pl.kc ? (K - P.k0) : pl.kc);
         P.first = (c == 0);
         P.last = (c == pl.nchunks - 1);
         int rc;
+        if (pl.mode64) {
+            if (ds->sell_mode != 1 && !ds->sell_plain) {
+                skm_set_error("assign_fast64: the SELL image is not in the dual-table layout");
+                return SKM_ERR_STATE;
+            }
+            const bool wide = getenv("SKM_FAST64_WIDE") != nullptr;      // tuning knob: one 1024-thread CTA per SM
+            switch (pl.kc) {
+                case 2:  rc = launch_fast64<2, 512, 2>(ctx, P, pl.smem); break;
+                case 6:  rc = launch_fast64<6, 512, 2>(ctx, P, pl.smem); break;
+                case 10: rc = wide ? launch_fast64<10, 1024, 1>(ctx, P, pl.smem) : launch_fast64<10, 512, 2>(ctx, P, pl.smem); break;
+                case 14: rc = launch_fast64<14, 512, 2>(ctx, P, pl.smem); break;
+                default: skm_set_error("assign_fast64: unsupported chunk %d", pl.kc); return SKM_ERR_UNSUPPORTED;
+            }
+            if (rc != SKM_OK) return rc;
+            continue;
+        }
         if (pl.global_table) {
             switch (pl.kc) {
                 case 4:  rc = launch_fast<4, 256, 4, true>(ctx, P, 0); break;

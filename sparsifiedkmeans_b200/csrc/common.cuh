@@ -117,6 +117,10 @@ struct skm_dataset {
     int4    *sell;
     int64_t *slice_ptr;                 // [nslices+1], in int4 units
     int64_t  nslices, sell_elems;       // sell_elems in int4 units
+    int      sell_mode;                 // 0: single table, quarter-warp (row mod 8) greedy order
+                                        // 1: dual table, half-warp (row mod 16) edge-coloured order
+    bool     sell_plain;                // stored order with true rows (streamed views)
+    int      sell_wmax;                 // largest slice width in entries
     bool     uniform_width;             // every slice has the same width
     int      sell_width2;               // pairs per column if uniform_width
     // row-major image for K2 (SKM_F32 only, see csr.cu): (column, value bits) pairs per row
@@ -169,6 +173,11 @@ int skm_launch_convert_value(skm_ctx *ctx, const void *src, int src_type, int64_
 int skm_validate_csc(skm_ctx *ctx, int64_t p, int64_t n, int64_t nnz, const int64_t *colptr,
                      const int32_t *rowidx, int64_t *max_col_nnz);
 int skm_build_sell(skm_dataset *ds);
+// re-order the SELL image in place for the kernel family `mode` (0 / 1, see skm_dataset); no-op if current
+int skm_sell_ensure_layout(skm_dataset *ds, int mode);
+// debug/verification: out[0] = columns whose SELL entries differ from the CSC image, out[1] = steps
+// (per quarter- or half-warp), out[2] = shared-memory wavefronts those steps cost
+int skm_sell_check(skm_dataset *ds, int64_t out[3]);
 int skm_build_csr(skm_dataset *ds);      // csr.cu
 // asynchronous pieces used by the streamed path (stream.cu); no host synchronisation inside
 int skm_launch_validate_async(skm_ctx *ctx, int64_t p, int64_t n, int64_t nnz, const int64_t *colptr,
@@ -208,8 +217,14 @@ struct FastPlan {
     size_t smem;      // dynamic shared memory per block
     int threads;
     bool global_table; // table gathered from global memory (too large for shared memory)
+    bool mode64;       // LDS.64 kernel on a dual table (needs the SELL image in layout mode 1)
+    int  boff;         // first row of the second table copy (mode64), else 0
+    int64_t rows;      // table rows per chunk (p + 1, or boff + p for a dual table)
 };
-bool skm_fast_plan(const skm_ctx *ctx, int64_t p, int64_t K, FastPlan *plan);
+// max_col_nnz < 0: the caller's SELL image is in stored order / cannot be re-laid out -> never mode64
+bool skm_fast_plan(const skm_ctx *ctx, int64_t p, int64_t K, FastPlan *plan, int64_t max_col_nnz = -1);
+size_t skm_fast_table_floats(int64_t p, const FastPlan &pl);
+int64_t skm_dual_boff(int64_t p);
 int  skm_launch_build_table(skm_ctx *ctx, int64_t p, int64_t K, const double *ct, const FastPlan &pl,
                             float *table, float *cmax);
 int  skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const FastPlan &pl,

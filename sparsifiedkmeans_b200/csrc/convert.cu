@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <vector>
 #include <cub/device/device_scan.cuh>
+#include "sched16.cuh"
 
 namespace {
 
@@ -194,6 +195,170 @@ __global__ void k_fill_sell_banked(int64_t p, int64_t n, int64_t nslices, int wm
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Layout mode 1 (dual table, LDS.64 kernel): exact conflict-free schedule per half-warp, see
+// sched16.cuh for the algorithm (balance over the two table copies + bipartite edge colouring).
+//
+// k_sched_dual16: one THREAD per half-warp problem (the colouring is sequential), scratch in
+// shared memory interleaved across the threads of the block.  It writes one code byte per
+// (lane, step) into the head of the slice's own SELL region; k_fill_sell_sched then materialises
+// the slice (warp per slice).
+struct SchedMem {
+    unsigned char *b;     // byte arrays, element i of thread t at b[i * nt + t]
+    uint32_t      *w;     // word arrays
+    int nt, t;
+    __device__ unsigned char &B(int i) const { return b[(size_t)i * nt + t]; }
+    __device__ uint32_t &Wd(int i) const { return w[(size_t)i * nt + t]; }
+};
+struct SchedOut {
+    unsigned char *dst; int W;
+    __device__ void operator()(int l, int t, unsigned char code) const { dst[(size_t)l * W + t] = code; }
+};
+
+__global__ void k_sched_dual16(int64_t n, int64_t nslices, int wmax, const int64_t *__restrict__ colptr,
+                               const int32_t *__restrict__ rowidx, const int64_t *__restrict__ slice_ptr,
+                               int4 *__restrict__ sell, unsigned long long *__restrict__ overflow_total)
+{
+    extern __shared__ __align__(16) unsigned char sraw[];
+    const int nt = blockDim.x, tid = threadIdx.x;
+    SchedMem M;
+    M.b = sraw; M.nt = nt; M.t = tid;
+    M.w = reinterpret_cast<uint32_t *>(sraw + (((size_t)skm_sched16_bytes(wmax) * nt + 15) & ~(size_t)15));
+
+    const int64_t prob = (int64_t)blockIdx.x * nt + tid;  // half-warp index
+    if (prob >= 2 * nslices) return;
+    const int64_t slice = prob >> 1;
+    const int half = (int)(prob & 1);
+    const int64_t base = slice_ptr[slice];
+    const int W = (int)((slice_ptr[slice + 1] - base) >> 5) * 2;
+    if (W == 0) return;
+    for (int i = 0; i < 256; ++i) M.B(i) = 0;
+    for (int l = 0; l < 16; ++l) {
+        const int64_t j = slice * SKM_SLICE + half * 16 + l;
+        int64_t a = 0, b = 0;
+        if (j < n) { a = colptr[j]; b = colptr[j + 1]; }
+        for (int64_t t = a; t < b; ++t) M.B(l * 16 + (rowidx[t] & 15)) += 1;
+    }
+    SchedOut out;
+    out.dst = reinterpret_cast<unsigned char *>(sell + base) + (size_t)half * 16 * W;
+    out.W = W;
+    const int ovf = skm_sched16(M, W, wmax, out);
+    if (ovf) atomicAdd(overflow_total, (unsigned long long)ovf);
+}
+
+template <typename VT>
+__global__ void k_fill_sell_sched(int64_t p, int64_t n, int64_t nslices, int wmax, int boff,
+                                  const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
+                                  const VT *__restrict__ val, const int64_t *__restrict__ slice_ptr,
+                                  int4 *__restrict__ sell)
+{
+    extern __shared__ unsigned short s_all[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
+    const int64_t warp = (int64_t)blockIdx.x * nwb + wib;
+    if (warp >= nslices) return;
+    // per warp: ord[wmax][32] (u16), start[16][32] (u16), code[wmax][32] (u8)
+    unsigned short *ord = s_all + (size_t)wib * (wmax * 32 + 16 * 32 + wmax * 16);
+    unsigned short *st = ord + (size_t)wmax * 32;
+    unsigned char *code = reinterpret_cast<unsigned char *>(st + 16 * 32);
+    const int64_t j = warp * SKM_SLICE + lane;
+    int64_t a = 0, b = 0;
+    if (j < n) { a = colptr[j]; b = colptr[j + 1]; }
+    const int len = (int)(b - a);
+    const int64_t base = slice_ptr[warp];
+    const int w2 = (int)((slice_ptr[warp + 1] - base) >> 5);
+    const int W = 2 * w2;
+    const unsigned char *sched = reinterpret_cast<const unsigned char *>(sell + base) + (size_t)lane * W;
+    for (int t = 0; t < W; ++t) code[t * 32 + lane] = sched[t];
+    // counting sort of this lane's entries by (row & 15)
+    for (int g = 0; g < 16; ++g) st[g * 32 + lane] = 0;
+    for (int t = 0; t < len; ++t) st[(rowidx[a + t] & 15) * 32 + lane] += 1;
+    int run = 0;
+    for (int g = 0; g < 16; ++g) { const int c = st[g * 32 + lane]; st[g * 32 + lane] = (unsigned short)run; run += c; }
+    {
+        unsigned short fill[16];
+#pragma unroll
+        for (int g = 0; g < 16; ++g) fill[g] = st[g * 32 + lane];
+        for (int t = 0; t < len; ++t) {
+            const int g = rowidx[a + t] & 15;
+            int pos = 0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) { if (q == g) { pos = fill[q]; fill[q] = (unsigned short)(pos + 1); } }
+            ord[pos * 32 + lane] = (unsigned short)t;
+        }
+    }
+    __syncwarp();                                            // every lane has read its codes: the region may be overwritten
+    int4 q4 = make_int4((int)p, 0, (int)p, 0);
+    for (int step = 0; step < W; ++step) {
+        const int cd = code[step * 32 + lane];
+        int r, xb = 0;
+        if (cd & 0x80) r = (int)p + (((cd & 15) - (int)(p & 15)) & 15);
+        else {
+            const int g = cd & 15;
+            const int pos = st[g * 32 + lane];
+            st[g * 32 + lane] = (unsigned short)(pos + 1);
+            const int e = ord[pos * 32 + lane];
+            r = rowidx[a + e] + ((cd & 0x10) ? boff : 0);
+            xb = __float_as_int((float)val[a + e]);
+        }
+        if (step & 1) {
+            q4.z = r; q4.w = xb;
+            sell[base + (int64_t)(step >> 1) * 32 + lane] = q4;
+        } else { q4.x = r; q4.y = xb; }
+    }
+}
+
+// verification of a SELL image against the CSC image + wavefront count of its schedule
+__global__ void k_sell_check(int64_t p, int64_t n, int64_t nslices, int mode, int boff,
+                             const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
+                             const float *__restrict__ val, const int64_t *__restrict__ slice_ptr,
+                             const int4 *__restrict__ sell, unsigned long long *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= nslices) return;
+    const int64_t j = warp * SKM_SLICE + lane;
+    int64_t a = 0, b = 0;
+    if (j < n) { a = colptr[j]; b = colptr[j + 1]; }
+    const int64_t base = slice_ptr[warp];
+    const int w2 = (int)((slice_ptr[warp + 1] - base) >> 5);
+    // order-independent fingerprints of the column: count, sum of rows, xor/sum of mixed (row, value) hashes
+    unsigned long long c0 = 0, s0 = 0, h0 = 0, c1 = 0, s1 = 0, h1 = 0;
+    auto mix = [](unsigned r, unsigned v) -> unsigned long long {
+        unsigned long long z = ((unsigned long long)r << 32 | v) + 0x9e3779b97f4a7c15ULL;
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL; z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+        return z ^ (z >> 31);
+    };
+    for (int64_t t = a; t < b; ++t) { c0++; s0 += (unsigned)rowidx[t]; h0 += mix((unsigned)rowidx[t], (unsigned)__float_as_int(val[t])); }
+    unsigned long long steps = 0, waves = 0;
+    const int group = mode == 1 ? 16 : 8, mod = mode == 1 ? 16 : 8;
+    bool bad = false;
+    for (int t = 0; t < 2 * w2; ++t) {
+        const int4 q = sell[base + (int64_t)(t >> 1) * 32 + lane];
+        int r = (t & 1) ? q.z : q.x;
+        const int xb = (t & 1) ? q.w : q.y;
+        const int cls = r & (mod - 1);
+        // wavefronts of this step: max multiplicity of a class within each group of lanes
+        int mult = 0;
+        for (int o = 0; o < group; ++o) {
+            const int oc = __shfl_sync(0xffffffffu, cls, (lane & ~(group - 1)) | o);
+            mult += (oc == cls);
+        }
+        int mx = mult;
+        for (int o = group >> 1; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((lane & (group - 1)) == 0) { steps += 1; waves += mx; }
+        if (mode == 1 && r >= boff) { r -= boff; if (r >= p) bad = true; }
+        if (r >= p) {                                        // pad: a zero row, value 0
+            if (xb != 0 || r >= p + (mode == 1 ? 16 : 1)) bad = true;
+            continue;
+        }
+        c1++; s1 += (unsigned)r; h1 += mix((unsigned)r, (unsigned)xb);
+    }
+    if (c0 != c1 || s0 != s1 || h0 != h1) bad = true;
+    if (j < n && bad) atomicAdd(&out[0], 1ULL);
+    if (steps) { atomicAdd(&out[1], steps); atomicAdd(&out[2], waves); }
+}
+
 }  // namespace
 
 
@@ -258,6 +423,8 @@ int skm_build_sell_async(skm_ctx *ctx, skm_dataset *ds, int32_t *w2, int64_t *el
     const int64_t n = ds->n, nslices = (n + SKM_SLICE - 1) / SKM_SLICE;
     ds->nslices = nslices;
     ds->uniform_width = false;
+    ds->sell_mode = 0;
+    ds->sell_plain = true;
     if (nslices == 0) return SKM_OK;
     int64_t blocks = (nslices * 32 + 255) / 256;
     k_slice_width<<<(unsigned)blocks, 256, 0, ctx->stream>>>(n, nslices, ds->colptr, w2);
@@ -379,7 +546,61 @@ int skm_build_sell(skm_dataset *ds)
     ds->device_bytes += (int64_t)sell_bytes + (int64_t)sizeof(int64_t) * (nslices + 1);
     int wmax = 0;
     for (int64_t s2 = 0; s2 < nslices; ++s2) wmax = hw[s2] * 2 > wmax ? hw[s2] * 2 : wmax;
-    const bool banked = ds->sell_elems > 0 && ds->store_dtype == SKM_F32 && wmax > 0 && wmax <= 1024 && !getenv("SKM_NO_BANKED");
+    ds->sell_wmax = wmax;
+    ds->sell_mode = -1;
+    ds->sell_plain = false;
+    SKM_TRY(skm_sell_ensure_layout(ds, 0));
+    SKM_CUDA(cudaStreamSynchronize(ctx->stream));   // hp goes out of scope
+    return SKM_OK;
+}
+
+// (Re)write the SELL image in the entry order of kernel family `mode`; widths and slice_ptr are
+// unchanged, so this is an in-place rewrite from the CSC image.
+int skm_sell_ensure_layout(skm_dataset *ds, int mode)
+{
+    skm_ctx *ctx = ds->ctx;
+    if (!ds->sell || ds->sell_elems == 0 || ds->nslices == 0) { ds->sell_mode = mode; return SKM_OK; }
+    if (ds->sell_mode == mode) return SKM_OK;
+    const int64_t n = ds->n, nslices = ds->nslices;
+    const int wmax = ds->sell_wmax;
+    if (ds->store_dtype != SKM_F32) {
+        int64_t blocks = (nslices * 32 + 255) / 256;
+        k_fill_sell<double><<<(unsigned)blocks, 256, 0, ctx->stream>>>(
+            ds->p, n, nslices, ds->colptr, ds->rowidx, (const double *)ds->val, ds->slice_ptr, ds->sell);
+        SKM_CHECK_LAUNCH(ctx);
+        ds->sell_mode = mode; ds->sell_plain = true;
+        return SKM_OK;
+    }
+    if (mode == 1) {
+        if (wmax <= 0 || wmax > 254) { skm_set_error("dual-table layout needs columns of at most 254 entries"); return SKM_ERR_UNSUPPORTED; }
+        // scheduler: one thread per half-warp, as many as the scratch allows (interleaved shared memory)
+        const size_t per = (size_t)skm_sched16_bytes(wmax) + 4 * (size_t)skm_sched16_words(wmax);
+        int nt = (int)(((size_t)ctx->smem_optin - 1024) / per);
+        if (nt > 64) nt = 64;
+        if (nt < 1) { skm_set_error("dual-table scheduler does not fit in shared memory"); return SKM_ERR_UNSUPPORTED; }
+        const size_t smem = (((size_t)skm_sched16_bytes(wmax) * nt + 15) & ~(size_t)15) + 4 * (size_t)skm_sched16_words(wmax) * nt;
+        SKM_CUDA(cudaFuncSetAttribute(k_sched_dual16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DevBuf ovf;
+        SKM_TRY(ovf.alloc(sizeof(unsigned long long)));
+        SKM_CUDA(cudaMemsetAsync(ovf.ptr, 0, sizeof(unsigned long long), ctx->stream));
+        const int64_t probs = 2 * nslices;
+        k_sched_dual16<<<(unsigned)((probs + nt - 1) / nt), nt, smem, ctx->stream>>>(
+            n, nslices, wmax, ds->colptr, ds->rowidx, ds->slice_ptr, ds->sell, ovf.as<unsigned long long>());
+        SKM_CHECK_LAUNCH(ctx);
+        int warps = 8;
+        const size_t per_warp = (size_t)wmax * 64 + 16 * 64 + (size_t)wmax * 32;
+        while (warps > 1 && (size_t)warps * per_warp > (size_t)ctx->smem_optin - 1024) warps >>= 1;
+        const size_t smem2 = (size_t)warps * per_warp;
+        SKM_CUDA(cudaFuncSetAttribute(k_fill_sell_sched<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        k_fill_sell_sched<float><<<(unsigned)((nslices + warps - 1) / warps), warps * 32, smem2, ctx->stream>>>(
+            ds->p, n, nslices, wmax, (int)skm_dual_boff(ds->p), ds->colptr, ds->rowidx, (const float *)ds->val,
+            ds->slice_ptr, ds->sell);
+        SKM_CHECK_LAUNCH(ctx);
+        SKM_CUDA(cudaStreamSynchronize(ctx->stream));          // ovf dies here
+        ds->sell_mode = 1; ds->sell_plain = false;
+        return SKM_OK;
+    }
+    const bool banked = wmax > 0 && wmax <= 1024 && !getenv("SKM_NO_BANKED");
     if (banked) {
         int warps = 8;
         while (warps > 1 && (size_t)warps * wmax * 64 > (size_t)ctx->smem_optin - 1024) warps >>= 1;
@@ -389,16 +610,35 @@ int skm_build_sell(skm_dataset *ds)
         k_fill_sell_banked<float><<<(unsigned)blocks, warps * 32, smem, ctx->stream>>>(
             ds->p, n, nslices, wmax, ds->colptr, ds->rowidx, (const float *)ds->val, ds->slice_ptr, ds->sell);
         SKM_CHECK_LAUNCH(ctx);
-    } else if (ds->sell_elems > 0) {
+        ds->sell_plain = false;
+    } else {
         int64_t blocks = (nslices * 32 + 255) / 256;
-        if (ds->store_dtype == SKM_F32)
-            k_fill_sell<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>(
-                ds->p, n, nslices, ds->colptr, ds->rowidx, (const float *)ds->val, ds->slice_ptr, ds->sell);
-        else
-            k_fill_sell<double><<<(unsigned)blocks, 256, 0, ctx->stream>>>(
-                ds->p, n, nslices, ds->colptr, ds->rowidx, (const double *)ds->val, ds->slice_ptr, ds->sell);
+        k_fill_sell<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>(
+            ds->p, n, nslices, ds->colptr, ds->rowidx, (const float *)ds->val, ds->slice_ptr, ds->sell);
         SKM_CHECK_LAUNCH(ctx);
+        ds->sell_plain = true;
     }
-    SKM_CUDA(cudaStreamSynchronize(ctx->stream));   // hp goes out of scope
+    ds->sell_mode = 0;
+    return SKM_OK;
+}
+
+int skm_sell_check(skm_dataset *ds, int64_t out[3])
+{
+    skm_ctx *ctx = ds->ctx;
+    out[0] = out[1] = out[2] = 0;
+    if (!ds->sell || ds->nslices == 0 || ds->store_dtype != SKM_F32) return SKM_OK;
+    DevBuf r;
+    SKM_TRY(r.alloc(3 * sizeof(unsigned long long)));
+    SKM_CUDA(cudaMemsetAsync(r.ptr, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    int64_t blocks = (ds->nslices * 32 + 255) / 256;
+    k_sell_check<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ds->p, ds->n, ds->nslices, ds->sell_mode == 1 ? 1 : 0,
+                                                           (int)skm_dual_boff(ds->p), ds->colptr, ds->rowidx,
+                                                           (const float *)ds->val, ds->slice_ptr, ds->sell,
+                                                           r.as<unsigned long long>());
+    SKM_CHECK_LAUNCH(ctx);
+    unsigned long long h[3];
+    SKM_CUDA(cudaMemcpyAsync(h, r.ptr, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    SKM_CUDA(cudaStreamSynchronize(ctx->stream));
+    out[0] = (int64_t)h[0]; out[1] = (int64_t)h[1]; out[2] = (int64_t)h[2];
     return SKM_OK;
 }

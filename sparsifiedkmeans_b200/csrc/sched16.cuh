@@ -1,0 +1,185 @@
+// sched16.cuh -- conflict-free shared-memory schedule for one half-warp of the LDS.64 assignment
+// kernel (layout mode 1, see convert.cu).  Host/device code: the device kernel runs it with one
+// thread per half-warp on interleaved shared memory, tests/test_sched16.py compiles it with g++
+// and checks the colouring on the CPU.
+//
+// Problem: 16 lanes (columns), lane l holds cnt[l][g] entries whose table row is g mod 16.  The
+// centroid table is staged twice; an entry of group g can be read from copy A (bank class g) or
+// copy B (class g+1 mod 16).  A step (one LDS.64 per lane) costs one wavefront iff the 16 classes
+// touched are distinct.  We need a W-step schedule.
+//   1. Choose copies so that no class holds more than W entries: excess flows round the ring
+//      c -> c+1 (only group-c entries can move from class c to c+1).
+//   2. Edge-colour the bipartite multigraph lanes x classes with W colours (colour = step).
+//      Koenig's theorem: possible when every degree is <= W.  Insert edges one at a time; if lane
+//      and class share no free colour, take a free at the lane, b free at the class, swap a<->b on
+//      the alternating path starting at the class, then use a.
+//   3. Steps where a lane has no entry are pads served from a zero row of a class still free.
+// Output: code[l * W + t] = group | copy << 4 for an entry, 0x80 | class for a pad.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SKM_HD __host__ __device__
+#else
+#define SKM_HD
+#endif
+
+SKM_HD static inline int skm_ffs32(uint32_t m)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)m);
+#else
+    return __builtin_ffs((int)m);
+#endif
+}
+
+// bytes / words of scratch per problem
+SKM_HD static inline int skm_sched16_bytes(int wmax) { return 768 + 32 * wmax; }
+SKM_HD static inline int skm_sched16_words(int wmax) { return 32 * ((wmax + 31) >> 5); }
+
+// Mem: B(i) -> unsigned char&, Wd(i) -> uint32_t&  (scratch of skm_sched16_bytes / _words)
+// On entry B(l*16+g), l,g in [0,16), holds cnt[l][g]; everything else is scratch.
+// Returns the number of entries that could not be scheduled conflict-free (0 when balanced).
+template <class Mem, class Out>
+SKM_HD static int skm_sched16(Mem &M, int W, int wmax, Out &out)
+{
+    const int nw = (wmax + 31) >> 5;
+    const int OFF_CNT = 0, OFF_MOV = 256, OFF_OVF = 512, OFF_AT = 768, OFF_ATC = 768 + 16 * wmax;
+    const int OFF_FL = 0, OFF_FC = 16 * nw;
+    for (int i = 256; i < 768; ++i) M.B(i) = 0;
+
+    // ---- 1. balance ----
+    int T[16], d[16], x[16];
+    for (int c = 0; c < 16; ++c) {
+        int s = 0;
+        for (int l = 0; l < 16; ++l) s += M.B(OFF_CNT + l * 16 + c);
+        T[c] = s; d[c] = s; x[c] = 0;
+    }
+    for (int pass = 0; pass < 64; ++pass) {
+        bool moved = false;
+        for (int c = 0; c < 16; ++c) {
+            const int ex = d[c] - W, avail = T[c] - x[c];
+            if (ex > 0 && avail > 0) {
+                const int mv = ex < avail ? ex : avail;
+                x[c] += mv; d[c] -= mv; d[(c + 1) & 15] += mv;
+                moved = true;
+            }
+        }
+        if (!moved) break;
+    }
+    for (int c = 0; c < 16; ++c) {          // spread the moves of group c over the lanes, round-robin
+        int rem = x[c];
+        while (rem > 0) {
+            bool any = false;
+            for (int l = 0; l < 16 && rem > 0; ++l) {
+                const int have = M.B(OFF_CNT + l * 16 + c), mv = M.B(OFF_MOV + l * 16 + c);
+                if (mv < have) { M.B(OFF_MOV + l * 16 + c) = (unsigned char)(mv + 1); --rem; any = true; }
+            }
+            if (!any) break;
+        }
+    }
+
+    // ---- 2. edge colouring ----
+    for (int i = 0; i < 32 * wmax; ++i) M.B(OFF_AT + i) = 0xFF;
+    for (int v = 0; v < 32; ++v)
+        for (int q = 0; q < nw; ++q) {
+            const int lo = q * 32;
+            M.Wd(v * nw + q) = (W - lo >= 32) ? 0xffffffffu : (W > lo ? ((1u << (W - lo)) - 1u) : 0u);
+        }
+    auto first_free = [&](int off, int v) -> int {
+        for (int q = 0; q < nw; ++q) { const uint32_t m = M.Wd(off + v * nw + q); if (m) return q * 32 + skm_ffs32(m) - 1; }
+        return -1;
+    };
+    auto set_free = [&](int off, int v, int t, bool fr) {
+        uint32_t m = M.Wd(off + v * nw + (t >> 5));
+        if (fr) m |= 1u << (t & 31); else m &= ~(1u << (t & 31));
+        M.Wd(off + v * nw + (t >> 5)) = m;
+    };
+    auto put = [&](int l, int c, int t) {
+        M.B(OFF_AT + l * wmax + t) = (unsigned char)c;
+        M.B(OFF_ATC + c * wmax + t) = (unsigned char)l;
+        set_free(OFF_FL, l, t, false);
+        set_free(OFF_FC, c, t, false);
+    };
+    int overflow = 0;
+    for (int l = 0; l < 16; ++l) {
+        for (int c = 0; c < 16; ++c) {
+            int mult = (int)M.B(OFF_CNT + l * 16 + c) - (int)M.B(OFF_MOV + l * 16 + c) +
+                       (int)M.B(OFF_MOV + l * 16 + ((c + 15) & 15));
+            for (; mult > 0; --mult) {
+                int tc = -1;
+                for (int q = 0; q < nw; ++q) {
+                    const uint32_t m = M.Wd(OFF_FL + l * nw + q) & M.Wd(OFF_FC + c * nw + q);
+                    if (m) { tc = q * 32 + skm_ffs32(m) - 1; break; }
+                }
+                if (tc >= 0) { put(l, c, tc); continue; }
+                const int a = first_free(OFF_FL, l), b = first_free(OFF_FC, c);
+                if (a < 0) { ++overflow; continue; }                         // lane longer than W: caller's bug
+                if (b < 0) { M.B(OFF_OVF + l * 16 + c) += 1; ++overflow; continue; }   // class holds more than W entries
+                int pl[34], pc[34], np = 0;         // path edges (lane, class), colours a, b, a, ...
+                int vc = c;
+                while (np < 32) {
+                    const int l1 = M.B(OFF_ATC + vc * wmax + a);
+                    if (l1 == 0xFF) break;
+                    pl[np] = l1; pc[np] = vc; ++np;
+                    const int c2 = M.B(OFF_AT + l1 * wmax + b);
+                    if (c2 == 0xFF) break;
+                    pl[np] = l1; pc[np] = c2; ++np;
+                    vc = c2;
+                }
+                for (int i = 0; i < np; ++i) {
+                    const int col = (i & 1) ? b : a;
+                    M.B(OFF_AT + pl[i] * wmax + col) = 0xFF;
+                    M.B(OFF_ATC + pc[i] * wmax + col) = 0xFF;
+                }
+                for (int i = 0; i < np; ++i) {
+                    const int col = (i & 1) ? a : b;
+                    M.B(OFF_AT + pl[i] * wmax + col) = (unsigned char)pc[i];
+                    M.B(OFF_ATC + pc[i] * wmax + col) = (unsigned char)pl[i];
+                }
+                for (int i = 0; i < np; ++i) {
+                    const int li = pl[i], ci = pc[i];
+                    set_free(OFF_FL, li, a, M.B(OFF_AT + li * wmax + a) == 0xFF);
+                    set_free(OFF_FL, li, b, M.B(OFF_AT + li * wmax + b) == 0xFF);
+                    set_free(OFF_FC, ci, a, M.B(OFF_ATC + ci * wmax + a) == 0xFF);
+                    set_free(OFF_FC, ci, b, M.B(OFF_ATC + ci * wmax + b) == 0xFF);
+                }
+                put(l, c, a);
+            }
+        }
+    }
+    // overflow entries: any free step of their lane (a conflict there is accepted)
+    if (overflow) {
+        for (int l = 0; l < 16; ++l)
+            for (int c = 0; c < 16; ++c)
+                for (int k = M.B(OFF_OVF + l * 16 + c); k > 0; --k) {
+                    const int t = first_free(OFF_FL, l);
+                    if (t < 0) break;
+                    M.B(OFF_AT + l * wmax + t) = (unsigned char)(c | 0x20);
+                    set_free(OFF_FL, l, t, false);
+                }
+    }
+
+    // ---- 3. codes ----
+    for (int l = 0; l < 16; ++l) {
+        for (int t = 0; t < W; ++t) {
+            const int e = M.B(OFF_AT + l * wmax + t);
+            unsigned char code;
+            if (e == 0xFF) {
+                int cf = -1;
+                for (int c = 0; c < 16; ++c)
+                    if ((M.Wd(OFF_FC + c * nw + (t >> 5)) >> (t & 31)) & 1u) { cf = c; break; }
+                if (cf < 0) cf = l; else set_free(OFF_FC, cf, t, false);
+                code = (unsigned char)(0x80 | cf);
+            } else {
+                const int c = e & 15, gb = (c + 15) & 15;
+                const int ia = OFF_CNT + l * 16 + c, ma = OFF_MOV + l * 16 + c;
+                const int ib = OFF_CNT + l * 16 + gb, mb = OFF_MOV + l * 16 + gb;
+                if ((int)M.B(ia) - (int)M.B(ma) > 0) { M.B(ia) -= 1; code = (unsigned char)c; }
+                else { M.B(mb) -= 1; M.B(ib) -= 1; code = (unsigned char)(gb | 0x10); }
+            }
+            out(l, t, code);
+        }
+    }
+    return overflow;
+}

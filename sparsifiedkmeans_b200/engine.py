@@ -223,6 +223,13 @@ class Dataset:
             pass
 
     # -- operators ----------------------------------------------------------
+    def layout_check(self, layout: int = -1) -> dict:
+        """Verify the streamed (SELL-32) image against the CSC matrix and count the shared-memory
+        wavefronts its entry order costs; layout 0/1 first re-orders it for that kernel family."""
+        out = np.zeros(4, dtype=np.int64)
+        check(self._lib.skm_dataset_layout_check(self.handle, int(layout), _ptr(out)))
+        return {"bad_columns": int(out[0]), "steps": int(out[1]), "wavefronts": int(out[2]), "layout": int(out[3])}
+
     def get_column(self, j: int) -> np.ndarray:
         out = np.empty(self.p, dtype=np.float64)
         check(self._lib.skm_dataset_get_column(self.handle, int(j), _ptr(out)))

@@ -76,6 +76,7 @@ def test_hadamard_rejects_bad_sizes(ctx):
 @pytest.mark.parametrize("kind", ["mixture", "unstructured"])
 @pytest.mark.parametrize("K,p,m", [(1, 32, 4), (2, 40, 6), (5, 64, 8), (10, 784, 78), (16, 128, 7),
                                    (33, 100, 10), (64, 1024, 51), (100, 256, 13), (130, 64, 5),
+                                   (6, 64, 8), (9, 200, 20), (13, 512, 26), (14, 96, 12),   # LDS.64 dual-table kernel
                                    (16, 32768, 40), (5, 20000, 25)])       # tables too large for shared memory
 def test_assign_matches_reference(ctx, store, kind, K, p, m):
     from sparsifiedkmeans_b200 import Dataset
@@ -88,6 +89,32 @@ def test_assign_matches_reference(ctx, store, kind, K, p, m):
         assert np.array_equal(d, wd)
     else:
         np.testing.assert_allclose(d, wd, rtol=2e-5, atol=1e-30)
+    ds.close()
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+@pytest.mark.parametrize("p,m,n", [(784, 78, 5000), (1024, 51, 3001), (64, 8, 700), (40, 40, 300)])
+def test_streamed_image_layouts(ctx, p, m, n, ragged):
+    """Both entry orders of the SELL image hold exactly the CSC entries; the dual-table order
+    (bipartite edge colouring per half-warp) is conflict-free: one wavefront per 8-byte gather."""
+    from sparsifiedkmeans_b200 import Dataset
+    X, c, gamma = make_sparsified(p=p, n=n, m=m, K=10, seed=p + m, kind="mixture", ragged=ragged)
+    ds = Dataset.from_scipy(X, store="f32", ctx=ctx)
+    r0 = ds.layout_check(0)
+    assert r0["bad_columns"] == 0 and r0["layout"] == 0 and r0["steps"] > 0
+    r1 = ds.layout_check(1)
+    assert r1["bad_columns"] == 0 and r1["layout"] == 1
+    if p >= 64:
+        assert r1["wavefronts"] == r1["steps"], r1          # conflict-free
+    assert r1["wavefronts"] / r1["steps"] <= r0["wavefronts"] / r0["steps"] + 1e-12
+    # the kernels agree whatever order the image was left in
+    wa, _, _ = host_ref.find_cluster_assignments(X, c, gamma)
+    a1, _ = ds.assign(c, gamma)                              # K = 10 -> dual-table kernel
+    a2, _ = ds.assign(c[:, :4], gamma)                       # K = 4  -> 16-byte kernel, re-orders the image
+    a3, _ = ds.assign(c, gamma)
+    assert np.array_equal(a1, wa) and np.array_equal(a3, wa)
+    assert np.array_equal(a2, host_ref.find_cluster_assignments(X, c[:, :4], gamma)[0])
+    assert ds.layout_check()["layout"] == 1
     ds.close()
 
 

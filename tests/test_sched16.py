@@ -1,0 +1,15 @@
+"""CPU test of the conflict-free half-warp scheduler (csrc/sched16.cuh is host/device code): compiled
+with g++ and run on random, ragged and adversarial row patterns."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_sched16_edge_colouring_on_cpu(tmp_path):
+    exe = tmp_path / "test_sched16"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "sparsifiedkmeans_b200", "csrc"),
+                           "-o", str(exe), os.path.join(ROOT, "tests", "native", "test_sched16.cpp")])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "bad 0" in out.stdout
