@@ -349,11 +349,11 @@ def run_ours(args):
     traffic = None
     try:   # DRAM bytes per launch from the committed ncu --set full capture (per-point figure x points)
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f)["k_assign_fast"]["dram_bytes_per_point"] * n
+            traffic = json.load(f)[L.kernel_name.split("<")[0]]["dram_bytes_per_point"] * n
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_assign_fast", "ms_per_launch": k1_ms_avg,
+                "traffic": traffic, "kernel": L.kernel_name, "ms_per_launch": k1_ms_avg,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "step_breakdown_ms": {k: v[0] / args.steps for k, v in tim.items() if v[1]}}
 

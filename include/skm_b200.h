@@ -207,6 +207,8 @@ int   skm_lloyd_get_counts(skm_lloyd *L, int64_t *counts /* host K, after finali
 int   skm_lloyd_get_assignments(skm_lloyd *L, int32_t *assign_out, double *dist_out);
 /* First local column attaining the largest distance (kmeans_sparsified.m:435). */
 int   skm_lloyd_argmax_distance(skm_lloyd *L, double *maxdist, int64_t *j);
+/* Name of the kernel skm_lloyd_assign runs for this state (reporting only; thread-local string). */
+const char *skm_lloyd_kernel_name(skm_lloyd *L);
 /* Device pointers to the local results (int32 0-based assignments, float/double distances). */
 void *skm_lloyd_assign_ptr(skm_lloyd *L);
 void *skm_lloyd_dist_ptr(skm_lloyd *L, int *dtype);

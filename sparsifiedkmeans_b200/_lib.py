@@ -85,6 +85,7 @@ SIGNATURES = {
     "skm_lloyd_get_counts": (_int, [_vp, _vp]),
     "skm_lloyd_get_assignments": (_int, [_vp, _vp, _vp]),
     "skm_lloyd_argmax_distance": (_int, [_vp, C.POINTER(_dbl), C.POINTER(_i64)]),
+    "skm_lloyd_kernel_name": (C.c_char_p, [_vp]),
     "skm_lloyd_assign_ptr": (_vp, [_vp]),
     "skm_lloyd_dist_ptr": (_vp, [_vp, C.POINTER(_int)]),
     "skm_lloyd_step_host": (_int, [_vp, _i64, _i64, _vp, _int, _vp, _int, _vp, _int, _vp, _i64, _int, _dbl, _dbl,

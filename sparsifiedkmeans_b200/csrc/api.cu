@@ -612,6 +612,20 @@ extern "C" int skm_lloyd_argmax_distance(skm_lloyd *L, double *maxdist, int64_t 
     return d2h_sync(ctx, j, i.ptr, sizeof(int64_t));
 }
 
+extern "C" const char *skm_lloyd_kernel_name(skm_lloyd *L)
+{
+    static thread_local char name[96];
+    name[0] = 0;
+    if (!L) return name;
+    FastPlan pl;
+    const skm_dataset *ds = L->ds;
+    if (ds->store_dtype == SKM_F32 && L->table && skm_fast_plan(ds->ctx, ds->p, L->K, &pl, ds->max_col_nnz)) {
+        if (pl.mode64) snprintf(name, sizeof name, "k_assign_fast64<%d>", pl.kc);
+        else snprintf(name, sizeof name, "k_assign_fast<%d>%s x%d", pl.kc, pl.global_table ? " (global table)" : "", pl.nchunks);
+    } else snprintf(name, sizeof name, "k_exact_assign");
+    return name;
+}
+
 extern "C" void *skm_lloyd_assign_ptr(skm_lloyd *L) { return L ? L->assign : nullptr; }
 extern "C" void *skm_lloyd_dist_ptr(skm_lloyd *L, int *dtype)
 {

@@ -69,13 +69,14 @@ __device__ __forceinline__ void tma_stage(void *smem_dst, const void *gsrc, uint
                 ::"r"(dst + off), "l"(src + off), "r"(sz), "r"(bar_a) : "memory");
         }
     }
-    uint32_t done = 0;
+    uint32_t done = 0, spins = 0;
     while (!done) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
             "selp.b32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(bar_a) : "memory");
+        if (!done && ++spins > (1u << 26)) __trap();       // a copy that never lands is a bug, not a hang
     }
 }
 
@@ -385,7 +386,7 @@ bool skm_fast_plan(const skm_ctx *ctx, int64_t p, int64_t K, FastPlan *plan, int
             plan->kc = kc;
             plan->ks = kc;
             plan->nchunks = 1;
-            plan->smem = (bytes + 127) & ~(size_t)127;
+            plan->smem = (bytes + 127 + 16) & ~(size_t)127;
             plan->threads = 512;
             plan->global_table = false;
             return true;
@@ -426,7 +427,7 @@ bool skm_fast_plan(const skm_ctx *ctx, int64_t p, int64_t K, FastPlan *plan, int
 size_t skm_fast_table_floats(int64_t p, const FastPlan &pl)
 {
     (void)p;
-    return (size_t)pl.rows * pl.ks * pl.nchunks;
+    return (size_t)pl.rows * pl.ks * pl.nchunks + 4;        // the staged size is rounded up to 16 bytes
 }
 
 int skm_launch_build_table(skm_ctx *ctx, int64_t p, int64_t K, const double *ct, const FastPlan &pl,
@@ -456,7 +457,7 @@ int skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const
     P.uniform = ds->uniform_width ? 1 : 0;
     P.width2 = ds->sell_width2;
     P.ks = pl.ks;
-    P.table_bytes = (uint32_t)((size_t)pl.rows * pl.ks * sizeof(float));
+    P.table_bytes = (uint32_t)((((size_t)pl.rows * pl.ks * sizeof(float)) + 15) & ~(size_t)15);   // bulk copies move multiples of 16 bytes
     P.ktotal = (int)K;
     P.ga = (float)(1.01 * (m + 5.0) * u);
     P.gb_unit = (float)(2.02 * u * sqrt(m));

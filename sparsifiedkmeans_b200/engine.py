@@ -309,6 +309,10 @@ class Lloyd:
         except Exception:
             pass
 
+    @property
+    def kernel_name(self) -> str:
+        return self._lib.skm_lloyd_kernel_name(self.handle).decode()
+
     def set_centers(self, centers):
         c, K = _centers(centers, self.ds.p)
         if K != self.K:
