@@ -104,7 +104,7 @@ def test_streamed_image_layouts(ctx, p, m, n, ragged):
     assert r0["bad_columns"] == 0 and r0["layout"] == 0 and r0["steps"] > 0
     r1 = ds.layout_check(1)
     assert r1["bad_columns"] == 0 and r1["layout"] == 1
-    if m >= 32:                                              # enough entries per class to balance the two copies
+    if p >= 512:                                             # random rows, enough entries per class to balance the two copies
         assert r1["wavefronts"] == r1["steps"], r1          # conflict-free
     assert r1["wavefronts"] / r1["steps"] <= r0["wavefronts"] / r0["steps"] + 1e-12
     # the kernels agree whatever order the image was left in
