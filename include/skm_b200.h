@@ -231,6 +231,24 @@ int   skm_lloyd_step_host(skm_ctx *ctx, int64_t p, int64_t n, const void *jc, in
                           double *centers_out, int32_t *assign_out, double *dist_out,
                           skm_iter_stats *stats, skm_reduce_fn reduce, void *reduce_user);
 
+/* Second pass over the ORIGINAL dense data (kmeans_sparsified.m:542-560 in core;
+ * private/recalculateAssignmentLargeFile.m:85-113 out of core -- the same two computations chunk by chunk):
+ *   centers_out(:,k) = mean of the columns j with assign_in[j] == k+1 (zero column for an empty cluster;
+ *                      label 0 = unassigned is skipped); counts_out[k] = members          (:545-551)
+ *   [assign_out, dist_out] = nearest column of `centers` in plain Euclidean distance: the dense
+ *                      branch of private/findClusterAssignments.m:124-171 (gamma is not used there) (:558)
+ * x: dense p x n column-major (points are columns), SKM_F32/SKM_F64, in HOST memory (streamed over
+ * PCIe in column chunks on a copy stream; a memory-mapped file works) or, x_on_device != 0, in device
+ * memory.  Every value is multiplied by `scale` first (the reference's X*(1+2*eps), :292; pass 1.0 for none).
+ * Either half may be skipped: centers_out == NULL (then assign_in may be NULL) or assign_out == dist_out
+ * == NULL (then centers may be NULL).  Distances are evaluated in fp32 as sum (x-c)^2 with the same
+ * rounding guard as the sparsified kernel; columns whose winner cannot be certified are re-evaluated in
+ * fp64 (n_rechecked, may be NULL).  assign_out is 1-based. */
+int   skm_second_pass(skm_ctx *ctx, int64_t p, int64_t n, const void *x, int x_type, int x_on_device,
+                      double scale, const double *centers, int64_t K, const int32_t *assign_in,
+                      double *centers_out, int64_t *counts_out, int32_t *assign_out, double *dist_out,
+                      int64_t chunk_cols, int64_t *n_rechecked);
+
 /* k-means++ support (private/Arthur_initialization.m:39-53): fold the masked
  * distance to ONE new centre into the running minimum kept on the device.
  * first != 0 resets the running minimum.  sum_d2 receives sum_j mind_j^2 over

@@ -116,6 +116,40 @@ def find_cluster_assignments(X: sp.csc_matrix, centers, gamma=None, centers_spar
     return assign, dist, D
 
 
+def find_cluster_assignments_dense(X: np.ndarray, centers: np.ndarray):
+    """Dense-X branch of findClusterAssignments, the non-pdist2 arm
+    (/root/reference/private/findClusterAssignments.m:154-163, :168-175):
+    distances(k,:) = nrm2 - 2*(X'*c_k)' + norm(c_k)^2, min over k (first occurrence), then
+    sqrt(max(0, .)) of the minimum only.  float64; the BLAS summation order of X'*c_k is not
+    pinned by the reference (parity unpinned at the 1e-15 level).
+    Returns (assign 1-based (n,), dist (n,), D2 (k, n) squared distances)."""
+    X = np.asarray(X, dtype=np.float64)
+    centers = np.asarray(centers, dtype=np.float64)
+    p, n = X.shape
+    k = centers.shape[1]
+    nrm2 = np.sum(X * X, axis=0)                                         # :155
+    D2 = np.empty((k, n))
+    for ki in range(k):
+        D2[ki, :] = nrm2 - 2.0 * (X.T @ centers[:, ki]) + np.linalg.norm(centers[:, ki]) ** 2   # :157
+    assign = np.argmin(D2, axis=0) + 1                                   # :169 (first occurrence)
+    dist = np.sqrt(np.maximum(0.0, D2[assign - 1, np.arange(n)]))        # :173
+    return assign, dist, D2
+
+
+def second_pass(XFull: np.ndarray, best_centers: np.ndarray, best_assign1: np.ndarray, K: int):
+    """The in-core two-pass block of kmeans_sparsified.m:542-560: XFull is the ORIGINAL data after
+    X*(1+2*eps) (:292, :310), best_centers the unmixed centres of the sparsified run (:523).
+    Returns (centers_twoPass (p,K), assignments_twoPass, distances_twoPass)."""
+    p, n = XFull.shape
+    c2 = np.zeros((p, K))                                                # :545
+    for ki in range(K):
+        ind = np.flatnonzero(best_assign1 == ki + 1)                     # :548
+        if ind.size:
+            c2[:, ki] = np.mean(XFull[:, ind], axis=1)                   # :550
+    a2, d2, _ = find_cluster_assignments_dense(XFull, best_centers)      # :558
+    return c2, a2, d2
+
+
 # ---------------------------------------------------------------------------
 # kmeans_sparsified.m: preconditioning + sampling (explicit randomness)
 # ---------------------------------------------------------------------------

@@ -90,6 +90,8 @@ SIGNATURES = {
     "skm_lloyd_dist_ptr": (_vp, [_vp, C.POINTER(_int)]),
     "skm_lloyd_step_host": (_int, [_vp, _i64, _i64, _vp, _int, _vp, _int, _vp, _int, _vp, _i64, _int, _dbl, _dbl,
                                    _int, _i64, _vp, _vp, _vp, C.POINTER(IterStats), _vp, _vp]),
+    "skm_second_pass": (_int, [_vp, _i64, _i64, _vp, _int, _int, _dbl, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64,
+                               C.POINTER(_i64)]),
     "skm_kpp_update": (_int, [_vp, _vp, _int, _dbl, _int, C.POINTER(_dbl)]),
     "skm_kpp_pick": (_int, [_vp, _dbl, C.POINTER(_i64)]),
     "skm_kpp_get_mindist": (_int, [_vp, _vp]),

@@ -351,6 +351,8 @@ int launch_fast64(skm_ctx *ctx, const FastParams &P, size_t smem)
 
 static const int kKcOptions[] = {4, 8, 12, 16, 24, 32, 48, 64};
 
+int skm_fast_stride(int kc) { return 4 * ((kc / 4) | 1); }
+
 static int stride_for(int kc)
 {
     int chunks = kc / 4;

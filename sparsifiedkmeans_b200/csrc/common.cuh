@@ -225,6 +225,7 @@ struct FastPlan {
 bool skm_fast_plan(const skm_ctx *ctx, int64_t p, int64_t K, FastPlan *plan, int64_t max_col_nnz = -1);
 size_t skm_fast_table_floats(int64_t p, const FastPlan &pl);
 int64_t skm_dual_boff(int64_t p);
+int skm_fast_stride(int kc);     // padded table row stride (floats) of the 16-byte kernels
 int  skm_launch_build_table(skm_ctx *ctx, int64_t p, int64_t K, const double *ct, const FastPlan &pl,
                             float *table, float *cmax);
 int  skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const FastPlan &pl,

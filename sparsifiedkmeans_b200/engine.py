@@ -452,6 +452,63 @@ def lloyd_step_host(p: int, n: int, jc, ir, val, centers, gamma_dist, gamma_upda
     return out_c.reshape(K, p).T.copy(), a, d, Lloyd._stats(st)
 
 
+def second_pass(X, centers=None, assign_in=None, scale: float = 1.0, want_assign: bool = True,
+                want_dist: bool = True, chunk_cols: int = 0, ctx: Context | None = None, x_device_ptr: int | None = None,
+                shape=None, x_dtype=None):
+    """The second pass over the ORIGINAL dense data (skm_second_pass; kmeans_sparsified.m:542-560,
+    private/recalculateAssignmentLargeFile.m:85-113).
+
+    X: dense (p, n) array with points as columns -- any array whose transpose is C-contiguous is
+    used in place (e.g. a np.memmap of an (n, p) file); float32 or float64.  `centers` (p, K) are
+    the centres to re-assign against; `assign_in` (n,) 1-based labels select the columns averaged
+    into the new centres.  Returns a dict with the requested pieces of
+    centers (p, K), counts (K,), assign (n,) 1-based, dist (n,), n_rechecked."""
+    ctx = ctx or default_context()
+    if x_device_ptr is not None:
+        p, n = shape
+        xt = SKM_F32 if np.dtype(x_dtype) == np.float32 else SKM_F64
+        xptr, on_dev, keep = int(x_device_ptr), 1, None
+    else:
+        p, n = X.shape
+        XT = X.T                                            # (n, p): a point per row, contiguous
+        if XT.dtype not in (np.float32, np.float64) or not XT.flags.c_contiguous:
+            XT = np.ascontiguousarray(XT, dtype=np.float64 if XT.dtype != np.float32 else np.float32)
+        xt = SKM_F32 if XT.dtype == np.float32 else SKM_F64
+        xptr, on_dev, keep = XT.ctypes.data, 0, XT
+    want_any_assign = want_assign or want_dist
+    c = K = None
+    if centers is not None:
+        c, K = _centers(centers, p)
+    a_in = None
+    if assign_in is not None:
+        a_in = np.ascontiguousarray(assign_in, dtype=np.int32).reshape(-1)
+        if a_in.shape[0] != n:
+            raise ValueError("assign_in must have one label per column")
+        if K is None:
+            K = int(a_in.max()) if a_in.size else 1
+    if K is None:
+        raise ValueError("need centers and/or assign_in")
+    out = {}
+    c_out = np.empty(p * K, dtype=np.float64) if a_in is not None else None
+    cnt = np.zeros(K, dtype=np.int64) if a_in is not None else None
+    a = np.empty(n, dtype=np.int32) if (want_assign and c is not None) else None
+    d = np.empty(n, dtype=np.float64) if (want_dist and c is not None) else None
+    nre = C.c_int64(0)
+    check(ctx._lib.skm_second_pass(ctx.handle, p, n, C.c_void_p(xptr), xt, on_dev, float(scale),
+                                   _ptr(c) if (c is not None and want_any_assign) else None, K, _ptr(a_in),
+                                   _ptr(c_out), _ptr(cnt), _ptr(a), _ptr(d), int(chunk_cols), C.byref(nre)))
+    del keep
+    if c_out is not None:
+        out["centers"] = c_out.reshape(K, p).T.copy()
+        out["counts"] = cnt
+    if a is not None:
+        out["assign"] = a
+    if d is not None:
+        out["dist"] = d
+    out["n_rechecked"] = int(nre.value)
+    return out
+
+
 def mix_hadamard(X, signs, compute: str = "f64", ctx: Context | None = None) -> np.ndarray:
     """mix(X) = hadamard(D*[X;0])/sqrt(p2) on the GPU (kmeans_sparsified.m:238-248,286-295).
     X is dense p x n (host), signs has p2 = 2^nextpow2(p) entries; returns p2 x n float64."""

@@ -17,8 +17,10 @@ from .engine import Context, Dataset, default_context
 def findClusterAssignments(X, centers, tryBuiltinMex=None, gamma=None, nargout: int = 2,
                            store: str = "f64", ctx: Context | None = None):
     """Sparse X, dense centres -> private/findClusterAssignments.m:77-80 then :168-171;
-    sparse X, sparse centres (scipy sparse `centers`) -> :63-75.  Dense X (:124-166) is the
-    non-sparsified K-means path and is out of scope for this engine.
+    sparse X, sparse centres (scipy sparse `centers`) -> :63-75.  Dense X -> :124-171 (plain
+    Euclidean nearest centre, gamma unused there), evaluated on the GPU as sum (x-c)^2 in fp32 with
+    fp64 re-evaluation of uncertified columns (skm_second_pass); the reference's closed-source
+    pdist2 / BLAS arithmetic is not reproducible bit for bit, ties below ~1e-12 relative are unpinned.
 
     `store` selects how an uploaded X is held: "f64" (default for this stateless call: every
     bit as the reference) or "f32" (the fast kernel; values are rounded to float first).
@@ -32,9 +34,7 @@ def findClusterAssignments(X, centers, tryBuiltinMex=None, gamma=None, nargout: 
         ds = Dataset.from_scipy(X, store=store, ctx=ctx or default_context())
         owns = True
     else:
-        raise NotImplementedError(
-            "findClusterAssignments: dense X (findClusterAssignments.m:124-166) is outside the "
-            "sparsified hot path this engine accelerates")
+        return _dense(np.asarray(X), centers, nargout, ctx or default_context())
     try:
         sparse_centers = sp.issparse(centers)
         c = np.asarray(centers.todense() if sparse_centers else centers, dtype=np.float64)
@@ -60,6 +60,29 @@ def findClusterAssignments(X, centers, tryBuiltinMex=None, gamma=None, nargout: 
     finally:
         if owns:
             ds.close()
+
+
+def _dense(X, centers, nargout, ctx):
+    """Dense-X branch (:124-171) and the optional mean-centres output (:178-188)."""
+    import scipy.sparse as sp
+    from .engine import second_pass
+    c = np.asarray(centers.todense() if sp.issparse(centers) else centers, dtype=np.float64)
+    if c.ndim == 1:
+        c = c.reshape(-1, 1)
+    if X.ndim == 1:
+        X = X.reshape(-1, 1)
+    if c.shape[0] != X.shape[0]:
+        raise ValueError("Array of centers not of correct size")                 # :55
+    res = second_pass(X, centers=c, ctx=ctx)
+    a, d = res["assign"], res["dist"]
+    if nargout < 3:
+        return a, d
+    K = c.shape[1]
+    out = np.zeros((X.shape[0], K))
+    if X.shape[1]:
+        m = second_pass(X, assign_in=a, want_assign=False, want_dist=False, ctx=ctx)["centers"]
+        out[:, :m.shape[1]] = m
+    return a, d, out
 
 
 def _dense_columns(X, ds):

@@ -9,7 +9,9 @@ sequences them the way kmeans_sparsified.m:213-607 does.
 
 Scope: the sparsified path (`Sparsify=True`) with the Hadamard sketch
 (or 'none').  The dense path (Sparsify=False), the DCT sketch, loading from disk (`DataFile`)
-and the two-pass outputs (nargout > 5) are outside the hot path and raise NotImplementedError.
+are outside the hot path and raise NotImplementedError.  The two-pass outputs (`nargout` 6..9:
+centers_twoPass, assignments_twoPass, distances_twoPass, SUMD_twoPass; kmeans_sparsified.m:525-571)
+come from one streamed pass over the original data (skm_second_pass).
 
 Randomness: MATLAB's generators are closed source, so the random draws (Rademacher signs, row
 samples, k-means++ picks) come from `numpy.random.default_rng(Seed)`; every draw can also be
@@ -142,8 +144,6 @@ def kmeans_sparsified(X=None, K=None, **opts):
         raise NotImplementedError("DataFile / load-from-disk (sampleAndMixFromLargeFile.m) is outside the hot path")
     if not o["Sparsify"]:
         raise NotImplementedError("Sparsify=false (dense K-means through pdist2) is outside the sparsified hot path")
-    if o["nargout"] > 5:
-        raise NotImplementedError("two-pass outputs (kmeans_sparsified.m:525-571) are outside the hot path")
     import scipy.sparse as sp
     rng = np.random.default_rng(o["Seed"])
     ctx: Context = o["Context"] or default_context(int(o["Device"]))
@@ -369,7 +369,38 @@ def kmeans_sparsified(X=None, K=None, **opts):
     OUTPUT["TimeOverall_OnePass"] = time.perf_counter() - t0
     C = unmix(best["centers"])                                                        # :523
     IDX, D = best["assignments"], best["distances"]
-    if not o["ColumnSamples"]:                                                        # :586-591
+    two = None
+    nargout = int(o["nargout"])
+    if nargout > 5:                                                                   # :525-571, in-core arm :542-560
+        # one streamed pass over the original data X*(1+2eps) (= XFull, :310): per-cluster means of the
+        # best assignments (:545-551) and, for nargout > 6, dense re-assignment against the unmixed
+        # centres (:558).  The reference only builds the assignments when nargout > 6.
+        from .engine import second_pass
+        if IDX.size != n:
+            raise KMeansError("two-pass outputs need assignments for every sample (EmptyAction='drop' removed them)")
+        t1 = time.perf_counter()
+        res = second_pass(Xd, centers=C if nargout > 6 else None, assign_in=IDX, scale=scale_eps,
+                          want_assign=nargout > 6, want_dist=nargout > 6, ctx=ctx)
+        OUTPUT["TimeSecondPass_Overall"] = time.perf_counter() - t1
+        C2 = res["centers"]
+        if C2.shape[1] < Kb:                                                          # labels never reached Kb
+            C2 = np.concatenate([C2, np.zeros((p, Kb - C2.shape[1]))], axis=1)
+        two = [C2]
+        if nargout > 6:
+            IDX2, D2 = res["assign"], res["dist"]
+            OUTPUT["SecondPassRechecked"] = res["n_rechecked"]
+            two += [IDX2, D2]
+            if nargout >= 9:                                                          # :562-570
+                SUMD2 = np.zeros(Kb)
+                for ki in range(Kb):
+                    # the reference sums the ONE-pass `distances` here (not distances_twoPass), :567
+                    SUMD2[ki] = np.sum(distances[IDX2 == ki + 1] ** 2)
+                two.append(SUMD2)
+    if not o["ColumnSamples"]:                                                        # :586-605
         C = C.T
+        if two is not None:
+            two[0] = two[0].T
     OUTPUT["TimeOverall"] = time.perf_counter() - t0
-    return IDX, C, SUMD, D, OUTPUT
+    if two is None:
+        return IDX, C, SUMD, D, OUTPUT
+    return (IDX, C, SUMD, D, OUTPUT, *two)

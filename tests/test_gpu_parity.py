@@ -177,8 +177,8 @@ def test_find_cluster_assignments_errors(ctx):
     X, c, gamma = make_sparsified(p=32, n=50, m=4, K=3, seed=1)
     with pytest.raises(ValueError, match="not of correct size"):
         findClusterAssignments(X, c[:-1], None, gamma)
-    with pytest.raises(NotImplementedError):
-        findClusterAssignments(np.asarray(X.todense()), c, None, gamma)
+    with pytest.raises(ValueError, match="not of correct size"):
+        findClusterAssignments(np.asarray(X.todense()), c[:-1], None, gamma)
 
 
 def test_upload_rejects_bad_csc(ctx):

@@ -134,6 +134,41 @@ def main():
                       "points_per_s": n / ms * 1e3, "GBps": n * (78 * 8 + 16) / 1e9 / ms * 1e3,
                       "reference_cost": "round k recomputes k centre-passes (Arthur_initialization.m:39); here 1 per round"}), flush=True)
     ds.close()
+    del colptr, rowidx, val
+    torch.cuda.empty_cache()
+
+    # ---- second pass over the original dense data, X resident on the device ----
+    from sparsifiedkmeans_b200 import second_pass
+    for (p, K) in ((784, 10), (1024, 64)):
+        n = min(2_000_000, budget // (4 * p))
+        g = torch.Generator(device=dev).manual_seed(3)
+        mu = torch.randn(K, p, generator=g, device=dev)
+        lab = torch.arange(n, device=dev) % K
+        x = mu[lab] + 0.3 * torch.randn(n, p, generator=g, device=dev)         # (n, p) row-major = p x n column-major
+        cen = (mu + 0.05 * torch.randn(K, p, generator=g, device=dev)).T.double().cpu().numpy()
+        lab1 = (lab + 1).int().cpu().numpy()
+        torch.cuda.synchronize()
+        holder = {}
+
+        def run(sums, assign):
+            holder["r"] = second_pass(None, centers=cen if assign else None, assign_in=lab1 if sums else None,
+                                      want_assign=assign, want_dist=assign, ctx=ctx, x_device_ptr=x.data_ptr(),
+                                      shape=(p, n), x_dtype=np.float32)
+        for name, sums, assign in (("dense per-cluster means (k_dense_sums)", True, False),
+                                   ("dense distance + argmin (k_dense_assign)", False, True)):
+            ctx.timing_enable(True); ctx.timing_read()
+            run(sums, assign); run(sums, assign)
+            tim = ctx.timing_read(); ctx.timing_enable(False)
+            k_ms = tim["assign"][0] / 2
+            out = {"stage": "second pass: " + name, "p": p, "n": n, "K": K, "kernel_ms": k_ms,
+                   "kernel_GBps": 4 * p * n / 1e9 / k_ms * 1e3, "frac_of_hbm_peak": 4 * p * n / 1e9 / k_ms * 1e3 / pk}
+            if assign:
+                out["rechecked"] = holder["r"]["n_rechecked"]
+                out["accuracy_vs_labels"] = float(np.mean(holder["r"]["assign"] == lab1))
+                out["fp32_Tinstr_per_s"] = 2 * K * p * n / 1e12 / k_ms * 1e3
+            print(json.dumps(out), flush=True)
+        del x, mu, lab
+        torch.cuda.empty_cache()
 
 
 if __name__ == "__main__":
