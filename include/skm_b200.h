@@ -288,6 +288,23 @@ int   skm_sample_rows(skm_ctx *ctx, int64_t p2, int64_t n, int64_t m, uint64_t s
 int   skm_dataset_from_dense_host(skm_ctx *ctx, int64_t p, int64_t p2, int64_t n, const void *x, int x_type,
                                   const double *signs, int64_t m, uint64_t seed, int64_t col0,
                                   int64_t chunk_cols, skm_dataset **out);
+/* ---- DCT sketch (kmeans_sparsified.m:226-231,256-258: chosen when p is not a power of two) ---- */
+
+/* y = dct(D .* x) (inverse == 0: mix, :295) or y = D .* idct(x) (inverse != 0: unmix, :296) for a dense
+ * p x n HOST matrix, column-major, fp64; dct is MATLAB's orthonormal DCT-II along columns.  signs
+ * (+-1, length p) may be NULL.  Applied as one dense product on the GPU (cuBLAS, loaded on first use). */
+int   skm_dct_mix(skm_ctx *ctx, int64_t p, int64_t n, const double *x, const double *signs, int inverse, double *y);
+/* skm_dataset_from_dense_host for the DCT sketch (no zero-padding: p2 = p): chunks cross PCIe, are
+ * multiplied by T*diag(signs)*(1+2eps) in fp32 and m rows per column are kept, divided by m/p.
+ * rows_host: int32[m*n] explicit 0-based rows per column (any order, distinct) or NULL = drawn on the
+ * device (Philox4x32-10 keyed by seed, counted by the global column col0+j). */
+int   skm_dataset_from_dense_host_dct(skm_ctx *ctx, int64_t p, int64_t n, const void *x, int x_type,
+                                      const double *signs, int64_t m, uint64_t seed, int64_t col0,
+                                      const int32_t *rows_host, int64_t chunk_cols, skm_dataset **out);
+/* The rows skm_dataset_from_dense_host_dct draws: rows_dev int32[m*n] (device), ascending per column;
+ * any 1 <= m <= p <= 32768 (skm_sample_rows is the power-of-two variant fused into the FWHT). */
+int   skm_sample_rows_general(skm_ctx *ctx, int64_t p, int64_t n, int64_t m, uint64_t seed, int64_t col0,
+                              int32_t *rows_dev);
 /* In-place device FWHT of a dense p2 x n float matrix with sign flip and 1/sqrt(p2). */
 int   skm_fwht_f32_inplace(skm_ctx *ctx, int64_t p2, int64_t n, float *x_dev,
                            const float *signs_dev);

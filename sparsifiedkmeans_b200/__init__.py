@@ -4,8 +4,9 @@ Host-side mirror of the reference's interface (same names, argument meaning and 
 behaviour) over libskm_b200.so, hand-written sm_100a CUDA behind a C ABI
 (include/skm_b200.h).  There is no CPU fallback.
 """
-from .engine import (Context, Dataset, IterStats, Lloyd, default_context,     # noqa: F401
-                     fwht_f32_inplace, lloyd_step_host, mix_hadamard, sample_rows, second_pass)
+from .engine import (Context, Dataset, IterStats, Lloyd, dct_mix, default_context,     # noqa: F401
+                     fwht_f32_inplace, lloyd_step_host, mix_hadamard, sample_rows, sample_rows_general,
+                     second_pass)
 from .find_cluster_assignments import findClusterAssignments                  # noqa: F401
 from .kmeans import (Arthur_initialization, KMeansError, kmeans_sparsified,    # noqa: F401
                      randsample_block, randsample_fixedNumberEntries)

@@ -100,6 +100,10 @@ SIGNATURES = {
     "skm_dataset_from_dense_host": (_int, [_vp, _i64, _i64, _i64, _vp, _int, _vp, _i64, C.c_uint64, _i64, _i64,
                                            C.POINTER(_vp)]),
     "skm_sample_rows": (_int, [_vp, _i64, _i64, _i64, C.c_uint64, _i64, _vp]),
+    "skm_dct_mix": (_int, [_vp, _i64, _i64, _vp, _vp, _int, _vp]),
+    "skm_dataset_from_dense_host_dct": (_int, [_vp, _i64, _i64, _vp, _int, _vp, _i64, C.c_uint64, _i64, _vp, _i64,
+                                               C.POINTER(_vp)]),
+    "skm_sample_rows_general": (_int, [_vp, _i64, _i64, _i64, C.c_uint64, _i64, _vp]),
     "skm_fwht_f32_inplace": (_int, [_vp, _i64, _i64, _vp, _vp]),
 }
 

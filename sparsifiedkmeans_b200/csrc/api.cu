@@ -64,6 +64,8 @@ extern "C" int skm_ctx_create(int device, void *cuda_stream, skm_ctx **out)
     ctx->timing = false;
     ctx->stream_cache = nullptr;
     ctx->stream_cache_free = nullptr;
+    ctx->blas = nullptr;
+    ctx->blas_free = nullptr;
     ctx->ev = nullptr;
     memset(ctx->ev_count, 0, sizeof ctx->ev_count);
     if (cudaMalloc((void **)&ctx->d_flag, 16 * sizeof(int)) != cudaSuccess ||
@@ -82,6 +84,7 @@ extern "C" void skm_ctx_destroy(skm_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->stream_cache && ctx->stream_cache_free) ctx->stream_cache_free(ctx->stream_cache);
+    if (ctx->blas && ctx->blas_free) ctx->blas_free(ctx->blas);
     if (ctx->d_flag) cudaFree(ctx->d_flag);
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
     if (ctx->ev) {

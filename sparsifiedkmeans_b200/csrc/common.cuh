@@ -64,6 +64,8 @@ struct skm_ctx {
     int          ev_count[SKM_T_SLOTS];
     void        *stream_cache;              // staging buffers of skm_lloyd_step_host, reused across calls
     void       (*stream_cache_free)(void *);
+    void        *blas;                      // lazily loaded cuBLAS binding (DCT sketch only), dct.cu
+    void       (*blas_free)(void *);
 };
 
 // RAII: records a start event now and a stop event at scope exit when timing is enabled

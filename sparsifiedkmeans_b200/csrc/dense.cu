@@ -47,7 +47,7 @@ struct DenseParams {
 };
 
 template <int KC, int G>
-__global__ void __launch_bounds__(256) k_dense_assign(const DenseParams P)
+__global__ void __launch_bounds__(256, 2) k_dense_assign(const DenseParams P)
 {
     extern __shared__ __align__(16) float s_tab[];
     const float *tab = P.table;
@@ -82,10 +82,9 @@ __global__ void __launch_bounds__(256) k_dense_assign(const DenseParams P)
             for (int q = 0; q < G; ++q)
 #pragma unroll
                 for (int k = 0; k < KC; ++k) acc[q][k] = 0.f;
-            for (int64_t r = lane; r < p; r += 32) {
-                float xv[G];
-#pragma unroll
-                for (int q = 0; q < G; ++q) xv[q] = __ldcs(xc[q] + r);
+            // U row-steps per trip: all U*G loads are issued before the arithmetic (bytes in flight)
+            constexpr int U = (KC * G <= 48) ? 4 : 2;
+            auto body = [&](const float (&xv)[G], int64_t r) {
                 if (c == 0) {
 #pragma unroll
                     for (int q = 0; q < G; ++q) xm[q] = fmaxf(xm[q], fabsf(xv[q]));
@@ -103,6 +102,22 @@ __global__ void __launch_bounds__(256) k_dense_assign(const DenseParams P)
                         d = xv[q] - v.w; acc[q][4 * k4 + 3] = fmaf(d, d, acc[q][4 * k4 + 3]);
                     }
                 }
+            };
+            int64_t r = lane;
+            for (; r + 32 * (U - 1) < p; r += 32 * U) {
+                float xv[U][G];
+#pragma unroll
+                for (int uu = 0; uu < U; ++uu)
+#pragma unroll
+                    for (int q = 0; q < G; ++q) xv[uu][q] = __ldcs(xc[q] + r + 32 * uu);
+#pragma unroll
+                for (int uu = 0; uu < U; ++uu) body(xv[uu], r + 32 * uu);
+            }
+            for (; r < p; r += 32) {
+                float xv[G];
+#pragma unroll
+                for (int q = 0; q < G; ++q) xv[q] = __ldcs(xc[q] + r);
+                body(xv, r);
             }
             // fold across the warp; every lane ends with every sum
 #pragma unroll
@@ -214,17 +229,17 @@ __global__ void __launch_bounds__(128) k_dense_sums(int64_t p, int64_t n, int kb
     const int64_t ja = (int64_t)blockIdx.y * per, jb = min(n, ja + per);
     const bool live = r < p;
     int64_t j = ja;
-    for (; j + 4 <= jb; j += 4) {
-        const int a0 = assign1[j] - 1 - k0, a1 = assign1[j + 1] - 1 - k0, a2 = assign1[j + 2] - 1 - k0, a3 = assign1[j + 3] - 1 - k0;
-        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-        if (live) {
-            v0 = __ldcs(x + j * p + r); v1 = __ldcs(x + (j + 1) * p + r);
-            v2 = __ldcs(x + (j + 2) * p + r); v3 = __ldcs(x + (j + 3) * p + r);
-        }
-        if ((unsigned)a0 < (unsigned)kb) bins[a0 * 128 + tid] += (double)v0;
-        if ((unsigned)a1 < (unsigned)kb) bins[a1 * 128 + tid] += (double)v1;
-        if ((unsigned)a2 < (unsigned)kb) bins[a2 * 128 + tid] += (double)v2;
-        if ((unsigned)a3 < (unsigned)kb) bins[a3 * 128 + tid] += (double)v3;
+    constexpr int UC = 8;                                  // columns in flight per thread
+    for (; j + UC <= jb; j += UC) {
+        int a[UC];
+        float v[UC];
+#pragma unroll
+        for (int u = 0; u < UC; ++u) a[u] = assign1[j + u] - 1 - k0;
+#pragma unroll
+        for (int u = 0; u < UC; ++u) v[u] = live ? __ldcs(x + (j + u) * p + r) : 0.f;
+#pragma unroll
+        for (int u = 0; u < UC; ++u)
+            if ((unsigned)a[u] < (unsigned)kb) bins[a[u] * 128 + tid] += (double)v[u];
     }
     for (; j < jb; ++j) {
         const int a0 = assign1[j] - 1 - k0;

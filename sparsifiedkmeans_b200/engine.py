@@ -197,6 +197,31 @@ class Dataset:
                                                    int(m), int(seed), int(col0), int(chunk_cols), C.byref(h)))
         return cls(ctx, h)
 
+    @classmethod
+    def from_dense_host_dct(cls, X, signs, m: int, seed: int = 0, col0: int = 0, rows=None, chunk_cols: int = 0,
+                            ctx: Context | None = None):
+        """DCT-sketch twin of from_dense_host (skm_dataset_from_dense_host_dct): X dense (p, n), points
+        are columns; keeps m rows per column of dct(D*X*(1+2eps)) / (m/p).  `rows` (m, n) optional
+        explicit 0-based rows; otherwise drawn on the device from (seed, col0 + column)."""
+        ctx = ctx or default_context()
+        X = np.asarray(X)
+        if X.dtype not in _NP_VALUE:
+            X = X.astype(np.float64)
+        p, n = X.shape
+        Xf = np.ascontiguousarray(X.T).reshape(-1)
+        d = np.ascontiguousarray(signs, dtype=np.float64).reshape(-1)
+        if d.shape[0] != p:
+            raise ValueError("signs must have p entries")
+        r = None
+        if rows is not None:
+            r = np.ascontiguousarray(np.asarray(rows, dtype=np.int32).T).reshape(-1)      # column j at [j*m, j*m+m)
+            if r.shape[0] != m * n:
+                raise ValueError("rows must be (m, n)")
+        h = C.c_void_p()
+        check(ctx._lib.skm_dataset_from_dense_host_dct(ctx.handle, p, n, _ptr(Xf), _NP_VALUE[Xf.dtype], _ptr(d), int(m),
+                                                       int(seed), int(col0), _ptr(r), int(chunk_cols), C.byref(h)))
+        return cls(ctx, h)
+
     def to_scipy(self):
         """Download as a scipy CSC matrix (float64 values) -- for tests and small data."""
         import scipy.sparse as sp
@@ -507,6 +532,29 @@ def second_pass(X, centers=None, assign_in=None, scale: float = 1.0, want_assign
         out["dist"] = d
     out["n_rechecked"] = int(nre.value)
     return out
+
+
+def dct_mix(X, signs=None, inverse: bool = False, ctx: Context | None = None) -> np.ndarray:
+    """mix(X) = dct(D*X) or, inverse, unmix(X) = D*idct(X) (kmeans_sparsified.m:256-258,295-296) for a
+    dense (p, n) host matrix, fp64, on the GPU (skm_dct_mix)."""
+    ctx = ctx or default_context()
+    X = np.asarray(X, dtype=np.float64)
+    if X.ndim == 1:
+        X = X.reshape(-1, 1)
+    p, n = X.shape
+    d = None if signs is None else np.ascontiguousarray(signs, dtype=np.float64).reshape(-1)
+    if d is not None and d.shape[0] != p:
+        raise ValueError("signs must have p entries")
+    Xf = np.ascontiguousarray(X.T).reshape(-1)
+    out = np.empty(p * n, dtype=np.float64)
+    check(ctx._lib.skm_dct_mix(ctx.handle, p, n, _ptr(Xf), _ptr(d), int(inverse), _ptr(out)))
+    return out.reshape(n, p).T
+
+
+def sample_rows_general(p: int, n: int, m: int, seed: int, col0: int, rows_ptr: int, ctx: Context | None = None):
+    """Row sets of the DCT pipeline's on-device sampler into device int32[m*n] (skm_sample_rows_general)."""
+    ctx = ctx or default_context()
+    check(ctx._lib.skm_sample_rows_general(ctx.handle, p, n, m, int(seed), int(col0), C.c_void_p(rows_ptr)))
 
 
 def mix_hadamard(X, signs, compute: str = "f64", ctx: Context | None = None) -> np.ndarray:

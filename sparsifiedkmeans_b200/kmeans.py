@@ -126,6 +126,36 @@ def Arthur_initialization(ds: Dataset, K: int, gamma, rng=None, first=None, unif
     return np.asarray(chosen, dtype=np.int64)
 
 
+def _open_data_file(path: str):
+    """DataFile mode (kmeans_sparsified.m:180-207, private/sampleAndMixFromLargeFile.m:60-107): the matrix
+    stays on disk and is read in column chunks.  The reference reads a MATLAB -v7.3 .mat through `matfile`
+    (HDF5); this image has no HDF5 reader, so the container here is a NumPy .npy file (2-D, float32 or
+    float64), memory-mapped: the precondition+sample pipeline and the second pass stream it chunk by chunk
+    without loading it.  A .mat path is tried through h5py when that module exists."""
+    import os
+    cand = [path, path + ".npy", path + ".mat"]
+    found = next((c for c in cand if os.path.isfile(c)), None)
+    if found is None:
+        raise KMeansError("Cannot find specified data file to load")                  # :191
+    if found.endswith(".mat"):
+        try:
+            import h5py                                                               # noqa: F401
+        except ImportError as e:
+            raise NotImplementedError("MATLAB -v7.3 files need h5py (HDF5), which this image lacks; save the matrix "
+                                      "with numpy.save and pass the .npy path") from e
+        f = h5py.File(found, "r")
+        names = [k for k in f.keys() if not k.startswith("#")]
+        if len(names) != 1:
+            raise KMeansError("Expected a single variable")                           # sampleAndMixFromLargeFile.m:62
+        return np.asarray(f[names[0]]).T                                              # HDF5 stores MATLAB arrays transposed
+    A = np.load(found, mmap_mode="r")
+    if A.ndim != 2 or A.shape[0] < 1 or A.shape[1] < 1:
+        raise KMeansError("Error reading file; returned bad size for matrix")         # :204
+    if A.dtype not in (np.float32, np.float64):
+        raise KMeansError("the data file must hold float32 or float64 values")
+    return A
+
+
 def kmeans_sparsified(X=None, K=None, **opts):
     """See the module docstring.  Returns (IDX, C, SUMD, D, OUTPUT)."""
     if X is None and K is None:                                                    # :120-125
@@ -140,18 +170,26 @@ def kmeans_sparsified(X=None, K=None, **opts):
         raise KMeansError("The value of 'SparsityLevel' is invalid", "MATLAB:InputParser:ArgumentFailedValidation")
     if str(o["EmptyAction"]).lower() not in ("singleton", "error", "drop"):
         raise KMeansError("The value of 'EmptyAction' is invalid", "MATLAB:InputParser:ArgumentFailedValidation")
-    if isinstance(X, str) or o["DataFile"]:
-        raise NotImplementedError("DataFile / load-from-disk (sampleAndMixFromLargeFile.m) is outside the hot path")
+    load_from_disk = isinstance(X, str) or bool(o["DataFile"])
+    if load_from_disk:                                                                # :180-207
+        if not o["Sparsify"]:
+            raise KMeansError('No reason to turn on "LoadFromDisk" option if not sampling')
+        if not isinstance(X, str) and X is not None:
+            warnings.warn('Loading data from disk, ignoring "X" input. Are you sure code is OK?')
+        X = _open_data_file(X if isinstance(X, str) else o["DataFile"])
     if not o["Sparsify"]:
         raise NotImplementedError("Sparsify=false (dense K-means through pdist2) is outside the sparsified hot path")
     import scipy.sparse as sp
     rng = np.random.default_rng(o["Seed"])
     ctx: Context = o["Context"] or default_context(int(o["Device"]))
-    OUTPUT = {"LoadFromDisk": False, "Options": {k: o[k] for k in _DEFAULTS}, "Sparsify": True}
+    OUTPUT = {"LoadFromDisk": load_from_disk, "Options": {k: o[k] for k in _DEFAULTS}, "Sparsify": True}
 
-    Xd = np.asarray(X.todense() if sp.issparse(X) else X, dtype=np.float64)
     if np.iscomplexobj(X):
         raise KMeansError("Code and distance computations require real data")        # :311-313
+    if isinstance(X, np.ndarray) and X.dtype in (np.float32, np.float64):
+        Xd = X                            # used in place (a memory-mapped file is streamed chunk by chunk)
+    else:
+        Xd = np.asarray(X.todense() if sp.issparse(X) else X, dtype=np.float64)
     if not o["ColumnSamples"]:
         Xd = Xd.T                                                                     # :213-215
     p, n = Xd.shape
@@ -172,11 +210,11 @@ def kmeans_sparsified(X=None, K=None, **opts):
         p2 = _nextpow2_size(p)
         OUTPUT["SlowHadamard"] = False
     elif sk == "dct":
-        raise NotImplementedError("SketchType 'DCT' (kmeans_sparsified.m:256-258) is not built yet; "
-                                  "pass SketchType='Hadamard' (rows are zero-padded to a power of two)")
+        if p > 32768:
+            raise NotImplementedError("the DCT sketch is applied as a dense p x p product; p <= 32768")
     elif sk not in ("nothing", "none"):
         raise KMeansError('bad type for "SketchType"')
-    if sk == "hadamard":
+    if sk in ("hadamard", "dct"):
         d = o["Signs"]
         if d is None:
             d = np.ones(p2) if o["FORCE_BUG"] else np.sign(rng.standard_normal(p2))    # :283-287
@@ -191,12 +229,18 @@ def kmeans_sparsified(X=None, K=None, **opts):
     def mix(A):                                                                       # :295
         if d is None:
             return np.asarray(A, dtype=np.float64)
+        if sk == "dct":
+            from .engine import dct_mix
+            return dct_mix(A, d, False, ctx)                                          # H = dct, :257
         from .engine import mix_hadamard
         return mix_hadamard(A, d, o["MixDtype"], ctx)
 
     def unmix(C):                                                                     # :296
         if d is None:
             return C
+        if sk == "dct":
+            from .engine import dct_mix
+            return dct_mix(C, d, True, ctx)                                           # Ht = idct, :258
         Y = ops.hadamard(C, ctx) / math.sqrt(p2)
         return (d.reshape(-1, 1) * Y)[:p, :]
 
@@ -206,14 +250,17 @@ def kmeans_sparsified(X=None, K=None, **opts):
     pipeline = str(o["Pipeline"]).lower()
     if pipeline == "auto":
         # all-GPU precondition + sample when nothing pins the random rows and the sizes allow it
-        pipeline = "device" if (d is not None and o["SampleRows"] is None and 32 <= p2 <= 32768
-                                and o["Store"] == "f32") else "host"
+        ok = (o["SampleRows"] is None and 32 <= p2 <= 32768) if sk == "hadamard" else (sk == "dct")
+        pipeline = "device" if (d is not None and ok and o["Store"] == "f32") else "host"
     if pipeline == "device":
-        if d is None or o["SampleRows"] is not None:
-            raise ValueError("Pipeline='device' needs the Hadamard sketch and on-device row sampling")
+        if d is None or (sk == "hadamard" and o["SampleRows"] is not None):
+            raise ValueError("Pipeline='device' needs the Hadamard sketch with on-device row sampling, or the DCT sketch")
         t1 = time.perf_counter()
         seed = int(rng.integers(0, 2 ** 63 - 1))
-        ds = Dataset.from_dense_host(Xd, d, small_p, seed=seed, ctx=ctx)          # applies *(1+2eps) itself
+        if sk == "dct":
+            ds = Dataset.from_dense_host_dct(Xd, d, small_p, seed=seed, rows=o["SampleRows"], ctx=ctx)
+        else:
+            ds = Dataset.from_dense_host(Xd, d, small_p, seed=seed, ctx=ctx)      # applies *(1+2eps) itself
         OUTPUT["TimeToSketch"] = time.perf_counter() - t1
         OUTPUT["TimeToSample"] = 0.0                                                  # fused into the sketch
         Xs = None

@@ -46,8 +46,10 @@ def test_option_validation_mirrors_input_parser():
         km.kmeans_sparsified(X, 2, Sparsify=True, EmptyAction="explode")
     with pytest.raises(NotImplementedError):
         km.kmeans_sparsified(X, 2)                       # dense path is out of scope
-    with pytest.raises(NotImplementedError):
-        km.kmeans_sparsified("data.mat", 2, Sparsify=True)
+    with pytest.raises(km.KMeansError, match="Cannot find specified data file"):
+        km.kmeans_sparsified("no_such_data_file", 2, Sparsify=True)                   # kmeans_sparsified.m:187-192
+    with pytest.raises(km.KMeansError, match="No reason"):
+        km.kmeans_sparsified("no_such_data_file", 2)                                  # :197-199
     assert km.kmeans_sparsified() == 2.1
 
 

@@ -43,6 +43,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--only-dense", action="store_true", help="only the dense second-pass stage")
     args = ap.parse_args()
     import torch
     from sparsifiedkmeans_b200 import Context, Dataset, fwht_f32_inplace
@@ -54,7 +55,7 @@ def main():
     budget = (1 if args.quick else 8) * (1 << 30)          # bytes of dense input per measurement
 
     # ---- K4: FWHT in place and FWHT + fixed-count row sample, gamma = 0.05 ----
-    for p2 in (512, 4096, 32768):
+    for p2 in (() if args.only_dense else (512, 4096, 32768)):
         n = min(1_000_000, budget // (4 * p2))
         x = torch.randn(n, p2, device=dev)                  # column-major p2 x n
         signs = torch.sign(torch.randn(p2, device=dev))
@@ -119,6 +120,8 @@ def main():
     sys.path.insert(0, ROOT)
     import bench
     n = 250_000 if args.quick else 1_250_000
+    if args.only_dense:
+        n = 1000
     colptr, rowidx, val, mu, start = bench.gen_shard_device(dev, n, 784, 78, 100, col0=0)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
