@@ -139,9 +139,10 @@ int  skm_dataset_create_csc(skm_ctx *ctx, int64_t p, int64_t n,
 void skm_dataset_destroy(skm_dataset *ds);
 int  skm_dataset_get_info(const skm_dataset *ds, skm_dataset_info *info);
 /* Verification / statistics of the streamed (SELL-32) image the fast assignment kernel reads.
- * layout: -1 = check the current image, 0 / 1 = first re-order it for kernel family 0 (16-byte
- * gathers, single table, greedy quarter-warp order) or 1 (8-byte gathers, dual table, exact
- * edge-coloured half-warp order; needs columns of at most 254 entries).
+ * layout: -1 = check the current image, 0 / 1 / 2 = first re-order it for kernel family 0 (16-byte
+ * gathers, single table, greedy quarter-warp order), 1 (8-byte gathers, dual table, exact
+ * edge-coloured half-warp order) or 2 (16-byte gathers, dual table, edge-coloured quarter-warp
+ * order); 1 and 2 need columns of at most 254 entries.
  * out[0] = columns whose image differs from the CSC matrix (must be 0), out[1] = gather steps,
  * out[2] = shared-memory wavefronts those steps cost (== out[1] when conflict-free),
  * out[3] = layout of the image. */

@@ -317,7 +317,7 @@ extern "C" int skm_dataset_layout_check(skm_dataset *ds, int layout, int64_t *ou
 {
     SKM_REQUIRE(ds && out, "NULL argument");
     SKM_TRY(enter(ds->ctx));
-    SKM_REQUIRE(layout >= -1 && layout <= 1, "layout must be -1 (current), 0 or 1");
+    SKM_REQUIRE(layout >= -1 && layout <= 2, "layout must be -1 (current), 0, 1 or 2");
     if (layout >= 0 && ds->store_dtype == SKM_F32) SKM_TRY(skm_sell_ensure_layout(ds, layout));
     SKM_TRY(skm_sell_check(ds, out));
     out[3] = ds->sell_mode;
@@ -475,7 +475,7 @@ extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
     SKM_REQUIRE(!has_gamma || gamma == gamma, "gamma is NaN");
     FastPlan pl;
     const bool fast = ds->store_dtype == SKM_F32 && L->table && skm_fast_plan(ctx, ds->p, L->K, &pl, ds->max_col_nnz);
-    if (fast) SKM_TRY(skm_sell_ensure_layout(ds, pl.mode64 ? 1 : 0));   // entry order of the kernel family (one-off)
+    if (fast) SKM_TRY(skm_sell_ensure_layout(ds, pl.layout));            // entry order of the kernel family (one-off)
     {
         SkmTimed t(ctx, SKM_T_PREP);
         SKM_TRY(skm_launch_prep_centers(ctx, ds->p, L->K, L->centers, has_gamma, gamma, L->cscaled_t, nullptr, nullptr));
@@ -624,7 +624,8 @@ extern "C" const char *skm_lloyd_kernel_name(skm_lloyd *L)
     const skm_dataset *ds = L->ds;
     if (ds->store_dtype == SKM_F32 && L->table && skm_fast_plan(ds->ctx, ds->p, L->K, &pl, ds->max_col_nnz)) {
         if (pl.mode64) snprintf(name, sizeof name, "k_assign_fast64<%d>", pl.kc);
-        else snprintf(name, sizeof name, "k_assign_fast<%d>%s x%d", pl.kc, pl.global_table ? " (global table)" : "", pl.nchunks);
+        else snprintf(name, sizeof name, "k_assign_fast<%d>%s%s x%d", pl.kc, pl.global_table ? " (global table)" : "",
+                      pl.dual8 ? " (dual table)" : "", pl.nchunks);
     } else snprintf(name, sizeof name, "k_exact_assign");
     return name;
 }

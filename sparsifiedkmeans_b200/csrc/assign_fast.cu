@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include <math.h>
 #include <stdlib.h>
+#include <algorithm>
 
 namespace {
 
@@ -383,6 +384,8 @@ bool skm_fast_plan(const skm_ctx *ctx, int64_t p, int64_t K, FastPlan *plan, int
         if (!off && K <= 14 && ((kc / 2) & 1) && max_col_nnz >= 0 && max_col_nnz <= 254 && p < (1 << 20) &&
             bytes <= budget / 2) {
             plan->mode64 = true;
+            plan->dual8 = false;
+            plan->layout = 1;
             plan->boff = (int)boff;
             plan->rows = boff + p;
             plan->kc = kc;
@@ -394,6 +397,8 @@ bool skm_fast_plan(const skm_ctx *ctx, int64_t p, int64_t K, FastPlan *plan, int
             return true;
         }
     }
+    plan->dual8 = false;
+    plan->layout = 0;
     int best = -1;
     // largest chunk whose table fits; then the smallest chunk that needs no more launches
     // (K=64 with room for 48 centres takes two launches of 32, not 48 + 16)
@@ -417,6 +422,44 @@ bool skm_fast_plan(const skm_ctx *ctx, int64_t p, int64_t K, FastPlan *plan, int
     const int launches = (int)((K + best - 1) / best);
     for (int kc : kKcOptions) {
         if ((K + kc - 1) / kc <= launches) { best = kc; break; }
+    }
+    // Dual-table alternative (conflict-free schedule, SELL layout mode 2): the table is staged twice, so
+    // chunks are smaller and there may be more launches.  Cost model in "centre units" per launch
+    // (measured, K=64 p=1024 m=51: 0.096 ms per centre with the greedy order's ~23% conflicts, 0.078
+    // conflict-free; a launch cannot beat its HBM pass, ~0.85 ms = 10.9 units).
+    {
+        static const bool off = getenv("SKM_NO_DUAL8") != nullptr;
+        static const bool force = getenv("SKM_FORCE_DUAL8") != nullptr;
+        const int64_t boff = skm_dual_boff(p);
+        int bd = -1;
+        for (int kc : kKcOptions) {
+            size_t bytes = (size_t)(boff + p) * stride_for(kc) * sizeof(float);
+            if (bytes > budget) break;
+            bd = kc;
+            if (kc >= K) break;
+        }
+        if (!off && bd > 0 && max_col_nnz >= 0 && max_col_nnz <= 254 && p < (1 << 20)) {
+            const int ld = (int)((K + bd - 1) / bd);
+            for (int kc : kKcOptions) { if ((K + kc - 1) / kc <= ld) { bd = kc; break; } }
+            auto cost = [&](int kc, double per_centre) {
+                double t = 0;
+                for (int64_t k0 = 0; k0 < K; k0 += kc) t += std::max(per_centre * (double)kc, 10.9 * 0.078);
+                return t;
+            };
+            const double t_single = cost(best, 0.096), t_dual = cost(bd, 0.078);
+            if (force || t_dual < 0.97 * t_single) {
+                plan->dual8 = true;
+                plan->layout = 2;
+                plan->boff = (int)boff;
+                plan->rows = boff + p;
+                plan->kc = bd;
+                plan->ks = stride_for(bd);
+                plan->nchunks = (int)((K + bd - 1) / bd);
+                plan->smem = (((size_t)plan->rows * plan->ks * sizeof(float)) + 127) & ~(size_t)127;
+                plan->threads = 256;
+                return true;
+            }
+        }
     }
     plan->kc = best;
     plan->ks = stride_for(best);
@@ -478,6 +521,10 @@ int skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const
         P.first = (c == 0);
         P.last = (c == pl.nchunks - 1);
         int rc;
+        if (pl.dual8 && ds->sell_mode != 2 && !ds->sell_plain) {
+            skm_set_error("assign_fast: the SELL image is not in the dual-table (mode 2) layout");
+            return SKM_ERR_STATE;
+        }
         if (pl.mode64) {
             if (ds->sell_mode != 1 && !ds->sell_plain) {
                 skm_set_error("assign_fast64: the SELL image is not in the dual-table layout");
@@ -503,16 +550,17 @@ int skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const
             if (rc != SKM_OK) return rc;
             continue;
         }
+        // CTA shape by table size: one wide CTA per SM when the table leaves room for nothing else
+        const bool one = pl.smem > 110 * 1024, two = !one && pl.smem > 54 * 1024;
         switch (pl.kc) {
-            case 4:  rc = launch_fast<4, 256, 4>(ctx, P, pl.smem); break;
-            case 8:  rc = launch_fast<8, 256, 4>(ctx, P, pl.smem); break;
-            case 12: rc = launch_fast<12, 256, 4>(ctx, P, pl.smem); break;
-            case 16: rc = launch_fast<16, 256, 4>(ctx, P, pl.smem); break;
-            case 24: rc = launch_fast<24, 256, 3>(ctx, P, pl.smem); break;
-            // a table above ~110 KB leaves room for one CTA per SM: use a wide CTA to keep 16 warps resident
-            case 32: rc = pl.smem > 110 * 1024 ? launch_fast<32, 512, 1>(ctx, P, pl.smem) : launch_fast<32, 256, 2>(ctx, P, pl.smem); break;
-            case 48: rc = pl.smem > 110 * 1024 ? launch_fast<48, 512, 1>(ctx, P, pl.smem) : launch_fast<48, 256, 2>(ctx, P, pl.smem); break;
-            case 64: rc = pl.smem > 110 * 1024 ? launch_fast<64, 512, 1>(ctx, P, pl.smem) : launch_fast<64, 256, 2>(ctx, P, pl.smem); break;
+            case 4:  rc = one ? launch_fast<4, 1024, 1>(ctx, P, pl.smem) : two ? launch_fast<4, 512, 2>(ctx, P, pl.smem) : launch_fast<4, 256, 4>(ctx, P, pl.smem); break;
+            case 8:  rc = one ? launch_fast<8, 1024, 1>(ctx, P, pl.smem) : two ? launch_fast<8, 512, 2>(ctx, P, pl.smem) : launch_fast<8, 256, 4>(ctx, P, pl.smem); break;
+            case 12: rc = one ? launch_fast<12, 1024, 1>(ctx, P, pl.smem) : two ? launch_fast<12, 512, 2>(ctx, P, pl.smem) : launch_fast<12, 256, 4>(ctx, P, pl.smem); break;
+            case 16: rc = one ? launch_fast<16, 1024, 1>(ctx, P, pl.smem) : two ? launch_fast<16, 512, 2>(ctx, P, pl.smem) : launch_fast<16, 256, 4>(ctx, P, pl.smem); break;
+            case 24: rc = one ? launch_fast<24, 512, 1>(ctx, P, pl.smem) : launch_fast<24, 256, 3>(ctx, P, pl.smem); break;
+            case 32: rc = one ? launch_fast<32, 512, 1>(ctx, P, pl.smem) : launch_fast<32, 256, 2>(ctx, P, pl.smem); break;
+            case 48: rc = one ? launch_fast<48, 512, 1>(ctx, P, pl.smem) : launch_fast<48, 256, 2>(ctx, P, pl.smem); break;
+            case 64: rc = one ? launch_fast<64, 512, 1>(ctx, P, pl.smem) : launch_fast<64, 256, 2>(ctx, P, pl.smem); break;
             default: skm_set_error("assign_fast: unsupported chunk %d", pl.kc); return SKM_ERR_UNSUPPORTED;
         }
         if (rc != SKM_OK) return rc;

@@ -120,7 +120,8 @@ struct skm_dataset {
     int64_t *slice_ptr;                 // [nslices+1], in int4 units
     int64_t  nslices, sell_elems;       // sell_elems in int4 units
     int      sell_mode;                 // 0: single table, quarter-warp (row mod 8) greedy order
-                                        // 1: dual table, half-warp (row mod 16) edge-coloured order
+                                        // 1: dual table, half-warp (row mod 16) edge-coloured order (8-byte gathers)
+                                        // 2: dual table, quarter-warp (row mod 8) edge-coloured order (16-byte gathers)
     bool     sell_plain;                // stored order with true rows (streamed views)
     int      sell_wmax;                 // largest slice width in entries
     bool     uniform_width;             // every slice has the same width
@@ -220,7 +221,9 @@ struct FastPlan {
     int threads;
     bool global_table; // table gathered from global memory (too large for shared memory)
     bool mode64;       // LDS.64 kernel on a dual table (needs the SELL image in layout mode 1)
-    int  boff;         // first row of the second table copy (mode64), else 0
+    bool dual8;        // 16-byte kernel on a dual table (needs the SELL image in layout mode 2)
+    int  boff;         // first row of the second table copy (mode64 / dual8), else 0
+    int  layout;       // SELL layout mode this plan reads: 0, 1 or 2
     int64_t rows;      // table rows per chunk (p + 1, or boff + p for a dual table)
 };
 // max_col_nnz < 0: the caller's SELL image is in stored order / cannot be re-laid out -> never mode64

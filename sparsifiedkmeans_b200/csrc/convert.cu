@@ -216,39 +216,41 @@ struct SchedOut {
     __device__ void operator()(int l, int t, unsigned char code) const { dst[(size_t)l * W + t] = code; }
 };
 
-__global__ void k_sched_dual16(int64_t n, int64_t nslices, int wmax, const int64_t *__restrict__ colptr,
-                               const int32_t *__restrict__ rowidx, const int64_t *__restrict__ slice_ptr,
-                               int4 *__restrict__ sell, unsigned long long *__restrict__ overflow_total)
+template <int NL>
+__global__ void k_sched_dual(int64_t n, int64_t nslices, int wmax, const int64_t *__restrict__ colptr,
+                             const int32_t *__restrict__ rowidx, const int64_t *__restrict__ slice_ptr,
+                             int4 *__restrict__ sell, unsigned long long *__restrict__ overflow_total)
 {
+    constexpr int PARTS = 32 / NL;                        // problems per slice: 2 half-warps or 4 quarter-warps
     extern __shared__ __align__(16) unsigned char sraw[];
     const int nt = blockDim.x, tid = threadIdx.x;
     SchedMem M;
     M.b = sraw; M.nt = nt; M.t = tid;
-    M.w = reinterpret_cast<uint32_t *>(sraw + (((size_t)skm_sched16_bytes(wmax) * nt + 15) & ~(size_t)15));
+    M.w = reinterpret_cast<uint32_t *>(sraw + (((size_t)skm_sched_bytes(NL, wmax) * nt + 15) & ~(size_t)15));
 
-    const int64_t prob = (int64_t)blockIdx.x * nt + tid;  // half-warp index
-    if (prob >= 2 * nslices) return;
-    const int64_t slice = prob >> 1;
-    const int half = (int)(prob & 1);
+    const int64_t prob = (int64_t)blockIdx.x * nt + tid;  // half- / quarter-warp index
+    if (prob >= PARTS * nslices) return;
+    const int64_t slice = prob / PARTS;
+    const int half = (int)(prob % PARTS);
     const int64_t base = slice_ptr[slice];
     const int W = (int)((slice_ptr[slice + 1] - base) >> 5) * 2;
     if (W == 0) return;
-    for (int i = 0; i < 256; ++i) M.B(i) = 0;
-    for (int l = 0; l < 16; ++l) {
-        const int64_t j = slice * SKM_SLICE + half * 16 + l;
+    for (int i = 0; i < NL * NL; ++i) M.B(i) = 0;
+    for (int l = 0; l < NL; ++l) {
+        const int64_t j = slice * SKM_SLICE + half * NL + l;
         int64_t a = 0, b = 0;
         if (j < n) { a = colptr[j]; b = colptr[j + 1]; }
-        for (int64_t t = a; t < b; ++t) M.B(l * 16 + (rowidx[t] & 15)) += 1;
+        for (int64_t t = a; t < b; ++t) M.B(l * NL + (rowidx[t] & (NL - 1))) += 1;
     }
     SchedOut out;
-    out.dst = reinterpret_cast<unsigned char *>(sell + base) + (size_t)half * 16 * W;
+    out.dst = reinterpret_cast<unsigned char *>(sell + base) + (size_t)half * NL * W;
     out.W = W;
-    const int ovf = skm_sched16(M, W, wmax, out);
+    const int ovf = skm_sched<NL>(M, W, wmax, out);
     if (ovf) atomicAdd(overflow_total, (unsigned long long)ovf);
 }
 
 template <typename VT>
-__global__ void k_fill_sell_sched(int64_t p, int64_t n, int64_t nslices, int wmax, int boff,
+__global__ void k_fill_sell_sched(int64_t p, int64_t n, int64_t nslices, int wmax, int boff, int nl,
                                   const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
                                   const VT *__restrict__ val, const int64_t *__restrict__ slice_ptr,
                                   int4 *__restrict__ sell)
@@ -270,9 +272,10 @@ __global__ void k_fill_sell_sched(int64_t p, int64_t n, int64_t nslices, int wma
     const int W = 2 * w2;
     const unsigned char *sched = reinterpret_cast<const unsigned char *>(sell + base) + (size_t)lane * W;
     for (int t = 0; t < W; ++t) code[t * 32 + lane] = sched[t];
-    // counting sort of this lane's entries by (row & 15)
+    // counting sort of this lane's entries by (row & (nl - 1))
+    const int mk = nl - 1;
     for (int g = 0; g < 16; ++g) st[g * 32 + lane] = 0;
-    for (int t = 0; t < len; ++t) st[(rowidx[a + t] & 15) * 32 + lane] += 1;
+    for (int t = 0; t < len; ++t) st[(rowidx[a + t] & mk) * 32 + lane] += 1;
     int run = 0;
     for (int g = 0; g < 16; ++g) { const int c = st[g * 32 + lane]; st[g * 32 + lane] = (unsigned short)run; run += c; }
     {
@@ -280,7 +283,7 @@ __global__ void k_fill_sell_sched(int64_t p, int64_t n, int64_t nslices, int wma
 #pragma unroll
         for (int g = 0; g < 16; ++g) fill[g] = st[g * 32 + lane];
         for (int t = 0; t < len; ++t) {
-            const int g = rowidx[a + t] & 15;
+            const int g = rowidx[a + t] & mk;
             int pos = 0;
 #pragma unroll
             for (int q = 0; q < 16; ++q) { if (q == g) { pos = fill[q]; fill[q] = (unsigned short)(pos + 1); } }
@@ -292,7 +295,7 @@ __global__ void k_fill_sell_sched(int64_t p, int64_t n, int64_t nslices, int wma
     for (int step = 0; step < W; ++step) {
         const int cd = code[step * 32 + lane];
         int r, xb = 0;
-        if (cd & 0x80) r = (int)p + (((cd & 15) - (int)(p & 15)) & 15);
+        if (cd & 0x80) r = (int)p + (((cd & 15) - (int)(p & mk)) & mk);
         else {
             const int g = cd & 15;
             const int pos = st[g * 32 + lane];
@@ -331,7 +334,7 @@ __global__ void k_sell_check(int64_t p, int64_t n, int64_t nslices, int mode, in
     };
     for (int64_t t = a; t < b; ++t) { c0++; s0 += (unsigned)rowidx[t]; h0 += mix((unsigned)rowidx[t], (unsigned)__float_as_int(val[t])); }
     unsigned long long steps = 0, waves = 0;
-    const int group = mode == 1 ? 16 : 8, mod = mode == 1 ? 16 : 8;
+    const int group = mode == 1 ? 16 : 8, mod = group;
     bool bad = false;
     for (int t = 0; t < 2 * w2; ++t) {
         const int4 q = sell[base + (int64_t)(t >> 1) * 32 + lane];
@@ -347,9 +350,9 @@ __global__ void k_sell_check(int64_t p, int64_t n, int64_t nslices, int mode, in
         int mx = mult;
         for (int o = group >> 1; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         if ((lane & (group - 1)) == 0) { steps += 1; waves += mx; }
-        if (mode == 1 && r >= boff) { r -= boff; if (r >= p) bad = true; }
+        if (mode >= 1 && r >= boff) { r -= boff; if (r >= p) bad = true; }
         if (r >= p) {                                        // pad: a zero row, value 0
-            if (xb != 0 || r >= p + (mode == 1 ? 16 : 1)) bad = true;
+            if (xb != 0 || r >= p + (mode >= 1 ? 16 : 1)) bad = true;
             continue;
         }
         c1++; s1 += (unsigned)r; h1 += mix((unsigned)r, (unsigned)xb);
@@ -571,21 +574,28 @@ int skm_sell_ensure_layout(skm_dataset *ds, int mode)
         ds->sell_mode = mode; ds->sell_plain = true;
         return SKM_OK;
     }
-    if (mode == 1) {
+    if (mode == 1 || mode == 2) {
         if (wmax <= 0 || wmax > 254) { skm_set_error("dual-table layout needs columns of at most 254 entries"); return SKM_ERR_UNSUPPORTED; }
-        // scheduler: one thread per half-warp, as many as the scratch allows (interleaved shared memory)
-        const size_t per = (size_t)skm_sched16_bytes(wmax) + 4 * (size_t)skm_sched16_words(wmax);
+        const int nl = mode == 1 ? 16 : 8;
+        // scheduler: one thread per half-/quarter-warp, as many as the scratch allows (interleaved shared memory)
+        const size_t per = (size_t)skm_sched_bytes(nl, wmax) + 4 * (size_t)skm_sched_words(nl, wmax);
         int nt = (int)(((size_t)ctx->smem_optin - 1024) / per);
         if (nt > 64) nt = 64;
         if (nt < 1) { skm_set_error("dual-table scheduler does not fit in shared memory"); return SKM_ERR_UNSUPPORTED; }
-        const size_t smem = (((size_t)skm_sched16_bytes(wmax) * nt + 15) & ~(size_t)15) + 4 * (size_t)skm_sched16_words(wmax) * nt;
-        SKM_CUDA(cudaFuncSetAttribute(k_sched_dual16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const size_t smem = (((size_t)skm_sched_bytes(nl, wmax) * nt + 15) & ~(size_t)15) + 4 * (size_t)skm_sched_words(nl, wmax) * nt;
         DevBuf ovf;
         SKM_TRY(ovf.alloc(sizeof(unsigned long long)));
         SKM_CUDA(cudaMemsetAsync(ovf.ptr, 0, sizeof(unsigned long long), ctx->stream));
-        const int64_t probs = 2 * nslices;
-        k_sched_dual16<<<(unsigned)((probs + nt - 1) / nt), nt, smem, ctx->stream>>>(
-            n, nslices, wmax, ds->colptr, ds->rowidx, ds->slice_ptr, ds->sell, ovf.as<unsigned long long>());
+        const int64_t probs = (32 / nl) * nslices;
+        if (nl == 16) {
+            SKM_CUDA(cudaFuncSetAttribute(k_sched_dual<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_sched_dual<16><<<(unsigned)((probs + nt - 1) / nt), nt, smem, ctx->stream>>>(
+                n, nslices, wmax, ds->colptr, ds->rowidx, ds->slice_ptr, ds->sell, ovf.as<unsigned long long>());
+        } else {
+            SKM_CUDA(cudaFuncSetAttribute(k_sched_dual<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_sched_dual<8><<<(unsigned)((probs + nt - 1) / nt), nt, smem, ctx->stream>>>(
+                n, nslices, wmax, ds->colptr, ds->rowidx, ds->slice_ptr, ds->sell, ovf.as<unsigned long long>());
+        }
         SKM_CHECK_LAUNCH(ctx);
         int warps = 8;
         const size_t per_warp = (size_t)wmax * 64 + 16 * 64 + (size_t)wmax * 32;
@@ -593,11 +603,11 @@ int skm_sell_ensure_layout(skm_dataset *ds, int mode)
         const size_t smem2 = (size_t)warps * per_warp;
         SKM_CUDA(cudaFuncSetAttribute(k_fill_sell_sched<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         k_fill_sell_sched<float><<<(unsigned)((nslices + warps - 1) / warps), warps * 32, smem2, ctx->stream>>>(
-            ds->p, n, nslices, wmax, (int)skm_dual_boff(ds->p), ds->colptr, ds->rowidx, (const float *)ds->val,
+            ds->p, n, nslices, wmax, (int)skm_dual_boff(ds->p), nl, ds->colptr, ds->rowidx, (const float *)ds->val,
             ds->slice_ptr, ds->sell);
         SKM_CHECK_LAUNCH(ctx);
         SKM_CUDA(cudaStreamSynchronize(ctx->stream));          // ovf dies here
-        ds->sell_mode = 1; ds->sell_plain = false;
+        ds->sell_mode = mode; ds->sell_plain = false;
         return SKM_OK;
     }
     const bool banked = wmax > 0 && wmax <= 1024 && !getenv("SKM_NO_BANKED");
@@ -631,7 +641,7 @@ int skm_sell_check(skm_dataset *ds, int64_t out[3])
     SKM_TRY(r.alloc(3 * sizeof(unsigned long long)));
     SKM_CUDA(cudaMemsetAsync(r.ptr, 0, 3 * sizeof(unsigned long long), ctx->stream));
     int64_t blocks = (ds->nslices * 32 + 255) / 256;
-    k_sell_check<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ds->p, ds->n, ds->nslices, ds->sell_mode == 1 ? 1 : 0,
+    k_sell_check<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ds->p, ds->n, ds->nslices, ds->sell_mode >= 1 ? ds->sell_mode : 0,
                                                            (int)skm_dual_boff(ds->p), ds->colptr, ds->rowidx,
                                                            (const float *)ds->val, ds->slice_ptr, ds->sell,
                                                            r.as<unsigned long long>());

@@ -392,7 +392,7 @@ extern "C" int skm_second_pass(skm_ctx *ctx, int64_t p, int64_t n, const void *x
         SKM_TRY(skm_launch_prep_centers(ctx, p, K, dcent.as<double>(), 0, 1.0, ct.as<double>(), nullptr, nullptr));
         FastPlan fp;
         fp.kc = dp.kc; fp.ks = dp.ks; fp.nchunks = dp.nchunks; fp.smem = 0; fp.threads = 256; fp.global_table = false;
-        fp.mode64 = false; fp.boff = 0; fp.rows = p + 1;
+        fp.mode64 = false; fp.dual8 = false; fp.layout = 0; fp.boff = 0; fp.rows = p + 1;
         SKM_TRY(skm_launch_build_table(ctx, p, K, ct.as<double>(), fp, table.as<float>(), cmax.as<float>()));
     }
     if (want_sums) {

@@ -33,55 +33,59 @@ SKM_HD static inline int skm_ffs32(uint32_t m)
 #endif
 }
 
+// NL = lanes per problem = bank classes: 16 (half-warp, 8-byte gathers) or 8 (quarter-warp, 16-byte gathers)
 // bytes / words of scratch per problem
-SKM_HD static inline int skm_sched16_bytes(int wmax) { return 768 + 32 * wmax; }
-SKM_HD static inline int skm_sched16_words(int wmax) { return 32 * ((wmax + 31) >> 5); }
+SKM_HD static inline int skm_sched_bytes(int nl, int wmax) { return 3 * nl * nl + 2 * nl * wmax; }
+SKM_HD static inline int skm_sched_words(int nl, int wmax) { return 2 * nl * ((wmax + 31) >> 5); }
+SKM_HD static inline int skm_sched16_bytes(int wmax) { return skm_sched_bytes(16, wmax); }
+SKM_HD static inline int skm_sched16_words(int wmax) { return skm_sched_words(16, wmax); }
 
 // Mem: B(i) -> unsigned char&, Wd(i) -> uint32_t&  (scratch of skm_sched16_bytes / _words)
-// On entry B(l*16+g), l,g in [0,16), holds cnt[l][g]; everything else is scratch.
+// On entry B(l*NL+g), l,g in [0,NL), holds cnt[l][g]; everything else is scratch.
 // Returns the number of entries that could not be scheduled conflict-free (0 when balanced).
-template <class Mem, class Out>
-SKM_HD static int skm_sched16(Mem &M, int W, int wmax, Out &out)
+template <int NL, class Mem, class Out>
+SKM_HD static int skm_sched(Mem &M, int W, int wmax, Out &out)
 {
+    constexpr int MK = NL - 1;
     const int nw = (wmax + 31) >> 5;
-    const int OFF_CNT = 0, OFF_MOV = 256, OFF_OVF = 512, OFF_AT = 768, OFF_ATC = 768 + 16 * wmax;
-    const int OFF_FL = 0, OFF_FC = 16 * nw;
-    for (int i = 256; i < 768; ++i) M.B(i) = 0;
+    const int OFF_CNT = 0, OFF_MOV = NL * NL, OFF_OVF = 2 * NL * NL, OFF_AT = 3 * NL * NL, OFF_ATC = 3 * NL * NL + NL * wmax;
+    const int OFF_FL = 0, OFF_FC = NL * nw;
+    for (int i = NL * NL; i < 3 * NL * NL; ++i) M.B(i) = 0;
 
     // ---- 1. balance ----
-    int T[16], d[16], x[16];
-    for (int c = 0; c < 16; ++c) {
+    int T[NL], d[NL], x[NL];
+    for (int c = 0; c < NL; ++c) {
         int s = 0;
-        for (int l = 0; l < 16; ++l) s += M.B(OFF_CNT + l * 16 + c);
+        for (int l = 0; l < NL; ++l) s += M.B(OFF_CNT + l * NL + c);
         T[c] = s; d[c] = s; x[c] = 0;
     }
     for (int pass = 0; pass < 64; ++pass) {
         bool moved = false;
-        for (int c = 0; c < 16; ++c) {
+        for (int c = 0; c < NL; ++c) {
             const int ex = d[c] - W, avail = T[c] - x[c];
             if (ex > 0 && avail > 0) {
                 const int mv = ex < avail ? ex : avail;
-                x[c] += mv; d[c] -= mv; d[(c + 1) & 15] += mv;
+                x[c] += mv; d[c] -= mv; d[(c + 1) & MK] += mv;
                 moved = true;
             }
         }
         if (!moved) break;
     }
-    for (int c = 0; c < 16; ++c) {          // spread the moves of group c over the lanes, round-robin
+    for (int c = 0; c < NL; ++c) {          // spread the moves of group c over the lanes, round-robin
         int rem = x[c];
         while (rem > 0) {
             bool any = false;
-            for (int l = 0; l < 16 && rem > 0; ++l) {
-                const int have = M.B(OFF_CNT + l * 16 + c), mv = M.B(OFF_MOV + l * 16 + c);
-                if (mv < have) { M.B(OFF_MOV + l * 16 + c) = (unsigned char)(mv + 1); --rem; any = true; }
+            for (int l = 0; l < NL && rem > 0; ++l) {
+                const int have = M.B(OFF_CNT + l * NL + c), mv = M.B(OFF_MOV + l * NL + c);
+                if (mv < have) { M.B(OFF_MOV + l * NL + c) = (unsigned char)(mv + 1); --rem; any = true; }
             }
             if (!any) break;
         }
     }
 
     // ---- 2. edge colouring ----
-    for (int i = 0; i < 32 * wmax; ++i) M.B(OFF_AT + i) = 0xFF;
-    for (int v = 0; v < 32; ++v)
+    for (int i = 0; i < 2 * NL * wmax; ++i) M.B(OFF_AT + i) = 0xFF;
+    for (int v = 0; v < 2 * NL; ++v)
         for (int q = 0; q < nw; ++q) {
             const int lo = q * 32;
             M.Wd(v * nw + q) = (W - lo >= 32) ? 0xffffffffu : (W > lo ? ((1u << (W - lo)) - 1u) : 0u);
@@ -102,10 +106,10 @@ SKM_HD static int skm_sched16(Mem &M, int W, int wmax, Out &out)
         set_free(OFF_FC, c, t, false);
     };
     int overflow = 0;
-    for (int l = 0; l < 16; ++l) {
-        for (int c = 0; c < 16; ++c) {
-            int mult = (int)M.B(OFF_CNT + l * 16 + c) - (int)M.B(OFF_MOV + l * 16 + c) +
-                       (int)M.B(OFF_MOV + l * 16 + ((c + 15) & 15));
+    for (int l = 0; l < NL; ++l) {
+        for (int c = 0; c < NL; ++c) {
+            int mult = (int)M.B(OFF_CNT + l * NL + c) - (int)M.B(OFF_MOV + l * NL + c) +
+                       (int)M.B(OFF_MOV + l * NL + ((c + MK) & MK));
             for (; mult > 0; --mult) {
                 int tc = -1;
                 for (int q = 0; q < nw; ++q) {
@@ -115,10 +119,10 @@ SKM_HD static int skm_sched16(Mem &M, int W, int wmax, Out &out)
                 if (tc >= 0) { put(l, c, tc); continue; }
                 const int a = first_free(OFF_FL, l), b = first_free(OFF_FC, c);
                 if (a < 0) { ++overflow; continue; }                         // lane longer than W: caller's bug
-                if (b < 0) { M.B(OFF_OVF + l * 16 + c) += 1; ++overflow; continue; }   // class holds more than W entries
+                if (b < 0) { M.B(OFF_OVF + l * NL + c) += 1; ++overflow; continue; }   // class holds more than W entries
                 int pl[34], pc[34], np = 0;         // path edges (lane, class), colours a, b, a, ...
                 int vc = c;
-                while (np < 32) {
+                while (np < 2 * NL) {
                     const int l1 = M.B(OFF_ATC + vc * wmax + a);
                     if (l1 == 0xFF) break;
                     pl[np] = l1; pc[np] = vc; ++np;
@@ -150,9 +154,9 @@ SKM_HD static int skm_sched16(Mem &M, int W, int wmax, Out &out)
     }
     // overflow entries: any free step of their lane (a conflict there is accepted)
     if (overflow) {
-        for (int l = 0; l < 16; ++l)
-            for (int c = 0; c < 16; ++c)
-                for (int k = M.B(OFF_OVF + l * 16 + c); k > 0; --k) {
+        for (int l = 0; l < NL; ++l)
+            for (int c = 0; c < NL; ++c)
+                for (int k = M.B(OFF_OVF + l * NL + c); k > 0; --k) {
                     const int t = first_free(OFF_FL, l);
                     if (t < 0) break;
                     M.B(OFF_AT + l * wmax + t) = (unsigned char)(c | 0x20);
@@ -161,20 +165,20 @@ SKM_HD static int skm_sched16(Mem &M, int W, int wmax, Out &out)
     }
 
     // ---- 3. codes ----
-    for (int l = 0; l < 16; ++l) {
+    for (int l = 0; l < NL; ++l) {
         for (int t = 0; t < W; ++t) {
             const int e = M.B(OFF_AT + l * wmax + t);
             unsigned char code;
             if (e == 0xFF) {
                 int cf = -1;
-                for (int c = 0; c < 16; ++c)
+                for (int c = 0; c < NL; ++c)
                     if ((M.Wd(OFF_FC + c * nw + (t >> 5)) >> (t & 31)) & 1u) { cf = c; break; }
                 if (cf < 0) cf = l; else set_free(OFF_FC, cf, t, false);
                 code = (unsigned char)(0x80 | cf);
             } else {
-                const int c = e & 15, gb = (c + 15) & 15;
-                const int ia = OFF_CNT + l * 16 + c, ma = OFF_MOV + l * 16 + c;
-                const int ib = OFF_CNT + l * 16 + gb, mb = OFF_MOV + l * 16 + gb;
+                const int c = e & MK, gb = (c + MK) & MK;
+                const int ia = OFF_CNT + l * NL + c, ma = OFF_MOV + l * NL + c;
+                const int ib = OFF_CNT + l * NL + gb, mb = OFF_MOV + l * NL + gb;
                 if ((int)M.B(ia) - (int)M.B(ma) > 0) { M.B(ia) -= 1; code = (unsigned char)c; }
                 else { M.B(mb) -= 1; M.B(ib) -= 1; code = (unsigned char)(gb | 0x10); }
             }
@@ -183,3 +187,6 @@ SKM_HD static int skm_sched16(Mem &M, int W, int wmax, Out &out)
     }
     return overflow;
 }
+
+template <class Mem, class Out>
+SKM_HD static int skm_sched16(Mem &M, int W, int wmax, Out &out) { return skm_sched<16>(M, W, wmax, out); }
