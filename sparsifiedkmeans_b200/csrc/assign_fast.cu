@@ -425,28 +425,29 @@ bool skm_fast_plan(const skm_ctx *ctx, int64_t p, int64_t K, FastPlan *plan, int
     }
     // Dual-table alternative (conflict-free schedule, SELL layout mode 2): the table is staged twice, so
     // chunks are smaller and there may be more launches.  Cost model in "centre units" per launch
-    // (measured, K=64 p=1024 m=51: 0.096 ms per centre with the greedy order's ~23% conflicts, 0.078
+    // (measured, K=64 p=1024 m=51: 0.096 ms per centre with the greedy order's ~23% conflicts, 0.084
     // conflict-free; a launch cannot beat its HBM pass, ~0.85 ms = 10.9 units).
     {
         static const bool off = getenv("SKM_NO_DUAL8") != nullptr;
         static const bool force = getenv("SKM_FORCE_DUAL8") != nullptr;
         const int64_t boff = skm_dual_boff(p);
+        auto cost = [&](int kc, double per_centre) {
+            double t = 0;
+            for (int64_t k0 = 0; k0 < K; k0 += kc) t += std::max(per_centre * (double)kc, 10.9 * 0.078);
+            return t;
+        };
+        // cheapest dual-table chunk among those whose doubled table fits (padding slots cost like centres)
         int bd = -1;
+        double t_dual = 1e300;
         for (int kc : kKcOptions) {
             size_t bytes = (size_t)(boff + p) * stride_for(kc) * sizeof(float);
             if (bytes > budget) break;
-            bd = kc;
+            const double t = cost(kc, 0.084);
+            if (t < t_dual - 1e-9) { t_dual = t; bd = kc; }
             if (kc >= K) break;
         }
         if (!off && bd > 0 && max_col_nnz >= 0 && max_col_nnz <= 254 && p < (1 << 20)) {
-            const int ld = (int)((K + bd - 1) / bd);
-            for (int kc : kKcOptions) { if ((K + kc - 1) / kc <= ld) { bd = kc; break; } }
-            auto cost = [&](int kc, double per_centre) {
-                double t = 0;
-                for (int64_t k0 = 0; k0 < K; k0 += kc) t += std::max(per_centre * (double)kc, 10.9 * 0.078);
-                return t;
-            };
-            const double t_single = cost(best, 0.096), t_dual = cost(bd, 0.078);
+            const double t_single = cost(best, 0.096);
             if (force || t_dual < 0.97 * t_single) {
                 plan->dual8 = true;
                 plan->layout = 2;

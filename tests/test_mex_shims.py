@@ -24,7 +24,7 @@ def shims():
     subprocess.check_call(["make", "-C", MEXDIR], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     return {n: refmex._load(os.path.join(MEXDIR, "_build", f"libmex_{n}.so"))
             for n in ("SparseMatrixMinusCluster", "SparseMatrixInnerProduct", "SparseMatrixColumnNormSq",
-                      "hadamard", "skm_lloyd_mex")}
+                      "hadamard", "skm_lloyd_mex", "skm_second_pass_mex")}
 
 
 def _bad_calls():
@@ -108,3 +108,36 @@ def test_lloyd_gateway_iterates_like_the_reference_loop(shims):
     wa2, wd2, _ = host_ref.find_cluster_assignments(X, c, None)
     assert np.array_equal(a2.ravel().astype(np.int64), wa2)
     refmex.call_mex(lib, [refmex.mx_string("free", keep), hm], 0)
+
+
+def test_second_pass_gateway_argument_errors(shims):
+    keep = []
+    X = refmex.mx_dense(np.zeros((6, 4)), keep)
+    c = refmex.mx_dense(np.zeros((6, 2)), keep)
+    a = refmex.mx_dense(np.ones((1, 4)), keep)
+    lib = shims["skm_second_pass_mex"]
+    for args, nlhs in (([X, c], 1), ([X, c, a], 4), ([X, refmex.mx_dense(np.zeros((5, 2)), keep), a], 1),
+                       ([X, c, refmex.mx_dense(np.ones((1, 3)), keep)], 1)):
+        with pytest.raises(refmex.MexError):
+            refmex.call_mex(lib, args, nlhs)
+
+
+@pytest.mark.gpu
+def test_second_pass_gateway_matches_two_pass_block(shims):
+    """[centers2, a2, d2] = skm_second_pass_mex(XFull, bestCenters, bestAssignments) against the oracle's
+    restatement of kmeans_sparsified.m:542-560."""
+    from oracle import host_ref
+    rng = np.random.default_rng(2)
+    p, n, K = 40, 900, 4
+    mu = rng.standard_normal((p, K))
+    lab = rng.integers(0, K, n)
+    X = mu[:, lab] + 0.2 * rng.standard_normal((p, n))
+    cen = mu + 0.05 * rng.standard_normal((p, K))
+    keep = []
+    c2, a2, d2 = refmex.call_mex(shims["skm_second_pass_mex"],
+                                 [refmex.mx_dense(X, keep), refmex.mx_dense(cen, keep),
+                                  refmex.mx_dense((lab + 1.0).reshape(1, -1), keep)], 3)
+    wc, wa, wd = host_ref.second_pass(X, cen, lab + 1, K)
+    np.testing.assert_allclose(c2, wc, rtol=1e-6, atol=1e-9)
+    assert np.array_equal(a2.ravel().astype(np.int64), wa)
+    np.testing.assert_allclose(d2.ravel(), wd, rtol=2e-5)
