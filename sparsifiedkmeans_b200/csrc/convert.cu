@@ -197,11 +197,12 @@ __global__ void k_fill_sell_banked(int64_t p, int64_t n, int64_t nslices, int wm
 
 
 // ---------------------------------------------------------------------------------------------
-// Layout mode 1 (dual table, LDS.64 kernel): exact conflict-free schedule per half-warp, see
-// sched16.cuh for the algorithm (balance over the two table copies + bipartite edge colouring).
+// Layout modes 1 / 2 (dual table): exact conflict-free schedule per half- / quarter-warp, see
+// sched16.cuh for the algorithm (balance over the two table copies, then a Birkhoff-von Neumann
+// decomposition of the padded lanes x classes matrix into permutations = steps).
 //
-// k_sched_dual16: one THREAD per half-warp problem (the colouring is sequential), scratch in
-// shared memory interleaved across the threads of the block.  It writes one code byte per
+// k_sched_dual: one THREAD per problem (the decomposition is sequential), ~1.1 KB of scratch per
+// problem in shared memory, interleaved across the threads of the block.  It writes one code byte per
 // (lane, step) into the head of the slice's own SELL region; k_fill_sell_sched then materialises
 // the slice (warp per slice).
 struct SchedMem {
@@ -226,7 +227,8 @@ __global__ void k_sched_dual(int64_t n, int64_t nslices, int wmax, const int64_t
     const int nt = blockDim.x, tid = threadIdx.x;
     SchedMem M;
     M.b = sraw; M.nt = nt; M.t = tid;
-    M.w = reinterpret_cast<uint32_t *>(sraw + (((size_t)skm_sched_bytes(NL, wmax) * nt + 15) & ~(size_t)15));
+    M.w = nullptr;                                        // the Birkhoff-von Neumann scheduler needs bytes only
+    (void)wmax;
 
     const int64_t prob = (int64_t)blockIdx.x * nt + tid;  // half- / quarter-warp index
     if (prob >= PARTS * nslices) return;
@@ -245,7 +247,7 @@ __global__ void k_sched_dual(int64_t n, int64_t nslices, int wmax, const int64_t
     SchedOut out;
     out.dst = reinterpret_cast<unsigned char *>(sell + base) + (size_t)half * NL * W;
     out.W = W;
-    const int ovf = skm_sched<NL>(M, W, wmax, out);
+    const int ovf = skm_sched_bvn<NL>(M, W, out);
     if (ovf) atomicAdd(overflow_total, (unsigned long long)ovf);
 }
 
@@ -578,11 +580,11 @@ int skm_sell_ensure_layout(skm_dataset *ds, int mode)
         if (wmax <= 0 || wmax > 254) { skm_set_error("dual-table layout needs columns of at most 254 entries"); return SKM_ERR_UNSUPPORTED; }
         const int nl = mode == 1 ? 16 : 8;
         // scheduler: one thread per half-/quarter-warp, as many as the scratch allows (interleaved shared memory)
-        const size_t per = (size_t)skm_sched_bytes(nl, wmax) + 4 * (size_t)skm_sched_words(nl, wmax);
+        const size_t per = (size_t)skm_bvn_bytes(nl);
         int nt = (int)(((size_t)ctx->smem_optin - 1024) / per);
-        if (nt > 64) nt = 64;
-        if (nt < 1) { skm_set_error("dual-table scheduler does not fit in shared memory"); return SKM_ERR_UNSUPPORTED; }
-        const size_t smem = (((size_t)skm_sched_bytes(nl, wmax) * nt + 15) & ~(size_t)15) + 4 * (size_t)skm_sched_words(nl, wmax) * nt;
+        nt = nt >= 256 ? 256 : (nt & ~31);
+        if (nt < 32) { skm_set_error("dual-table scheduler does not fit in shared memory"); return SKM_ERR_UNSUPPORTED; }
+        const size_t smem = per * nt;
         DevBuf ovf;
         SKM_TRY(ovf.alloc(sizeof(unsigned long long)));
         SKM_CUDA(cudaMemsetAsync(ovf.ptr, 0, sizeof(unsigned long long), ctx->stream));

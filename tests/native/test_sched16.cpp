@@ -27,7 +27,12 @@ int main(int argc,char**argv){
     for(int l=0;l<TNL;++l){ for(int r:rows[l]) cnt[l][r&(TNL-1)]++; }
     for(int l=0;l<TNL;++l) for(int g=0;g<TNL;++g) M.b[l*TNL+g]=cnt[l][g];
     Out O; O.W=W; O.c.assign(TNL*W,0x77);
+    #ifdef USE_BVN
+    M.b.assign(skm_bvn_bytes(TNL),0xAB); for(int l=0;l<TNL;++l) for(int g=0;g<TNL;++g) M.b[l*TNL+g]=cnt[l][g];
+    int o = skm_sched_bvn<TNL>(M,W,O); ovf+=o;
+#else
     int o = skm_sched<TNL>(M,W,wmax,O); ovf+=o;
+#endif
     // verify: per lane multiset of groups matches cnt; per step classes distinct
     int got[TNL][TNL]; memset(got,0,sizeof got);
     for(int t=0;t<W;++t){ int cls[TNL]; int used[TNL]={0};

@@ -9,10 +9,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 import pytest
 
 
+@pytest.mark.parametrize("impl", ["bvn", "colouring"])   # the device kernel runs the Birkhoff-von Neumann variant
 @pytest.mark.parametrize("nl", [16, 8])            # half-warp / 8-byte gathers and quarter-warp / 16-byte gathers
-def test_sched16_edge_colouring_on_cpu(tmp_path, nl):
+def test_sched16_edge_colouring_on_cpu(tmp_path, nl, impl):
     exe = tmp_path / "test_sched16"
-    subprocess.check_call(["g++", "-O2", "-std=c++17", f"-DTNL={nl}", "-I", os.path.join(ROOT, "sparsifiedkmeans_b200", "csrc"),
+    subprocess.check_call(["g++", "-O2", "-std=c++17", f"-DTNL={nl}", *(["-DUSE_BVN"] if impl == "bvn" else []),
+                           "-I", os.path.join(ROOT, "sparsifiedkmeans_b200", "csrc"),
                            "-o", str(exe), os.path.join(ROOT, "tests", "native", "test_sched16.cpp")])
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
