@@ -342,6 +342,24 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (K1: fused distance + argmin) ----
     peak, peak_src = _peaks()
+    # live device-to-device copy rate on this box, for orientation only (read + write bytes / time); the
+    # roofline denominator stays MEASURED_PEAKS.json (or the recipe's fallback)
+    copy_gbs = None
+    try:
+        a = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+        b_ = torch.empty_like(a)
+        b_.copy_(a)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            b_.copy_(a)
+        c1.record()
+        torch.cuda.synchronize()
+        copy_gbs = 5 * 2 * a.numel() / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        del a, b_
+    except Exception:
+        pass
     k1_ms, k1_groups = tim["assign"]
     k1_ms_avg = k1_ms / max(k1_groups, 1)
     alg_bytes = n * (m * 8 + 8)                         # m*(4+4) + 4 + 4 per point
@@ -355,6 +373,7 @@ def run_ours(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": L.kernel_name, "ms_per_launch": k1_ms_avg,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "d2d_copy_gbs_this_run": copy_gbs,
                 "step_breakdown_ms": {k: v[0] / args.steps for k, v in tim.items() if v[1]}}
 
     # ---- end to end: host buffers in, host results out, every step ----

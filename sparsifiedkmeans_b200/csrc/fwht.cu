@@ -411,14 +411,27 @@ __global__ void __launch_bounds__(256) k_fwht_sample_warp(int64_t n, int m_keep,
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, off, o); if (lane >= o) off += t; }
         const int total = __shfl_sync(0xffffffffu, off, 31);
         if (total != m_keep) *bad_flag = 1;                 // repeated rows inside a column
-        int64_t out = col * (int64_t)m_keep + (off - cnt);
-        while (b) {
-            const int bit = __ffs(b) - 1;
-            b &= b - 1;
-            const int r = (lane << 5) + bit;
-            rowidx[out] = r;
-            val[out] = __fdiv_rn(__fdiv_rn(s[r], root), level);
-            ++out;
+        // emit: output o is the (o - base_L)-th set bit of word L, where L is the first word whose
+        // inclusive prefix exceeds o (binary search over the prefixes with shuffles).  One output per
+        // lane, so the divisions and the global stores run 32 wide and the stores are coalesced.
+        const int base_l = off - cnt;
+        const int64_t out0 = col * (int64_t)m_keep;
+        for (int ob = 0; ob < m_keep; ob += 32) {
+            const int o = ob + lane;
+            int pos = 0;
+#pragma unroll
+            for (int sft = 16; sft; sft >>= 1) {
+                const int tt = __shfl_sync(0xffffffffu, off, pos + sft - 1);
+                if (tt <= o) pos += sft;
+            }
+            uint32_t bl = __shfl_sync(0xffffffffu, b, pos);
+            const int k = o - __shfl_sync(0xffffffffu, base_l, pos);
+            if (o < m_keep && o < total) {
+                for (int i = 0; i < k; ++i) bl &= bl - 1;
+                const int r = (pos << 5) + __ffs(bl) - 1;
+                rowidx[out0 + o] = r;
+                val[out0 + o] = __fdiv_rn(__fdiv_rn(s[r], root), level);
+            }
         }
         if (lane == 0) { colptr[col] = col * (int64_t)m_keep; if (col == n - 1) colptr[n] = n * (int64_t)m_keep; }
         __syncwarp();
