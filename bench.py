@@ -367,7 +367,7 @@ def run_ours(args):
     traffic = None
     try:   # DRAM bytes per launch from the committed ncu --set full capture (per-point figure x points)
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f)[L.kernel_name.split("<")[0]]["dram_bytes_per_point"] * n
+            traffic = json.load(f)[L.kernel_name]["dram_bytes_per_point"] * n      # keyed by the kernel the plan runs
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
