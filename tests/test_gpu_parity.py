@@ -124,6 +124,28 @@ def test_streamed_image_layouts(ctx, p, m, n, ragged):
     ds.close()
 
 
+@pytest.mark.parametrize("K", [2, 10, 16, 40])
+def test_assign_long_columns_and_tiny_shards(ctx, K):
+    """Columns longer than the dual-table scheduler's byte-sized state (> 254 entries) fall back to the
+    single-table order; shards smaller than one 32-column slice and single-column shards still work."""
+    from sparsifiedkmeans_b200 import Dataset
+    X, c, gamma = make_sparsified(p=1024, n=200, m=300, K=K, seed=K, kind="mixture")
+    ds = Dataset.from_scipy(X, store="f32", ctx=ctx)
+    assert ds.max_col_nnz == 300
+    a, d = ds.assign(c, gamma)
+    wa, wd, _ = host_ref.find_cluster_assignments(X, c, gamma)
+    assert np.array_equal(a, wa)
+    assert ds.layout_check()["layout"] == 0 and ds.layout_check()["bad_columns"] == 0
+    ds.close()
+    for n in (1, 5, 33):
+        X, c, gamma = make_sparsified(p=96, n=n, m=12, K=K, seed=K + n, kind="unstructured")
+        ds = Dataset.from_scipy(X, store="f32", ctx=ctx)
+        a, _ = ds.assign(c, gamma)
+        assert np.array_equal(a, host_ref.find_cluster_assignments(X, c, gamma)[0])
+        assert ds.layout_check()["bad_columns"] == 0
+        ds.close()
+
+
 def test_assign_near_ties_are_resolved_exactly(ctx):
     """Duplicate centres and 1-ulp perturbations: the fp32 kernel must hand these to the fp64 path."""
     from sparsifiedkmeans_b200 import Dataset
