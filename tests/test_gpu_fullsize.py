@@ -113,3 +113,47 @@ def test_fullsize_streamed_equals_resident(big):
     assert np.array_equal(a, wa)
     want, _, _, _ = cport.centroid_update(P, Xs.shape[1], K, Xs.indptr, Xs.indices, Xs.data, wa, gamma, start, True)
     assert np.max(np.abs(newc - want)) <= 1e-6 * np.max(np.abs(want))
+
+
+def test_fullsize_config3_shard_k64(ctx):
+    """BASELINE.json configs[2]'s per-GPU shard (n=1.25e7, p=1024, K=64, 51 entries per point): the K=64
+    plan (four launches of 16 centres on the dual table, merged through best2) against the oracle on
+    slices, the conservation laws of one full iteration, and a conflict-free image."""
+    import torch
+    import bench
+    from oracle import host_ref
+    from sparsifiedkmeans_b200 import Dataset, Lloyd
+    from sparsifiedkmeans_b200._lib import SKM_F32, SKM_I32, SKM_I64
+    n, p, k, m = 12_500_000, 1024, 64, 51
+    dev = torch.device("cuda:0")
+    colptr, rowidx, val, mu, start = bench.gen_shard_device(dev, n, p, m, k, col0=0)
+    torch.cuda.synchronize()
+    slices = {}
+    w = 30_000
+    for name, j0 in (("head", 0), ("middle", n // 2 - 7), ("tail", n - w)):
+        r = rowidx[j0 * m:(j0 + w) * m].cpu().numpy().astype(np.int64)
+        v = val[j0 * m:(j0 + w) * m].cpu().numpy().astype(np.float64)
+        slices[name] = (j0, sp.csc_matrix((v, r, np.arange(w + 1, dtype=np.int64) * m), shape=(p, w)))
+    ds = Dataset.from_device_csc(p, n, colptr.data_ptr(), SKM_I64, rowidx.data_ptr(), SKM_I32, val.data_ptr(), SKM_F32,
+                                 store="f32", ctx=ctx)
+    del colptr, rowidx, val
+    torch.cuda.empty_cache()
+    L = Lloyd(ds, k)
+    try:
+        gamma = m / p
+        L.set_centers(start)
+        st = L.step(gamma, gamma, True)
+        a, d = L.assignments()
+        assert st.n_points == n and a.min() >= 1 and a.max() <= k
+        for name, (j0, Xs) in slices.items():
+            wa, wd, _ = host_ref.find_cluster_assignments(Xs, start, gamma)
+            assert np.array_equal(a[j0:j0 + w], wa), name
+            np.testing.assert_allclose(d[j0:j0 + w], wd, rtol=2e-5)
+        assert np.array_equal(np.bincount(a - 1, minlength=k), L.counts())
+        np.testing.assert_allclose(st.sumsq, float(np.sum(d.astype(np.float64) ** 2)), rtol=1e-6)
+        chk = ds.layout_check()
+        assert chk["bad_columns"] == 0
+        if "dual table" in L.kernel_name:
+            assert chk["layout"] == 2 and chk["wavefronts"] <= 1.0001 * chk["steps"]
+    finally:
+        L.close(); ds.close()
