@@ -195,6 +195,16 @@ int   skm_lloyd_assign_sparse(skm_lloyd *L, int has_gamma, double gamma);
  * support counts N (p x K), member counts (K) and sum of squared distances (1).
  * Asynchronous on the context stream. */
 int   skm_lloyd_accumulate(skm_lloyd *L);
+/* How skm_lloyd_accumulate obtains the sums.  0 (default): recompute from all columns every iteration, as
+ * the reference does (kmeans_sparsified.m:430-453).  1: incremental -- the per-shard sums of the previous
+ * iteration are kept and only the columns whose assignment changed move their entries between clusters
+ * (the sums depend on nothing but the assignments, so the centres are the same up to fp64 rounding; every
+ * 64th iteration, or when more than n/16 columns moved, the sums are recomputed in full).  The sum of squared
+ * distances and the member counts are always exact for the current assignment. */
+int   skm_lloyd_set_update_mode(skm_lloyd *L, int mode);
+/* What the last skm_lloyd_accumulate did: kind 0 = full recompute, 1 = moved n_changed columns,
+ * 2 = no assignment changed (n_changed = 0).  n_changed = -1 after a full recompute. */
+int   skm_lloyd_last_update(skm_lloyd *L, int *kind, int64_t *n_changed);
 /* Device pointer / length (in doubles) of [S | N | counts | sumsq] for the collective. */
 void *skm_lloyd_partials(skm_lloyd *L, int64_t *n_doubles);
 /* K3: C(:,k) = gamma*S(:,k)./(N(:,k)+1e-16) (ml_correction) or S(:,k)/count_k, for

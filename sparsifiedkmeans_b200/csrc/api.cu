@@ -372,6 +372,7 @@ extern "C" void skm_lloyd_destroy(skm_lloyd *L)
     cudaFree(L->cmax); cudaFree(L->assign); cudaFree(L->dist_f32); cudaFree(L->dist_f64);
     cudaFree(L->best2); cudaFree(L->flagged); cudaFree(L->nflag); cudaFree(L->partials);
     cudaFree(L->stats);
+    cudaFree(L->acc_local); cudaFree(L->assign_prev); cudaFree(L->changed); cudaFree(L->nchanged);
     if (L->h_stats) cudaFreeHost(L->h_stats);
     if (L->h_counts) cudaFreeHost(L->h_counts);
     delete L;
@@ -504,14 +505,70 @@ extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
     return SKM_OK;
 }
 
+extern "C" int skm_lloyd_set_update_mode(skm_lloyd *L, int mode)
+{
+    SKM_REQUIRE(L, "NULL argument");
+    SKM_REQUIRE(mode == 0 || mode == 1, "update mode must be 0 (recompute) or 1 (incremental)");
+    SKM_TRY(enter(L->ds->ctx));
+    if (mode == 1 && !L->acc_local) {
+        const int64_t p = L->ds->p, n = L->ds->n, K = L->K;
+        SKM_TRY(dev_alloc((void **)&L->acc_local, sizeof(double) * (2 * p * K + K + 1), "acc_local"));
+        SKM_TRY(dev_alloc((void **)&L->assign_prev, sizeof(int32_t) * n, "assign_prev"));
+        SKM_TRY(dev_alloc((void **)&L->changed, sizeof(int32_t) * n, "changed"));
+        SKM_TRY(dev_alloc((void **)&L->nchanged, sizeof(int) * 4, "nchanged"));
+    }
+    L->update_mode = mode;
+    L->acc_valid = false;
+    return SKM_OK;
+}
+
 extern "C" int skm_lloyd_accumulate(skm_lloyd *L)
 {
     SKM_REQUIRE(L, "NULL argument");
-    SKM_TRY(enter(L->ds->ctx));
+    skm_ctx *ctx = L->ds->ctx;
+    SKM_TRY(enter(ctx));
     if (!L->assigned) { skm_set_error("skm_lloyd_accumulate called before skm_lloyd_assign"); return SKM_ERR_STATE; }
-    SkmTimed t(L->ds->ctx, SKM_T_ACCUM);
-    SKM_TRY(skm_launch_accumulate(L->ds->ctx, L->ds, L->K, L->assign, L->assign_c, L->dist_f32, L->dist_is_f64 ? L->dist_f64 : nullptr, L->partials));
+    SkmTimed t(ctx, SKM_T_ACCUM);
+    const int64_t p = L->ds->p, n = L->ds->n, K = L->K;
+    const double *d64 = L->dist_is_f64 ? L->dist_f64 : nullptr;
+    if (L->update_mode == 0) {
+        SKM_TRY(skm_launch_accumulate(ctx, L->ds, K, L->assign, L->assign_c, L->dist_f32, d64, L->partials));
+        L->last_update_kind = 0; L->last_changed = -1;
+        L->accumulated = true;
+        return SKM_OK;
+    }
+    // incremental: acc_local holds this shard's [S | N | counts] for assign_prev.  The sums only depend on the
+    // assignments, so columns that kept theirs contribute nothing new; a full recompute every 64 incremental
+    // iterations bounds the drift of the +/- updates (each is one fp64 rounding).
+    const int64_t nacc = 2 * p * K + K;
+    bool full = !L->acc_valid || L->incr_run >= 64;
+    int64_t nch = 0;
+    if (!full) {
+        SKM_TRY(skm_launch_diff_assign(ctx, n, K, L->assign, L->assign_prev, L->dist_f32, d64, L->changed, L->nchanged,
+                                       L->acc_local + nacc));
+        SKM_CUDA(cudaMemcpyAsync(ctx->h_flag + 12, L->nchanged, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        SKM_CUDA(cudaStreamSynchronize(ctx->stream));
+        nch = ctx->h_flag[12];
+        if (nch > n / 16) full = true;                      // many movers: the row-major pass is cheaper
+    }
+    if (full) {
+        SKM_TRY(skm_launch_accumulate(ctx, L->ds, K, L->assign, L->assign_c, L->dist_f32, d64, L->acc_local));
+        SKM_CUDA(cudaMemcpyAsync(L->assign_prev, L->assign, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+        L->acc_valid = true; L->incr_run = 0; L->last_update_kind = 0; L->last_changed = -1;
+    } else {
+        SKM_TRY(skm_launch_move_changed(ctx, L->ds, K, L->assign, L->assign_prev, L->changed, L->nchanged, nch, L->acc_local));
+        L->incr_run += 1; L->last_update_kind = nch ? 1 : 2; L->last_changed = nch;
+    }
+    SKM_CUDA(cudaMemcpyAsync(L->partials, L->acc_local, sizeof(double) * (nacc + 1), cudaMemcpyDeviceToDevice, ctx->stream));
     L->accumulated = true;
+    return SKM_OK;
+}
+
+extern "C" int skm_lloyd_last_update(skm_lloyd *L, int *kind, int64_t *n_changed)
+{
+    SKM_REQUIRE(L, "NULL argument");
+    if (kind) *kind = L->last_update_kind;
+    if (n_changed) *n_changed = L->last_changed;
     return SKM_OK;
 }
 

@@ -161,6 +161,16 @@ struct skm_lloyd {
     double  *stats;          // device [8]: dff^2, has_nan, n_empty, ...
     double  *h_stats;        // pinned
     int64_t *h_counts;       // pinned [K]
+    // incremental K2 (opt-in, skm_lloyd_set_update_mode): sums of the previous iteration kept per shard
+    int      update_mode;    // 0 = recompute every iteration (default), 1 = incremental
+    double  *acc_local;      // [2*p*K + K + 1] this shard's [S | N | counts | -] (partials is what the all-reduce sums)
+    int32_t *assign_prev;    // [n] assignments acc_local corresponds to
+    int32_t *changed;        // [n] columns whose assignment changed
+    int     *nchanged;       // device counter
+    bool     acc_valid;
+    int      incr_run;       // incremental iterations since the last full recompute
+    int      last_update_kind; // 0 full, 1 incremental, 2 nothing changed
+    int64_t  last_changed;
     bool     assigned, accumulated;
     bool     dist_is_f64;    // which of dist_f64 / dist_f32 the last assignment wrote
     int64_t  last_rechecked;
@@ -243,6 +253,10 @@ int skm_launch_accumulate(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const 
                           bool zero_first = true);
 int skm_launch_finalize(skm_ctx *ctx, int64_t p, int64_t K, const double *partials, double gamma,
                         int ml_correction, double *centers, double *centers_old, double *stats);
+int skm_launch_diff_assign(skm_ctx *ctx, int64_t n, int64_t K, const int32_t *assign, const int32_t *prev,
+                           const float *dist32, const double *dist64, int32_t *changed, int *nchanged, double *sumsq);
+int skm_launch_move_changed(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const int32_t *assign, int32_t *prev,
+                            const int32_t *changed, const int *nchanged, int64_t nchanged_host, double *acc);
 int skm_launch_argmax(skm_ctx *ctx, int64_t n, const float *dist32, const double *dist64,
                       double *out_val, int64_t *out_idx);
 

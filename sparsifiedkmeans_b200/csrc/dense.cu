@@ -413,13 +413,9 @@ extern "C" int skm_second_pass(skm_ctx *ctx, int64_t p, int64_t n, const void *x
     if (!x_on_device) { SKM_TRY(raw[0].alloc(xs * p * chunk_cols)); SKM_TRY(raw[1].alloc(xs * p * chunk_cols)); }
     if (need_cast) SKM_TRY(x32.alloc(sizeof(float) * p * chunk_cols));
 
+    const int64_t nchunks = n > 0 ? (n + chunk_cols - 1) / chunk_cols : 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t up[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
-    if (!x_on_device) {
-        SKM_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) { cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&freed[i], cudaEventDisableTiming); }
-    }
-    const int64_t nchunks = n > 0 ? (n + chunk_cols - 1) / chunk_cols : 0;
     auto issue = [&](int64_t c) {
         const int64_t j0 = c * chunk_cols, nc = std::min(chunk_cols, n - j0);
         if (c >= 2) cudaStreamWaitEvent(copy_stream, freed[c & 1], 0);
@@ -431,6 +427,11 @@ extern "C" int skm_second_pass(skm_ctx *ctx, int64_t p, int64_t n, const void *x
     std::vector<int> h_nflag;
     DevBuf nflag_log;
     if (want_assign && nchunks > 0) { SKM_TRY(nflag_log.alloc(sizeof(int) * nchunks)); h_nflag.resize(nchunks); }
+    // every allocation is done: from here on nothing returns before the stream and events are released
+    if (!x_on_device) {
+        SKM_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) { cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&freed[i], cudaEventDisableTiming); }
+    }
     if (!x_on_device && nchunks > 0) issue(0);
     for (int64_t c = 0; c < nchunks && rc == SKM_OK; ++c) {
         if (!x_on_device && c + 1 < nchunks) issue(c + 1);

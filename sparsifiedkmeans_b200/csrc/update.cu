@@ -210,6 +210,68 @@ __global__ void k_accumulate_csr(int64_t p, int k0, int kb, int64_t nunits,
     }
 }
 
+// ---- incremental K2 (opt-in): only the columns whose assignment changed move their entries ----
+// k_diff_assign: list of changed columns, member-count deltas, and the sum of squared distances
+// (that one changes for every column, so it is recomputed in full here).
+__global__ void k_diff_assign(int64_t n, int64_t K, const int32_t *__restrict__ assign, const int32_t *__restrict__ prev,
+                              const float *__restrict__ dist32, const double *__restrict__ dist64,
+                              int32_t *__restrict__ changed, int *__restrict__ nchanged, double *__restrict__ sumsq)
+{
+    double local = 0.0;
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; j < n; j += stride) {
+        const int a = assign[j];
+        if (a != prev[j]) changed[atomicAdd(nchanged, 1)] = (int32_t)j;
+        if (a >= 0 && a < K) {
+            const double d = dist64 ? dist64[j] : (double)dist32[j];
+            local += d * d;
+        }
+    }
+    __shared__ double red[32];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+        if (s != 0.0 || s != s) atomicAdd(sumsq, s);
+    }
+}
+
+// one warp per changed column: its entries leave the old cluster's sums and join the new one's
+template <typename VT>
+__global__ void k_move_changed(int64_t p, int64_t K, const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
+                               const VT *__restrict__ val, const int32_t *__restrict__ assign, int32_t *__restrict__ prev,
+                               const int32_t *__restrict__ changed, const int *__restrict__ nchanged,
+                               double *__restrict__ acc /* [S | N | counts] */)
+{
+    double *S = acc, *N = acc + p * K, *counts = acc + 2 * p * K;
+    const int lane = threadIdx.x & 31;
+    int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t total = *nchanged;
+    for (; w < total; w += nwarps) {
+        const int64_t j = changed[w];
+        const int64_t ko = prev[j], kn = assign[j];
+        const bool has_o = ko >= 0 && ko < K, has_n = kn >= 0 && kn < K;
+        const int64_t t0 = colptr[j], t1 = colptr[j + 1];
+        for (int64_t t = t0 + lane; t < t1; t += 32) {
+            const int64_t r = rowidx[t];
+            const double x = (double)val[t];
+            if (has_o) { atomicAdd(&S[ko * p + r], -x); atomicAdd(&N[ko * p + r], -1.0); }
+            if (has_n) { atomicAdd(&S[kn * p + r], x); atomicAdd(&N[kn * p + r], 1.0); }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            if (has_o) atomicAdd(&counts[ko], -1.0);
+            if (has_n) atomicAdd(&counts[kn], 1.0);
+            prev[j] = (int32_t)kn;
+        }
+    }
+}
+
 // stats[0] += sum (old-new)^2 ; stats[1] = 1 if any NaN in new centres
 __global__ void k_finalize(int64_t p, int64_t K, const double *__restrict__ partials, double gamma,
                            int ml, double *__restrict__ centers, double *__restrict__ centers_old,
@@ -446,5 +508,38 @@ int skm_launch_argmax(skm_ctx *ctx, int64_t n, const float *dist32, const double
     k_argmax_final<<<1, 32, 0, ctx->stream>>>(nb, bv.as<double>(), bi.as<int64_t>(), out_val, out_idx);
     SKM_CHECK_LAUNCH(ctx);
     SKM_CUDA(cudaStreamSynchronize(ctx->stream));   // temporaries are freed on return
+    return SKM_OK;
+}
+
+// Incremental K2, step 1: changed[] / *nchanged and the fresh sum of squared distances (into *sumsq, zeroed here).
+int skm_launch_diff_assign(skm_ctx *ctx, int64_t n, int64_t K, const int32_t *assign, const int32_t *prev,
+                           const float *dist32, const double *dist64, int32_t *changed, int *nchanged, double *sumsq)
+{
+    SKM_CUDA(cudaMemsetAsync(nchanged, 0, sizeof(int), ctx->stream));
+    SKM_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(double), ctx->stream));
+    if (n == 0) return SKM_OK;
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    k_diff_assign<<<(unsigned)blocks, 256, 0, ctx->stream>>>(n, K, assign, prev, dist32, dist64, changed, nchanged, sumsq);
+    SKM_CHECK_LAUNCH(ctx);
+    return SKM_OK;
+}
+
+// Incremental K2, step 2: move the entries of the changed columns between clusters in acc = [S | N | counts].
+int skm_launch_move_changed(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const int32_t *assign, int32_t *prev,
+                            const int32_t *changed, const int *nchanged, int64_t nchanged_host, double *acc)
+{
+    if (nchanged_host <= 0) return SKM_OK;
+    int64_t blocks = (nchanged_host * 32 + 255) / 256;
+    const int64_t cap = (int64_t)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    if (ds->store_dtype == SKM_F32)
+        k_move_changed<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>(ds->p, K, ds->colptr, ds->rowidx, (const float *)ds->val,
+                                                                        assign, prev, changed, nchanged, acc);
+    else
+        k_move_changed<double><<<(unsigned)blocks, 256, 0, ctx->stream>>>(ds->p, K, ds->colptr, ds->rowidx, (const double *)ds->val,
+                                                                         assign, prev, changed, nchanged, acc);
+    SKM_CHECK_LAUNCH(ctx);
     return SKM_OK;
 }

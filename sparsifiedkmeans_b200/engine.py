@@ -308,7 +308,7 @@ class Dataset:
 class Lloyd:
     """Iteration state for K centres on one resident shard (skm_lloyd)."""
 
-    def __init__(self, ds: Dataset, K: int):
+    def __init__(self, ds: Dataset, K: int, incremental: bool = False):
         self.ds = ds
         self.K = int(K)
         self._lib = ds._lib
@@ -316,6 +316,18 @@ class Lloyd:
         check(self._lib.skm_lloyd_create(ds.handle, self.K, C.byref(h)))
         self._h = h
         ds._children.add(self)
+        if incremental:
+            self.set_update_mode(True)
+
+    def set_update_mode(self, incremental: bool):
+        """False: per-cluster sums recomputed from all columns every iteration (the reference's way);
+        True: only columns whose assignment changed move their entries (skm_lloyd_set_update_mode)."""
+        check(self._lib.skm_lloyd_set_update_mode(self.handle, 1 if incremental else 0))
+
+    def last_update(self) -> tuple[str, int]:
+        kind, nch = C.c_int(0), C.c_int64(0)
+        check(self._lib.skm_lloyd_last_update(self.handle, C.byref(kind), C.byref(nch)))
+        return ("full", "incremental", "unchanged")[kind.value], int(nch.value)
 
     @property
     def handle(self):

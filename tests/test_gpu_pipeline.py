@@ -277,3 +277,40 @@ def test_sharded_kmeanspp_on_one_gpu_matches_reference(ctx):
     idx, C = sharded_arthur_initialization(eng, 6, gamma, X.shape[1], 0, first=3, uniforms=iter(u))
     assert np.array_equal(idx, want) and np.array_equal(C, np.asarray(cen.todense()))
     eng.close(); ds.close()
+
+
+@pytest.mark.parametrize("store", ["f32", "f64"])
+def test_incremental_update_equals_full_recompute(ctx, store):
+    """skm_lloyd_set_update_mode(1): only the columns that changed cluster move their entries.  Over a run
+    with many, few and no movers the assignments stay identical to the recompute-everything run and the
+    centres agree to fp64 rounding; statistics (objective, counts) are exact for the current assignment."""
+    from sparsifiedkmeans_b200 import Dataset, Lloyd
+    from tests.util import make_sparsified
+    X, c, gamma = make_sparsified(p=64, n=30000, m=8, K=8, seed=21, kind="unstructured")
+    ds = Dataset.from_scipy(X, store=store, ctx=ctx)
+    A, B = Lloyd(ds, 8), Lloyd(ds, 8, incremental=True)
+    A.set_centers(c); B.set_centers(c)
+    kinds = []
+    for it in range(40):
+        sa = A.step(gamma, gamma, True)
+        sb = B.step(gamma, gamma, True)
+        kind, nch = B.last_update()
+        kinds.append(kind)
+        aa, _ = A.assignments()
+        ab, _ = B.assignments()
+        assert np.array_equal(aa, ab), it
+        assert np.array_equal(A.counts(), B.counts())
+        np.testing.assert_allclose(B.get_centers(), A.get_centers(), rtol=1e-11, atol=1e-13)
+        np.testing.assert_allclose(sb.sumsq, sa.sumsq, rtol=1e-12)
+        np.testing.assert_allclose(sb.dff, sa.dff, rtol=1e-6, atol=1e-12)
+        if kind == "incremental":
+            assert 0 < nch <= ds.n // 16
+        if sa.dff == 0.0:
+            break
+    assert kinds[0] == "full" and "incremental" in kinds
+    # a fixed point: nothing moves, nothing is recomputed
+    B.step(gamma, gamma, True)
+    B.step(gamma, gamma, True)
+    if sa.dff == 0.0:
+        assert B.last_update() == ("unchanged", 0)
+    A.close(); B.close(); ds.close()
