@@ -180,6 +180,15 @@ def sharded_arthur_initialization(engine, K: int, gamma, n_total: int, lo: int, 
         dist.all_gather_object(bounds, (int(lo), int(lo + engine.n_local)), group=group)
     else:
         bounds[0] = (int(lo), int(lo + engine.n_local))
+    p = engine.p
+    if on:
+        import torch
+        # two small tensor collectives per round (NCCL on the GPU, gloo on the CPU): the local D^2 sums
+        # (all-gather of one double) and [global index | column] from the rank that owns the pick
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        g_in = torch.zeros(1, dtype=torch.float64, device=dev)
+        g_out = torch.zeros(world, dtype=torch.float64, device=dev)
+        box = torch.zeros(1 + p, dtype=torch.float64, device=dev)
 
     def owner_of(g):
         for r, (a, b) in enumerate(bounds):
@@ -187,25 +196,31 @@ def sharded_arthur_initialization(engine, K: int, gamma, n_total: int, lo: int, 
                 return r
         raise ValueError(f"global column {g} is owned by no rank")
 
-    def fetch(g):
-        r = owner_of(g)
-        col = engine.get_column(g - bounds[r][0]) if r == me else None
-        if on:
-            box = [col]
-            dist.broadcast_object_list(box, src=r, group=group)
-            col = box[0]
-        return col
+    def publish(src, g_local):
+        """rank `src` owns local column g_local: every rank gets (global index, dense column)"""
+        if not on:
+            return bounds[0][0] + int(g_local), engine.get_column(int(g_local))
+        if src == me:
+            col = np.asarray(engine.get_column(int(g_local)), dtype=np.float64)
+            box[0] = float(bounds[me][0] + int(g_local))
+            box[1:] = torch.from_numpy(col).to(dev)
+        dist.broadcast(box, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
+        h = box.cpu().numpy()
+        return int(h[0]), h[1:].copy()
 
     it = iter(uniforms)
-    chosen = [int(first)]
-    cols = [fetch(chosen[0])]
+    r0 = owner_of(int(first))
+    g0, c0 = publish(r0, int(first) - bounds[r0][0])
+    chosen = [g0]
+    cols = [c0]
     for _ in range(K - 1):
         local = engine.kpp_update(cols[-1], gamma, first=(len(chosen) == 1)) if engine.n_local else 0.0
-        sums = [None] * world
         if on:
-            dist.all_gather_object(sums, float(local), group=group)
+            g_in[0] = float(local)
+            dist.all_gather_into_tensor(g_out, g_in, group=group)
+            sums = [float(v) for v in g_out.cpu().numpy()]
         else:
-            sums[0] = float(local)
+            sums = [float(local)]
         total = 0.0
         prefix = []
         for v in sums:                       # same summation order on every rank
@@ -215,27 +230,25 @@ def sharded_arthur_initialization(engine, K: int, gamma, n_total: int, lo: int, 
         def pick():
             u = float(next(it))
             if not (total > 0):              # all distances zero: uniform (Arthur_initialization.m:44-48)
-                return min(int(u * n_total), n_total - 1)
+                g = min(int(u * n_total), n_total - 1)
+                q = owner_of(g)
+                return publish(q, g - bounds[q][0])
             target = u * total
             q = world - 1
             for r in range(world):
                 if target < prefix[r] + sums[r] and sums[r] > 0:
                     q = r
                     break
-            j = engine.kpp_pick(target - prefix[q]) if q == me else None
-            if on:
-                box = [j]
-                dist.broadcast_object_list(box, src=q, group=group)
-                j = box[0]
-            return bounds[q][0] + int(j)
+            j = engine.kpp_pick(target - prefix[q]) if q == me else 0
+            return publish(q, j)
 
-        g = pick()
+        g, col = pick()
         counter = 1
         while g in chosen and counter < 400:  # :54-61
-            g = pick()
+            g, col = pick()
             counter += 1
         if g in chosen:
             raise RuntimeError("Cannot sample with replacement with this distribution")
         chosen.append(g)
-        cols.append(fetch(g))
+        cols.append(col)
     return np.asarray(chosen, dtype=np.int64), np.stack(cols, axis=1)
