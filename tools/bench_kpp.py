@@ -46,6 +46,7 @@ def main():
     lo, hi = shard_bounds(args.n, world, rank)
     ctx = Context(local)
     colptr, rowidx, val, mu, start = bench.gen_shard_device(dev, hi - lo, p, m, 10, col0=lo)
+    torch.cuda.synchronize()                       # the library reads these on its own stream
     ds = Dataset.from_device_csc(p, hi - lo, colptr.data_ptr(), SKM_I64, rowidx.data_ptr(), SKM_I32, val.data_ptr(), SKM_F32,
                                  store="f32", ctx=ctx)
     del colptr, rowidx, val
