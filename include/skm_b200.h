@@ -195,6 +195,17 @@ int   skm_lloyd_assign_sparse(skm_lloyd *L, int has_gamma, double gamma);
  * support counts N (p x K), member counts (K) and sum of squared distances (1).
  * Asynchronous on the context stream. */
 int   skm_lloyd_accumulate(skm_lloyd *L);
+/* How skm_lloyd_assign finds the nearest centre.  0 (default): every centre is evaluated for every column in
+ * every call.  1: bounded (SKM_F32 datasets) -- a lower bound on the distance to every centre but the
+ * assigned one is carried from call to call and lowered by the movement of the centres (the masked distance
+ * is a seminorm of the centre, so it changes by at most ||c_new - c_old||); a column whose distance to its
+ * own centre stays below that bound, with the fast kernel's rounding guard and a 1e-6 relative margin, keeps
+ * its assignment after ONE centre evaluation; the others are re-evaluated against every centre (fp64,
+ * reference order).  Assignments and distances are the same as in mode 0.  The bounds are dropped whenever
+ * the mode is set. */
+int   skm_lloyd_set_assign_mode(skm_lloyd *L, int mode);
+/* Columns the last bounded skm_lloyd_assign had to re-evaluate (-1: that call evaluated every column). */
+int   skm_lloyd_last_assign(skm_lloyd *L, int64_t *n_flagged);
 /* How skm_lloyd_accumulate obtains the sums.  0 (default): recompute from all columns every iteration, as
  * the reference does (kmeans_sparsified.m:430-453).  1: incremental -- the per-shard sums of the previous
  * iteration are kept and only the columns whose assignment changed move their entries between clusters

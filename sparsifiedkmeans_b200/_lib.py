@@ -79,6 +79,8 @@ SIGNATURES = {
     "skm_lloyd_assign": (_int, [_vp, _int, _dbl]),
     "skm_lloyd_assign_sparse": (_int, [_vp, _int, _dbl]),
     "skm_lloyd_accumulate": (_int, [_vp]),
+    "skm_lloyd_set_assign_mode": (_int, [_vp, _int]),
+    "skm_lloyd_last_assign": (_int, [_vp, C.POINTER(_i64)]),
     "skm_lloyd_set_update_mode": (_int, [_vp, _int]),
     "skm_lloyd_last_update": (_int, [_vp, C.POINTER(_int), C.POINTER(_i64)]),
     "skm_lloyd_partials": (_vp, [_vp, C.POINTER(_i64)]),

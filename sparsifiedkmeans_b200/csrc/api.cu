@@ -373,6 +373,7 @@ extern "C" void skm_lloyd_destroy(skm_lloyd *L)
     cudaFree(L->best2); cudaFree(L->flagged); cudaFree(L->nflag); cudaFree(L->partials);
     cudaFree(L->stats);
     cudaFree(L->acc_local); cudaFree(L->assign_prev); cudaFree(L->changed); cudaFree(L->nchanged);
+    cudaFree(L->lb); cudaFree(L->centers_prev); cudaFree(L->table_t); cudaFree(L->shift);
     if (L->h_stats) cudaFreeHost(L->h_stats);
     if (L->h_counts) cudaFreeHost(L->h_counts);
     delete L;
@@ -467,6 +468,34 @@ extern "C" int skm_lloyd_set_center_column(skm_lloyd *L, int64_t k, const double
     return SKM_OK;
 }
 
+extern "C" int skm_lloyd_set_assign_mode(skm_lloyd *L, int mode)
+{
+    SKM_REQUIRE(L, "NULL argument");
+    SKM_REQUIRE(mode == 0 || mode == 1, "assign mode must be 0 (evaluate every centre) or 1 (bounded)");
+    SKM_TRY(enter(L->ds->ctx));
+    if (mode == 1 && L->ds->store_dtype != SKM_F32) {
+        skm_set_error("the bounded assignment needs an SKM_F32 dataset");
+        return SKM_ERR_UNSUPPORTED;
+    }
+    if (mode == 1 && !L->lb) {
+        const int64_t p = L->ds->p, n = L->ds->n, K = L->K;
+        SKM_TRY(dev_alloc((void **)&L->lb, sizeof(float) * n, "lb"));
+        SKM_TRY(dev_alloc((void **)&L->centers_prev, sizeof(double) * p * K, "centers_prev"));
+        SKM_TRY(dev_alloc((void **)&L->table_t, sizeof(float) * K * (p + 1), "table_t"));
+        SKM_TRY(dev_alloc((void **)&L->shift, sizeof(float) * (K + 4), "shift"));
+    }
+    L->assign_mode = mode;
+    L->lb_valid = false;
+    return SKM_OK;
+}
+
+extern "C" int skm_lloyd_last_assign(skm_lloyd *L, int64_t *n_flagged)
+{
+    SKM_REQUIRE(L, "NULL argument");
+    if (n_flagged) *n_flagged = L->last_bounded_flagged;
+    return SKM_OK;
+}
+
 extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
 {
     SKM_REQUIRE(L, "NULL argument");
@@ -480,20 +509,58 @@ extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
     {
         SkmTimed t(ctx, SKM_T_PREP);
         SKM_TRY(skm_launch_prep_centers(ctx, ds->p, L->K, L->centers, has_gamma, gamma, L->cscaled_t, nullptr, nullptr));
-        if (fast) SKM_TRY(skm_launch_build_table(ctx, ds->p, L->K, L->cscaled_t, pl, L->table, L->cmax));
     }
     ExactArgs ea = exact_args(ds, L->K, L->cscaled_t);
     L->last_rechecked = -1;
+    L->last_bounded_flagged = -1;
+    const bool want_bounds = fast && L->assign_mode == 1;
+    float *lb = want_bounds ? L->lb : nullptr;
+    if (want_bounds) {
+        // bounded pass: valid when the bounds exist and refer to the same scaling of the centres
+        const double gnow = has_gamma ? gamma : nan("");
+        const bool same_scale = (gnow == L->gamma_prev) || (gnow != gnow && L->gamma_prev != L->gamma_prev);
+        const bool usable = L->lb_valid && same_scale && L->assigned;
+        {
+            SkmTimed t(ctx, SKM_T_PREP);
+            SKM_TRY(skm_launch_center_shift(ctx, ds->p, L->K, L->centers, L->centers_prev, has_gamma, gamma, L->shift));
+        }
+        L->gamma_prev = gnow;
+        if (usable) {
+            int64_t nfl = 0;
+            {
+                SkmTimed t(ctx, SKM_T_ASSIGN);
+                SKM_TRY(skm_launch_build_table_t(ctx, ds->p, L->K, L->cscaled_t, L->table_t, L->cmax));
+                SKM_TRY(skm_launch_assign_bounded(ctx, ds, L->K, L->table_t, L->cmax, L->shift, L->assign, L->lb, L->dist_f32,
+                                                  L->flagged, L->nflag));
+                SKM_CUDA(cudaMemcpyAsync(ctx->h_flag + 13, L->nflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                SKM_CUDA(cudaStreamSynchronize(ctx->stream));
+                nfl = ctx->h_flag[13];
+            }
+            L->last_bounded_flagged = nfl;
+            if (nfl <= ds->n / 8) {
+                // few columns left their bound: every centre, fp64, the reference's order; refreshes their lb
+                SkmTimed t(ctx, SKM_T_RECHECK);
+                SKM_TRY(skm_launch_exact_assign(ctx, ea, L->assign, nullptr, L->dist_f32, L->flagged, L->nflag, ds->n, L->lb));
+                L->dist_is_f64 = false;
+                L->assigned = true;
+                L->accumulated = false;
+                return SKM_OK;
+            }
+            // many movers: the full pass below re-evaluates everything and rewrites every bound
+        }
+    }
     if (fast) {
         {
             SkmTimed t(ctx, SKM_T_ASSIGN);
+            SKM_TRY(skm_launch_build_table(ctx, ds->p, L->K, L->cscaled_t, pl, L->table, L->cmax));
             SKM_TRY(skm_launch_assign_fast(ctx, ds, L->K, pl, L->table, L->cmax, L->assign, L->dist_f32, L->best2,
-                                           L->flagged, L->nflag));
+                                           L->flagged, L->nflag, nullptr, lb));
         }
         // columns the guard could not certify: fp64, reference order
         SkmTimed t(ctx, SKM_T_RECHECK);
-        SKM_TRY(skm_launch_exact_assign(ctx, ea, L->assign, nullptr, L->dist_f32, L->flagged, L->nflag, ds->n));
+        SKM_TRY(skm_launch_exact_assign(ctx, ea, L->assign, nullptr, L->dist_f32, L->flagged, L->nflag, ds->n, lb));
         L->dist_is_f64 = false;
+        if (want_bounds) L->lb_valid = true;
     } else {
         SkmTimed t(ctx, SKM_T_ASSIGN);
         SKM_TRY(skm_launch_exact_assign(ctx, ea, L->assign, L->dist_f64, L->dist_f32, nullptr, nullptr, 0));
@@ -719,6 +786,7 @@ extern "C" int skm_lloyd_assign_sparse(skm_lloyd *L, int has_gamma, double gamma
     skm_dataset *ds = L->ds;
     skm_ctx *ctx = ds->ctx;
     SKM_TRY(enter(ctx));
+    L->lb_valid = false;                                   // the bounds refer to dense-centre distances
     const int64_t p = ds->p, K = L->K;
     DevBuf mask, xdiv;
     SKM_TRY(mask.alloc((size_t)(p + 1) * K));

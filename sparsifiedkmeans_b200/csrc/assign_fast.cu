@@ -41,6 +41,7 @@ struct FastParams {
     float2        *best2;
     int32_t       *flagged;
     int           *nflag;
+    float         *lb;           // optional: lower bound on the distance to every centre but the winner (bounded.cu)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -134,6 +135,17 @@ __device__ __forceinline__ void finish_column(const FastParams &P, const float (
     }
     P.assign[j] = i1;
     P.dist[j] = sqrtf(b1);
+    if (P.lb) {
+        // sqrt(second-best sum minus its error bound), rounded down; uncertified columns get theirs from
+        // the fp64 re-evaluation (NaN / single centre: 0 resp. +inf keep the bounded test conservative)
+        float lbv = 0.f;
+        if (P.ktotal == 1) lbv = INF;
+        else if (b2 == b2) {
+            const float e2 = ga * b2 + gb * sqrtf(b2) + ge;
+            lbv = sqrtf(fmaxf(b2 - e2, 0.f)) * (1.f - 4.76837158203125e-07f);
+        }
+        P.lb[j] = lbv;
+    }
     if (!certified) {
         const int slot = atomicAdd(P.nflag, 1);
         P.flagged[slot] = (int32_t)j;
@@ -489,7 +501,7 @@ int skm_launch_build_table(skm_ctx *ctx, int64_t p, int64_t K, const double *ct,
 
 int skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const FastPlan &pl,
                            const float *table, const float *cmax, int32_t *assign, float *dist,
-                           float *best2, int32_t *flagged, int *nflag, const int *m_dev)
+                           float *best2, int32_t *flagged, int *nflag, const int *m_dev, float *lb)
 {
     SKM_CUDA(cudaMemsetAsync(nflag, 0, sizeof(int), ctx->stream));
     if (ds->n == 0) return SKM_OK;
@@ -515,6 +527,7 @@ int skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const
     P.best2 = reinterpret_cast<float2 *>(best2);
     P.flagged = flagged;
     P.nflag = nflag;
+    P.lb = lb;
     for (int c = 0; c < pl.nchunks; ++c) {
         P.table = table + (size_t)c * pl.rows * pl.ks;
         P.k0 = c * pl.kc;
@@ -522,15 +535,11 @@ int skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const
         P.first = (c == 0);
         P.last = (c == pl.nchunks - 1);
         int rc;
-        if (pl.dual8 && ds->sell_mode != 2 && !ds->sell_plain) {
-            skm_set_error("assign_fast: the SELL image is not in the dual-table (mode 2) layout");
+        if (!ds->sell_plain && ds->sell_mode != pl.layout) {
+            skm_set_error("assign_fast: the SELL image is in layout %d, the plan reads layout %d", ds->sell_mode, pl.layout);
             return SKM_ERR_STATE;
         }
         if (pl.mode64) {
-            if (ds->sell_mode != 1 && !ds->sell_plain) {
-                skm_set_error("assign_fast64: the SELL image is not in the dual-table layout");
-                return SKM_ERR_STATE;
-            }
             const bool wide = getenv("SKM_FAST64_WIDE") != nullptr;      // tuning knob: one 1024-thread CTA per SM
             switch (pl.kc) {
                 case 2:  rc = launch_fast64<2, 512, 2>(ctx, P, pl.smem); break;

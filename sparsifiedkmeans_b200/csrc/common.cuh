@@ -171,6 +171,15 @@ struct skm_lloyd {
     int      incr_run;       // incremental iterations since the last full recompute
     int      last_update_kind; // 0 full, 1 incremental, 2 nothing changed
     int64_t  last_changed;
+    // bounded assignment (opt-in, skm_lloyd_set_assign_mode): Hamerly-style bounds carried across iterations
+    int      assign_mode;    // 0 = evaluate every centre for every column (default), 1 = bounded
+    float   *lb;             // [n] lower bound on the distance to every centre but the assigned one
+    bool     lb_valid;
+    double  *centers_prev;   // [p*K] the centres (unscaled) the bounds refer to
+    double   gamma_prev;     // and the scaling they were divided by (NaN: none)
+    float   *table_t;        // [K][p+1] fp32 centres, one row per centre (bounded kernel)
+    float   *shift;          // [K + 4] per-centre movement; then max, second max, argmax
+    int64_t  last_bounded_flagged;   // columns the bounds could not keep (-1: the pass evaluated everything)
     bool     assigned, accumulated;
     bool     dist_is_f64;    // which of dist_f64 / dist_f32 the last assignment wrote
     int64_t  last_rechecked;
@@ -215,7 +224,7 @@ int skm_launch_exact_dist(skm_ctx *ctx, const ExactArgs &a, int64_t j0, int64_t 
 int skm_launch_exact_dist_beta(skm_ctx *ctx, const ExactArgs &a, double beta, double *dist);
 int skm_launch_exact_assign(skm_ctx *ctx, const ExactArgs &a, int32_t *assign, double *dist64,
                             float *dist32, const int32_t *subset, const int *subset_count_dev,
-                            int64_t subset_max);
+                            int64_t subset_max, float *lb = nullptr);
 int skm_launch_inner_product(skm_ctx *ctx, int64_t n, const int64_t *colptr, const int32_t *rowidx,
                              const double *val, const double *c, double *inner, double *normsq);
 int skm_launch_prep_centers(skm_ctx *ctx, int64_t p, int64_t K, const double *centers,
@@ -245,7 +254,16 @@ int  skm_launch_build_table(skm_ctx *ctx, int64_t p, int64_t K, const double *ct
                             float *table, float *cmax);
 int  skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const FastPlan &pl,
                             const float *table, const float *cmax, int32_t *assign, float *dist,
-                            float *best2, int32_t *flagged, int *nflag, const int *m_dev = nullptr);
+                            float *best2, int32_t *flagged, int *nflag, const int *m_dev = nullptr,
+                            float *lb = nullptr);
+
+// bounded.cu
+int skm_launch_center_shift(skm_ctx *ctx, int64_t p, int64_t K, const double *centers, double *centers_prev,
+                            int has_gamma, double gamma, float *shift /* [K+4] */);
+int skm_launch_build_table_t(skm_ctx *ctx, int64_t p, int64_t K, const double *ct, float *table_t, float *cmax);
+int skm_launch_assign_bounded(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const float *table_t, const float *cmax,
+                              const float *shift, const int32_t *assign, float *lb, float *dist,
+                              int32_t *flagged, int *nflag);
 
 // update.cu
 int skm_launch_accumulate(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const int32_t *assign,

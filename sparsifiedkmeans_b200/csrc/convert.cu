@@ -552,9 +552,8 @@ int skm_build_sell(skm_dataset *ds)
     int wmax = 0;
     for (int64_t s2 = 0; s2 < nslices; ++s2) wmax = hw[s2] * 2 > wmax ? hw[s2] * 2 : wmax;
     ds->sell_wmax = wmax;
-    ds->sell_mode = -1;
+    ds->sell_mode = -1;                 // filled lazily, in the entry order of the first kernel family that reads it
     ds->sell_plain = false;
-    SKM_TRY(skm_sell_ensure_layout(ds, 0));
     SKM_CUDA(cudaStreamSynchronize(ctx->stream));   // hp goes out of scope
     return SKM_OK;
 }
@@ -639,6 +638,7 @@ int skm_sell_check(skm_dataset *ds, int64_t out[3])
     skm_ctx *ctx = ds->ctx;
     out[0] = out[1] = out[2] = 0;
     if (!ds->sell || ds->nslices == 0 || ds->store_dtype != SKM_F32) return SKM_OK;
+    if (ds->sell_mode < 0) SKM_TRY(skm_sell_ensure_layout(ds, 0));
     DevBuf r;
     SKM_TRY(r.alloc(3 * sizeof(unsigned long long)));
     SKM_CUDA(cudaMemsetAsync(r.ptr, 0, 3 * sizeof(unsigned long long), ctx->stream));

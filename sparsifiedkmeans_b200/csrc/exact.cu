@@ -65,36 +65,51 @@ __global__ void k_exact_dist_beta(ExactArgs a, double b, double *__restrict__ di
     dist[j] = __dsqrt_rn(s);
 }
 
-// one warp per column (or per entry of `subset`): lanes stride over the centres
+// one warp per column (or per entry of `subset`): lanes stride over the centres.
+// lb (optional): a lower bound on the distance to every centre but the winner (the second-smallest
+// distance, rounded down) -- the state of the bounded assignment (bounded.cu).
 template <typename VT>
 __global__ void k_exact_assign(ExactArgs a, int32_t *__restrict__ assign, double *__restrict__ dist64,
                                float *__restrict__ dist32, const int32_t *__restrict__ subset,
-                               const int *__restrict__ subset_count, int64_t total)
+                               const int *__restrict__ subset_count, int64_t total, float *__restrict__ lb)
 {
     const int lane = threadIdx.x & 31;
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     if (subset_count) total = min(total, (int64_t)*subset_count);
+    const double DINF = __longlong_as_double(0x7ff0000000000000LL);
     for (; warp < total; warp += nwarps) {
         const int64_t j = subset ? (int64_t)subset[warp] : warp;
-        double bv = 0.0;
+        double bv = 0.0, sv = DINF;
         int bk = -1;
         for (int64_t k = lane; k < a.K; k += 32) {
             const double v = __dsqrt_rn(masked_sum<VT>(a, j, k));
             if (v != v) continue;                       // MATLAB min skips NaN
-            if (bk < 0 || v < bv) { bv = v; bk = (int)k; }
+            if (bk < 0) { bv = v; bk = (int)k; }
+            else if (v < bv) { sv = bv; bv = v; bk = (int)k; }
+            else if (v < sv) sv = v;
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
             const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const double osv = __shfl_xor_sync(0xffffffffu, sv, o);
             const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
-            if (ok >= 0 && (bk < 0 || ov < bv || (ov == bv && ok < bk))) { bv = ov; bk = ok; }
+            if (ok >= 0) {
+                if (bk < 0) { bv = ov; bk = ok; sv = osv; }
+                else {
+                    const bool other = ov < bv || (ov == bv && ok < bk);
+                    const double loser = other ? bv : ov;
+                    sv = fmin(fmin(sv, osv), loser);
+                    if (other) { bv = ov; bk = ok; }
+                }
+            }
         }
         if (lane == 0) {
-            if (bk < 0) { bv = __longlong_as_double(0x7ff8000000000000LL); bk = 0; }   // all NaN
+            if (bk < 0) { bv = __longlong_as_double(0x7ff8000000000000LL); bk = 0; sv = 0.0; }   // all NaN
             assign[j] = bk;
             if (dist64) dist64[j] = bv;
             if (dist32) dist32[j] = (float)bv;
+            if (lb) lb[j] = __double2float_rd(sv * (1.0 - 1e-9));
         }
     }
 }
@@ -181,7 +196,7 @@ int skm_launch_exact_dist_beta(skm_ctx *ctx, const ExactArgs &a, double beta, do
 
 int skm_launch_exact_assign(skm_ctx *ctx, const ExactArgs &a, int32_t *assign, double *dist64,
                             float *dist32, const int32_t *subset, const int *subset_count_dev,
-                            int64_t subset_max)
+                            int64_t subset_max, float *lb)
 {
     int64_t total = subset ? subset_max : a.n;
     if (total <= 0) return SKM_OK;
@@ -190,10 +205,10 @@ int skm_launch_exact_assign(skm_ctx *ctx, const ExactArgs &a, int32_t *assign, d
     if (blocks > cap) blocks = cap;
     if (a.val_type == SKM_F32)
         k_exact_assign<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>(a, assign, dist64, dist32, subset,
-                                                                        subset_count_dev, total);
+                                                                        subset_count_dev, total, lb);
     else
         k_exact_assign<double><<<(unsigned)blocks, 256, 0, ctx->stream>>>(a, assign, dist64, dist32, subset,
-                                                                         subset_count_dev, total);
+                                                                         subset_count_dev, total, lb);
     SKM_CHECK_LAUNCH(ctx);
     return SKM_OK;
 }

@@ -308,7 +308,7 @@ class Dataset:
 class Lloyd:
     """Iteration state for K centres on one resident shard (skm_lloyd)."""
 
-    def __init__(self, ds: Dataset, K: int, incremental: bool = False):
+    def __init__(self, ds: Dataset, K: int, incremental: bool = False, bounded: bool = False):
         self.ds = ds
         self.K = int(K)
         self._lib = ds._lib
@@ -318,6 +318,18 @@ class Lloyd:
         ds._children.add(self)
         if incremental:
             self.set_update_mode(True)
+        if bounded:
+            self.set_assign_mode(True)
+
+    def set_assign_mode(self, bounded: bool):
+        """True: bounds carried across calls let most columns keep their centre after one centre evaluation
+        (skm_lloyd_set_assign_mode); assignments and distances are unchanged."""
+        check(self._lib.skm_lloyd_set_assign_mode(self.handle, 1 if bounded else 0))
+
+    def last_assign_flagged(self) -> int:
+        v = C.c_int64(0)
+        check(self._lib.skm_lloyd_last_assign(self.handle, C.byref(v)))
+        return int(v.value)
 
     def set_update_mode(self, incremental: bool):
         """False: per-cluster sums recomputed from all columns every iteration (the reference's way);

@@ -314,3 +314,46 @@ def test_incremental_update_equals_full_recompute(ctx, store):
     if sa.dff == 0.0:
         assert B.last_update() == ("unchanged", 0)
     A.close(); B.close(); ds.close()
+
+
+@pytest.mark.parametrize("kind,p,n,m,K", [("unstructured", 64, 30000, 8, 8), ("mixture", 784, 20000, 78, 10),
+                                          ("unstructured", 1024, 12000, 51, 64), ("mixture", 256, 9000, 13, 130),
+                                          ("unstructured", 96, 5000, 12, 2)])
+def test_bounded_assignment_equals_full_evaluation(ctx, kind, p, n, m, K):
+    """skm_lloyd_set_assign_mode(1): bounds carried across iterations.  Every iteration the assignments must
+    equal those of the run that evaluates every centre (and, first iteration, the oracle's), distances agree
+    to fp32 rounding, and once the centres settle most columns are kept by their bound."""
+    from sparsifiedkmeans_b200 import Dataset, Lloyd
+    X, c, gamma = make_sparsified(p=p, n=n, m=m, K=K, seed=K + p, kind=kind)
+    ds = Dataset.from_scipy(X, store="f32", ctx=ctx)
+    A, B = Lloyd(ds, K), Lloyd(ds, K, incremental=True, bounded=True)
+    A.set_centers(c); B.set_centers(c)
+    flagged = []
+    for it in range(25):
+        sa = A.step(gamma, gamma, True)
+        sb = B.step(gamma, gamma, True)
+        aa, da = A.assignments()
+        ab, db = B.assignments()
+        assert np.array_equal(aa, ab), (it, int(np.count_nonzero(aa != ab)))
+        np.testing.assert_allclose(db, da, rtol=3e-6, atol=1e-30)
+        np.testing.assert_allclose(B.get_centers(), A.get_centers(), rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(sb.sumsq, sa.sumsq, rtol=1e-5)
+        if it == 0:
+            assert np.array_equal(aa, host_ref.find_cluster_assignments(X, c, gamma)[0])
+            assert B.last_assign_flagged() == -1                 # no bounds yet: everything evaluated
+        flagged.append(B.last_assign_flagged())
+        if sa.dff == 0.0 and it > 3:
+            break
+    assert any(f >= 0 for f in flagged[1:])                       # the bounded pass ran
+    if sa.dff == 0.0:
+        assert flagged[-1] >= 0 and flagged[-1] <= n // 50        # at the fixed point (almost) everything is kept
+    # a centre replaced from outside (EmptyAction) is just another movement
+    cen = B.get_centers(); cen[:, 0] = X[:, 7].toarray().ravel() * gamma
+    A.set_centers(cen); B.set_centers(cen)
+    A.step(gamma, gamma, True); B.step(gamma, gamma, True)
+    assert np.array_equal(A.assignments()[0], B.assignments()[0])
+    # and a change of the distance scaling drops the bounds
+    A.assign(None); B.assign(None)
+    assert B.last_assign_flagged() == -1
+    assert np.array_equal(A.assignments()[0], B.assignments()[0])
+    A.close(); B.close(); ds.close()
