@@ -486,6 +486,8 @@ extern "C" int skm_lloyd_set_assign_mode(skm_lloyd *L, int mode)
     }
     L->assign_mode = mode;
     L->lb_valid = false;
+    L->bounded_skip = 0;
+    L->bounded_backoff = 0;
     return SKM_OK;
 }
 
@@ -519,7 +521,10 @@ extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
         // bounded pass: valid when the bounds exist and refer to the same scaling of the centres
         const double gnow = has_gamma ? gamma : nan("");
         const bool same_scale = (gnow == L->gamma_prev) || (gnow != gnow && L->gamma_prev != L->gamma_prev);
-        const bool usable = L->lb_valid && same_scale && L->assigned;
+        bool usable = L->lb_valid && same_scale && L->assigned;
+        // back off after a pass that kept too few columns: while the centres still move a lot the bounded pass
+        // is pure overhead (the full pass rewrites every bound anyway, so skipping costs nothing)
+        if (usable && L->bounded_skip > 0) { L->bounded_skip -= 1; usable = false; }
         {
             SkmTimed t(ctx, SKM_T_PREP);
             SKM_TRY(skm_launch_center_shift(ctx, ds->p, L->K, L->centers, L->centers_prev, has_gamma, gamma, L->shift));
@@ -538,6 +543,7 @@ extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
             }
             L->last_bounded_flagged = nfl;
             if (nfl <= ds->n / 8) {
+                L->bounded_backoff = 0;
                 // few columns left their bound: every centre, fp64, the reference's order; refreshes their lb
                 SkmTimed t(ctx, SKM_T_RECHECK);
                 SKM_TRY(skm_launch_exact_assign(ctx, ea, L->assign, nullptr, L->dist_f32, L->flagged, L->nflag, ds->n, L->lb));
@@ -547,6 +553,8 @@ extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
                 return SKM_OK;
             }
             // many movers: the full pass below re-evaluates everything and rewrites every bound
+            L->bounded_backoff = L->bounded_backoff ? (L->bounded_backoff < 8 ? 2 * L->bounded_backoff : 8) : 1;
+            L->bounded_skip = L->bounded_backoff;
         }
     }
     if (fast) {

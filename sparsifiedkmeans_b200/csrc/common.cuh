@@ -180,6 +180,7 @@ struct skm_lloyd {
     float   *table_t;        // [K][p+1] fp32 centres, one row per centre (bounded kernel)
     float   *shift;          // [K + 4] per-centre movement; then max, second max, argmax
     int64_t  last_bounded_flagged;   // columns the bounds could not keep (-1: the pass evaluated everything)
+    int      bounded_skip, bounded_backoff;   // passes to sit out after a bounded pass that kept too few columns
     bool     assigned, accumulated;
     bool     dist_is_f64;    // which of dist_f64 / dist_f32 the last assignment wrote
     int64_t  last_rechecked;

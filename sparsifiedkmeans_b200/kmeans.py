@@ -39,7 +39,7 @@ _DEFAULTS = dict(
     unbiasedInitialization=True, denseCenters=False,
 )
 _EXTRA = dict(Seed=None, Signs=None, SampleRows=None, StartIndices=None, Store="f32", Device=0,
-              MixDtype="f64", nargout=5, Context=None, Pipeline="auto", IncrementalUpdate=True)
+              MixDtype="f64", nargout=5, Context=None, Pipeline="auto", IncrementalUpdate=True, BoundedAssign=True)
 
 
 class KMeansError(RuntimeError):
@@ -336,7 +336,10 @@ def kmeans_sparsified(X=None, K=None, **opts):
             # IncrementalUpdate: the per-cluster sums only depend on the assignments, so from the second
             # iteration on only the columns that changed cluster move their entries (same centres up to fp64
             # rounding; False recomputes them from all columns every iteration like kmeans_sparsified.m:430-453)
-            L = Lloyd(ds, Kt, incremental=bool(o["IncrementalUpdate"]))
+            # BoundedAssign: bounds carried across iterations let a column keep its centre after one centre
+            # evaluation once the centres move little (same assignments; fp32 datasets only)
+            bounded = bool(o["BoundedAssign"]) and ds.store_dtype == "f32"
+            L = Lloyd(ds, Kt, incremental=bool(o["IncrementalUpdate"]), bounded=bounded)
             L.set_centers(centers)
             its = 0
             dff = obj = math.nan
@@ -371,7 +374,7 @@ def kmeans_sparsified(X=None, K=None, **opts):
                         _, distances = L.assignments()
                         L.close()
                         Kt = keep.size
-                        L = Lloyd(ds, Kt, incremental=bool(o["IncrementalUpdate"]))
+                        L = Lloyd(ds, Kt, incremental=bool(o["IncrementalUpdate"]), bounded=bounded)
                         L.set_centers(cen)
                         assignments = np.zeros(0, dtype=np.int32)                     # :457 assignments = []
                         dropped_last = True

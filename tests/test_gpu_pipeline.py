@@ -347,8 +347,11 @@ def test_bounded_assignment_equals_full_evaluation(ctx, kind, p, n, m, K):
     assert any(f >= 0 for f in flagged[1:])                       # the bounded pass ran
     if sa.dff == 0.0:
         # the centres stopped moving in the last update: from the next pass on every bound holds
-        A.step(gamma, gamma, True); B.step(gamma, gamma, True)
-        assert np.array_equal(A.assignments()[0], B.assignments()[0])
+        for _ in range(12):                                       # a failed bounded pass is followed by a back-off
+            A.step(gamma, gamma, True); B.step(gamma, gamma, True)
+            assert np.array_equal(A.assignments()[0], B.assignments()[0])
+            if B.last_assign_flagged() >= 0:
+                break
         assert 0 <= B.last_assign_flagged() <= n // 50, B.last_assign_flagged()
     # a centre replaced from outside (EmptyAction) is just another movement
     cen = B.get_centers(); cen[:, 0] = X[:, 7].toarray().ravel() * gamma
