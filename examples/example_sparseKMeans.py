@@ -42,7 +42,8 @@ def main():
     # accuracy up to relabelling (majority vote per cluster)
     acc = sum(np.bincount(lab[IDX == c + 1], minlength=a.k).max() for c in range(a.k) if np.any(IDX == c + 1)) / a.n
     print(f"GPU  kmeans_sparsified: {t * 1e3:8.1f} ms  accuracy {acc:.4f}  iterations/replicate {OUT['iterations'].mean():.1f}  "
-          f"pipeline={OUT['Pipeline']} sketch {OUT['TimeToSketch'] * 1e3:.1f} ms")
+          f"pipeline={OUT['Pipeline']} sketch {OUT['TimeToSketch'] * 1e3:.1f} ms  "
+          f"replicates {OUT['replicateTimes'].sum() * 1e3:.1f} ms (init {OUT['TimeInitialization'] * 1e3:.1f} ms)")
     if a.cpu:
         from oracle import host_ref
         from sparsifiedkmeans_b200.kmeans import matlab_round, randsample_block

@@ -338,8 +338,11 @@ def kmeans_sparsified(X=None, K=None, **opts):
             # rounding; False recomputes them from all columns every iteration like kmeans_sparsified.m:430-453)
             # BoundedAssign: bounds carried across iterations let a column keep its centre after one centre
             # evaluation once the centres move little (same assignments; fp32 datasets only)
-            bounded = bool(o["BoundedAssign"]) and ds.store_dtype == "f32"
-            L = Lloyd(ds, Kt, incremental=bool(o["IncrementalUpdate"]), bounded=bounded)
+            # (both modes add a host synchronisation per iteration, which only pays off on matrices of some size)
+            big = ds.nnz >= 2_000_000
+            bounded = bool(o["BoundedAssign"]) and ds.store_dtype == "f32" and big
+            incremental = bool(o["IncrementalUpdate"]) and big
+            L = Lloyd(ds, Kt, incremental=incremental, bounded=bounded)
             L.set_centers(centers)
             its = 0
             dff = obj = math.nan
@@ -374,7 +377,7 @@ def kmeans_sparsified(X=None, K=None, **opts):
                         _, distances = L.assignments()
                         L.close()
                         Kt = keep.size
-                        L = Lloyd(ds, Kt, incremental=bool(o["IncrementalUpdate"]), bounded=bounded)
+                        L = Lloyd(ds, Kt, incremental=incremental, bounded=bounded)
                         L.set_centers(cen)
                         assignments = np.zeros(0, dtype=np.int32)                     # :457 assignments = []
                         dropped_last = True
