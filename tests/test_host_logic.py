@@ -61,3 +61,28 @@ def test_shard_bounds_cover_all_columns():
             assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_oracle_dense_branch_and_second_pass_restatement():
+    """The oracle's restatement of the dense branch (findClusterAssignments.m:154-175, expand-quadratic arm) and of the
+    in-core two-pass block (kmeans_sparsified.m:542-560) against a direct evaluation of their definitions."""
+    from oracle import host_ref
+    rng = np.random.default_rng(4)
+    p, n, K = 30, 400, 5
+    X = rng.standard_normal((p, n))
+    c = rng.standard_normal((p, K))
+    a, d, D2 = host_ref.find_cluster_assignments_dense(X, c)
+    direct = np.stack([np.sqrt(((X - c[:, [k]]) ** 2).sum(axis=0)) for k in range(K)])
+    assert np.array_equal(a, direct.argmin(axis=0) + 1)
+    np.testing.assert_allclose(d, direct.min(axis=0), rtol=1e-10)
+    np.testing.assert_allclose(D2, direct ** 2, rtol=1e-9, atol=1e-9)
+    c[:, 3] = c[:, 1]                                      # a duplicated centre never wins over its twin (first occurrence)
+    a2, _, _ = host_ref.find_cluster_assignments_dense(X, c)
+    assert not np.any(a2 == 4)
+    lab = rng.integers(1, K + 1, n)
+    lab[lab == 2] = 1                                      # an empty cluster keeps its zero column (:545)
+    c2, a3, d3 = host_ref.second_pass(X, c, lab, K)
+    assert np.all(c2[:, 1] == 0)
+    for k in (0, 2, 3, 4):
+        np.testing.assert_allclose(c2[:, k], X[:, lab == k + 1].mean(axis=1), rtol=1e-12)
+    assert np.array_equal(a3, a2)
