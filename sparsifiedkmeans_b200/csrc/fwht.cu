@@ -379,7 +379,12 @@ __global__ void __launch_bounds__(256) k_fwht_sample_warp(int64_t n, int m_keep,
     const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const float root = sqrtf((float)P2), level = __fdiv_rn((float)m_keep, (float)P2);
     for (; col < n; col += stride) {
-        // the sample does not depend on the data: mark it first, while the column buffer is free
+        // issue the column's loads first: the sample does not depend on the data, so marking it (row list
+        // reads or the Philox draws) runs while they are in flight instead of in front of them
+        const float *g = x + col * P2;
+        float v[E];
+#pragma unroll
+        for (int j = 0; j < E; ++j) v[j] = __ldcs(g + ((j << 5) | lane));
         bits[lane] = 0u;
         __syncwarp();
         if (rows) {
@@ -393,13 +398,8 @@ __global__ void __launch_bounds__(256) k_fwht_sample_warp(int64_t n, int m_keep,
             mark_random_rows(bits, reinterpret_cast<int *>(s), P2, m_keep, seed, col0 + col, lane, 32, WarpBarrierAny());
         }
         __syncwarp();
-        const float *g = x + col * P2;
-        float v[E];
 #pragma unroll
-        for (int j = 0; j < E; ++j) {
-            const int idx = (j << 5) | lane;
-            v[j] = __ldcs(g + idx) * __ldg(signs + idx);
-        }
+        for (int j = 0; j < E; ++j) v[j] *= __ldg(signs + ((j << 5) | lane));
         wht_regs_and_lanes<E>(v, lane);
 #pragma unroll
         for (int j = 0; j < E; ++j) s[(j << 5) | lane] = v[j];
@@ -453,6 +453,11 @@ __global__ void __launch_bounds__(32 * W) k_fwht_sample_cta(int64_t n, int m_kee
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const float root = sqrtf((float)P2), level = __fdiv_rn((float)m_keep, (float)P2);
     for (int64_t col = blockIdx.x; col < n; col += gridDim.x) {
+        // loads first, marking while they are in flight (see k_fwht_sample_warp)
+        const float *g = x + col * P2;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __ldcs(g + ((w << 10) | (j << 5) | lane));
         bits[threadIdx.x] = 0u;
         __syncthreads();
         if (rows) {
@@ -466,13 +471,8 @@ __global__ void __launch_bounds__(32 * W) k_fwht_sample_cta(int64_t n, int m_kee
             mark_random_rows(bits, reinterpret_cast<int *>(s), P2, m_keep, seed, col0 + col, threadIdx.x, T, CtaBarrierAny());
         }
         __syncthreads();
-        const float *g = x + col * P2;
-        float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int idx = (w << 10) | (j << 5) | lane;
-            v[j] = __ldcs(g + idx) * __ldg(signs + idx);
-        }
+        for (int j = 0; j < 32; ++j) v[j] *= __ldg(signs + ((w << 10) | (j << 5) | lane));
         wht_regs_and_lanes<32>(v, lane);
 #pragma unroll
         for (int j = 0; j < 32; ++j) s[(w << 10) | (j << 5) | lane] = v[j];
