@@ -326,7 +326,8 @@ __device__ __forceinline__ void mark_random_rows(uint32_t *bits, int *owner, int
     }
 }
 
-struct WarpBarrierAny { __device__ bool operator()(bool p) const { return __any_sync(0xffffffffu, p); } };
+// __syncwarp orders the lanes' shared-memory accesses (a vote alone converges the warp but is no memory barrier)
+struct WarpBarrierAny { __device__ bool operator()(bool p) const { __syncwarp(); const bool r = __any_sync(0xffffffffu, p); __syncwarp(); return r; } };
 struct CtaBarrierAny { __device__ bool operator()(bool p) const { return __syncthreads_or(p) != 0; } };
 
 // rows_out[col*m .. +m) = the sampled rows of global column col0+col, ascending
