@@ -144,11 +144,13 @@ __device__ __forceinline__ void wht_regs_and_lanes(float (&v)[E], int lane)
     }
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const bool up = (lane & o) != 0;
+        // upper lane of the pair: other - v, lower lane: v + other; as ONE fused multiply-add with a +-1
+        // factor (exact: the product is v or -v, so the result is the same single rounding of the sum)
+        const float sg = (lane & o) ? -1.f : 1.f;
 #pragma unroll
         for (int j = 0; j < E; ++j) {
             const float other = __shfl_xor_sync(0xffffffffu, v[j], o);
-            v[j] = up ? other - v[j] : v[j] + other;
+            v[j] = fmaf(sg, v[j], other);
         }
     }
 }
