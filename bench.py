@@ -288,7 +288,9 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     # pinned host copy for the end-to-end leg (made before the device tensors are released)
-    n_e2e = min(n, args.e2e_n) if args.e2e_n else n
+    # columns per end-to-end step: everything on one GPU; under torchrun a bounded sample per rank, so that the
+    # pinned host copies of all ranks together stay well inside the box's memory (throughput does not depend on it)
+    n_e2e = min(n, args.e2e_n) if args.e2e_n else (n if world == 1 else min(n, 4_000_000))
     h_colptr = torch.empty(n_e2e + 1, dtype=torch.int64, pin_memory=True)
     h_rowidx = torch.empty(n_e2e * m, dtype=torch.int32, pin_memory=True)
     h_val = torch.empty(n_e2e * m, dtype=torch.float32, pin_memory=True)
