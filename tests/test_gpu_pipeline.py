@@ -363,3 +363,23 @@ def test_bounded_assignment_equals_full_evaluation(ctx, kind, p, n, m, K):
     assert B.last_assign_flagged() == -1
     assert np.array_equal(A.assignments()[0], B.assignments()[0])
     A.close(); B.close(); ds.close()
+
+
+def test_kmeans_driver_modes_do_not_change_the_result(ctx):
+    """Above 2e6 stored entries kmeans_sparsified turns the bounded assignment and the incremental update on;
+    the run must be the one the plain modes produce (same seeds => same sample, same k-means++ picks)."""
+    from sparsifiedkmeans_b200 import kmeans_sparsified
+    rng = np.random.default_rng(12)
+    n, p, K = 42000, 512, 6
+    mu = rng.standard_normal((K, p))
+    lab = rng.integers(K, size=n)
+    X = (mu[lab] + 0.8 * rng.standard_normal((n, p))).astype(np.float32)      # overlapping clusters: several iterations
+    kw = dict(Sparsify=True, SparsityLevel=0.1, Seed=3, Replicates=2, MaxIter=30, Context=ctx)
+    fast = kmeans_sparsified(X, K, **kw)
+    plain = kmeans_sparsified(X, K, IncrementalUpdate=False, BoundedAssign=False, **kw)
+    assert fast[4]["iterations"].sum() >= 6
+    assert np.array_equal(fast[4]["iterations"], plain[4]["iterations"])
+    assert np.array_equal(fast[0], plain[0])
+    np.testing.assert_allclose(fast[1], plain[1], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(fast[3], plain[3], rtol=3e-6)
+    np.testing.assert_allclose(fast[2], plain[2], rtol=1e-5)
