@@ -374,10 +374,12 @@ def test_kmeans_driver_modes_do_not_change_the_result(ctx):
     mu = rng.standard_normal((K, p))
     lab = rng.integers(K, size=n)
     X = (mu[lab] + 0.8 * rng.standard_normal((n, p))).astype(np.float32)      # overlapping clusters: several iterations
-    kw = dict(Sparsify=True, SparsityLevel=0.1, Seed=3, Replicates=2, MaxIter=30, Context=ctx)
+    # one replicate: with several, two replicates that reach the same clustering tie on the objective up to
+    # rounding and the "best" one (hence the label order) is decided by the last bit
+    kw = dict(Sparsify=True, SparsityLevel=0.1, Seed=3, Replicates=1, MaxIter=30, Context=ctx)
     fast = kmeans_sparsified(X, K, **kw)
     plain = kmeans_sparsified(X, K, IncrementalUpdate=False, BoundedAssign=False, **kw)
-    assert fast[4]["iterations"].sum() >= 6
+    assert fast[4]["iterations"].sum() >= 4
     assert np.array_equal(fast[4]["iterations"], plain[4]["iterations"])
     assert np.array_equal(fast[0], plain[0])
     np.testing.assert_allclose(fast[1], plain[1], rtol=1e-9, atol=1e-11)
