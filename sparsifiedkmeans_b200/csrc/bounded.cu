@@ -40,7 +40,10 @@ struct BoundedParams {
     int           *nflag;
 };
 
-template <int THREADS>
+// PADTAIL: the last batch of a column is padded with (zero row, 0) entries instead of a serial tail.  It pays
+// when part of the table is read through L2 (K = 64: 1.52 -> 1.39 ms) and costs when everything is in shared
+// memory and the kernel already runs at the HBM rate (K = 10: 0.98 -> 1.07 ms), so the launcher picks.
+template <int THREADS, bool PADTAIL>
 __global__ void __launch_bounds__(THREADS) k_assign_bounded(const BoundedParams P)
 {
     extern __shared__ __align__(16) float s_tab[];
@@ -78,20 +81,42 @@ __global__ void __launch_bounds__(THREADS) k_assign_bounded(const BoundedParams 
             const float d = x - v;
             acc = fmaf(d, d, acc);
         };
-        // software pipeline over batches of four 16-byte loads (eight entries); the last batch is padded with
-        // (zero row, 0) entries instead of a serial tail, and the next batch is in flight while the current one is
-        // gathered (ncu before: 41 cycles of long-scoreboard stall per issue at K=64 with 32 resident warps -- a
-        // latency-bound kernel needs more bytes in flight per warp, not more warps)
-        const int4 padq = make_int4(P.p, 0, P.p, 0);
-        auto fetch = [&](int t) -> int4 { return t < w2 ? __ldcs(src + t * 32) : padq; };
-        int4 n0 = fetch(0), n1 = fetch(1), n2 = fetch(2), n3 = fetch(3);
-        for (int t2 = 0; t2 < w2; t2 += 4) {
-            const int4 q0 = n0, q1 = n1, q2 = n2, q3 = n3;
-            n0 = fetch(t2 + 4); n1 = fetch(t2 + 5); n2 = fetch(t2 + 6); n3 = fetch(t2 + 7);
-            one(q0.x, __int_as_float(q0.y)); one(q0.z, __int_as_float(q0.w));
-            one(q1.x, __int_as_float(q1.y)); one(q1.z, __int_as_float(q1.w));
-            one(q2.x, __int_as_float(q2.y)); one(q2.z, __int_as_float(q2.w));
-            one(q3.x, __int_as_float(q3.y)); one(q3.z, __int_as_float(q3.w));
+        // software pipeline: the next four 16-byte loads are in flight while the current eight entries are
+        // gathered (ncu before this: 41 cycles of long-scoreboard stall per issue at K=64, 32 resident warps --
+        // a latency-bound kernel needs more bytes in flight per warp, not more warps)
+        if (PADTAIL) {
+            const int4 padq = make_int4(P.p, 0, P.p, 0);
+            auto fetch = [&](int t) -> int4 { return t < w2 ? __ldcs(src + t * 32) : padq; };
+            int4 n0 = fetch(0), n1 = fetch(1), n2 = fetch(2), n3 = fetch(3);
+            for (int t2 = 0; t2 < w2; t2 += 4) {
+                const int4 q0 = n0, q1 = n1, q2 = n2, q3 = n3;
+                n0 = fetch(t2 + 4); n1 = fetch(t2 + 5); n2 = fetch(t2 + 6); n3 = fetch(t2 + 7);
+                one(q0.x, __int_as_float(q0.y)); one(q0.z, __int_as_float(q0.w));
+                one(q1.x, __int_as_float(q1.y)); one(q1.z, __int_as_float(q1.w));
+                one(q2.x, __int_as_float(q2.y)); one(q2.z, __int_as_float(q2.w));
+                one(q3.x, __int_as_float(q3.y)); one(q3.z, __int_as_float(q3.w));
+            }
+        } else {
+            int t2 = 0;
+            int4 n0, n1, n2, n3;
+            if (w2 >= 4) {
+                n0 = __ldcs(src + 0 * 32); n1 = __ldcs(src + 1 * 32); n2 = __ldcs(src + 2 * 32); n3 = __ldcs(src + 3 * 32);
+            }
+            for (; t2 + 4 <= w2; t2 += 4) {
+                const int4 q0 = n0, q1 = n1, q2 = n2, q3 = n3;
+                if (t2 + 8 <= w2) {
+                    n0 = __ldcs(src + (t2 + 4) * 32); n1 = __ldcs(src + (t2 + 5) * 32);
+                    n2 = __ldcs(src + (t2 + 6) * 32); n3 = __ldcs(src + (t2 + 7) * 32);
+                }
+                one(q0.x, __int_as_float(q0.y)); one(q0.z, __int_as_float(q0.w));
+                one(q1.x, __int_as_float(q1.y)); one(q1.z, __int_as_float(q1.w));
+                one(q2.x, __int_as_float(q2.y)); one(q2.z, __int_as_float(q2.w));
+                one(q3.x, __int_as_float(q3.y)); one(q3.z, __int_as_float(q3.w));
+            }
+            for (; t2 < w2; ++t2) {
+                const int4 q = __ldcs(src + t2 * 32);
+                one(q.x, __int_as_float(q.y)); one(q.z, __int_as_float(q.w));
+            }
         }
         if (!live) continue;
         // bound after this move of the centres (rounded down), then the test with K1's rounding guard
@@ -215,7 +240,8 @@ int skm_launch_assign_bounded(skm_ctx *ctx, const skm_dataset *ds, int64_t K, co
     P.gb_unit = (float)(2.02 * u * sqrt(m));
     P.ge_unit = (float)(2.1 * u * u * m);
     P.cmax = cmax; P.shift = shift; P.assign = assign; P.lb = lb; P.dist = dist; P.flagged = flagged; P.nflag = nflag;
-    auto kern = k_assign_bounded<1024>;
+    const bool padtail = ksm < K;                             // part of the table is read through L2
+    auto kern = padtail ? k_assign_bounded<1024, true> : k_assign_bounded<1024, false>;
     SKM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     SKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 1024, smem));
