@@ -36,10 +36,12 @@ def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
 class CudaShardEngine:
     """libskm_b200 on this rank's GPU."""
 
-    def __init__(self, ds, K: int):
+    def __init__(self, ds, K: int, incremental: bool = False, bounded: bool = False):
         from .engine import Lloyd
         self.ds = ds
-        self.L = Lloyd(ds, K)
+        # both modes are per-shard decisions (each rank keeps its own sums and bounds); the all-reduce buffer
+        # is a copy of the kept sums, so the collective is issued by every rank in every iteration either way
+        self.L = Lloyd(ds, K, incremental=incremental, bounded=bounded)
         self.n_local, self.p, self.K = ds.n, ds.p, int(K)
         self._ext = None
 
