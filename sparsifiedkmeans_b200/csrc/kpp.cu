@@ -4,6 +4,7 @@
 // running minimum gives bit-identical values with one centre-pass per round.  Distances are
 // evaluated in fp64 in the reference's order (SparseMatrixMinusCluster.c:133-141, K = 1).
 #include "common.cuh"
+#include <stdlib.h>
 #include <vector>
 
 namespace {
@@ -13,19 +14,23 @@ __global__ void k_kpp_update(int64_t n, const int64_t *__restrict__ colptr,
                              const int32_t *__restrict__ rowidx, const VT *__restrict__ val,
                              const double *__restrict__ c, int first, double *__restrict__ mind)
 {
-    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    double s = 0.0;
-    for (int64_t t = colptr[j]; t < colptr[j + 1]; ++t) {
-        const double d = __dsub_rn((double)val[t], c[rowidx[t]]);
-        s = __dadd_rn(s, __dmul_rn(d, d));
-    }
-    const double d = __dsqrt_rn(s);
-    if (first) mind[j] = d;
-    else {
-        const double o = mind[j];
-        // MATLAB min ignores NaN unless both are NaN
-        mind[j] = (d != d) ? o : ((o != o) ? d : (d < o ? d : o));
+    // thread per column, grid-stride: the launcher keeps FEW warps resident per SM on purpose.  A thread walks
+    // its own column, so a warp touches 32 different 128-byte lines per step and re-uses each of them for 32
+    // steps; that only works while the lines of all resident warps (8 KB per warp) fit in L1.
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        double s = 0.0;
+        for (int64_t t = colptr[j]; t < colptr[j + 1]; ++t) {
+            const double d = __dsub_rn((double)val[t], c[rowidx[t]]);
+            s = __dadd_rn(s, __dmul_rn(d, d));
+        }
+        const double d = __dsqrt_rn(s);
+        if (first) mind[j] = d;
+        else {
+            const double o = mind[j];
+            // MATLAB min ignores NaN unless both are NaN
+            mind[j] = (d != d) ? o : ((o != o) ? d : (d < o ? d : o));
+        }
     }
 }
 
@@ -53,6 +58,11 @@ int skm_launch_kpp_update(skm_ctx *ctx, const skm_dataset *ds, const double *c_s
     (void)unused;
     if (ds->n == 0) return SKM_OK;
     int64_t blocks = (ds->n + 255) / 256;
+    {
+        static const char *e = getenv("SKM_KPP_CTAS");           // resident 256-thread CTAs per SM (0 = one per 256 columns)
+        const int per_sm = e ? atoi(e) : 0;
+        if (per_sm > 0 && blocks > (int64_t)ctx->sm_count * per_sm) blocks = (int64_t)ctx->sm_count * per_sm;
+    }
     if (ds->store_dtype == SKM_F32)
         k_kpp_update<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>(ds->n, ds->colptr, ds->rowidx,
                                                                       (const float *)ds->val, c_scaled, first, mind);
