@@ -14,9 +14,9 @@ __global__ void k_kpp_update(int64_t n, const int64_t *__restrict__ colptr,
                              const int32_t *__restrict__ rowidx, const VT *__restrict__ val,
                              const double *__restrict__ c, int first, double *__restrict__ mind)
 {
-    // thread per column, grid-stride: the launcher keeps FEW warps resident per SM on purpose.  A thread walks
-    // its own column, so a warp touches 32 different 128-byte lines per step and re-uses each of them for 32
-    // steps; that only works while the lines of all resident warps (8 KB per warp) fit in L1.
+    // thread per column, grid-stride.  Measured 2.3-2.4 TB/s algorithmic whatever the number of resident warps
+    // (8 ... 64 per SM, tools/debug/kpp_probe.py): the walk is a dependent chain per thread (index load -> centre
+    // gather -> three fp64 operations in the reference's order), not a capacity problem.
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
         double s = 0.0;
@@ -59,7 +59,7 @@ int skm_launch_kpp_update(skm_ctx *ctx, const skm_dataset *ds, const double *c_s
     if (ds->n == 0) return SKM_OK;
     int64_t blocks = (ds->n + 255) / 256;
     {
-        static const char *e = getenv("SKM_KPP_CTAS");           // resident 256-thread CTAs per SM (0 = one per 256 columns)
+        static const char *e = getenv("SKM_KPP_CTAS");           // tuning knob: resident 256-thread CTAs per SM
         const int per_sm = e ? atoi(e) : 0;
         if (per_sm > 0 && blocks > (int64_t)ctx->sm_count * per_sm) blocks = (int64_t)ctx->sm_count * per_sm;
     }
