@@ -16,7 +16,10 @@ __global__ void k_kpp_update(int64_t n, const int64_t *__restrict__ colptr,
 {
     // thread per column, grid-stride.  Measured 2.3-2.4 TB/s algorithmic whatever the number of resident warps
     // (8 ... 64 per SM, tools/debug/kpp_probe.py): the walk is a dependent chain per thread (index load -> centre
-    // gather -> three fp64 operations in the reference's order), not a capacity problem.
+    // gather -> three fp64 operations in the reference's order), not a capacity problem.  A staged variant
+    // (warp-cooperative coalesced pass writing the rounded squares to shared memory, then per-lane ordered sums)
+    // was bit-identical but 3.6x slower: 20 KB of squares per warp leaves 8 warps per SM and too few bytes in
+    // flight; it would need bulk asynchronous copies of the slice to pay off.
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
         double s = 0.0;
