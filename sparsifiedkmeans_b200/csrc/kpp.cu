@@ -37,51 +37,6 @@ __global__ void k_kpp_update(int64_t n, const int64_t *__restrict__ colptr,
     }
 }
 
-// Staged form of the same update: a warp takes 32 consecutive columns, whose entries are one contiguous
-// range of the CSC image.  Phase A walks that range column by column with ALL lanes (coalesced 128-byte
-// reads, many independent loads in flight) and leaves the squared differences (x - c[row])^2 -- each one
-// rounded exactly as the reference rounds it -- in shared memory; phase B lets lane l add up column l's
-// squares in stored order, so the sum is the reference's sum bit for bit, without the per-thread chain of
-// dependent global loads of k_kpp_update.
-template <typename VT>
-__global__ void __launch_bounds__(128) k_kpp_update_staged(int64_t n, int stride, const int64_t *__restrict__ colptr,
-                                                           const int32_t *__restrict__ rowidx, const VT *__restrict__ val,
-                                                           const double *__restrict__ c, int first, double *__restrict__ mind)
-{
-    extern __shared__ double kpp_sq[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double *sq = kpp_sq + (size_t)wib * 32 * stride;
-    const int64_t nslices = (n + 31) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t sl = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; sl < nslices; sl += nwarps) {
-        const int64_t j = sl * 32 + lane;
-        int64_t a = 0, b = 0;
-        if (j < n) { a = colptr[j]; b = colptr[j + 1]; }
-        for (int cc = 0; cc < 32; ++cc) {
-            const int64_t ca = __shfl_sync(0xffffffffu, a, cc), cb = __shfl_sync(0xffffffffu, b, cc);
-            double *dst = sq + (size_t)cc * stride;
-            for (int64_t t = ca + lane; t < cb; t += 32) {
-                const double d = __dsub_rn((double)val[t], c[rowidx[t]]);
-                dst[t - ca] = __dmul_rn(d, d);
-            }
-        }
-        __syncwarp();
-        if (j < n) {
-            const double *src = sq + (size_t)lane * stride;
-            const int len = (int)(b - a);
-            double s = 0.0;
-            for (int t = 0; t < len; ++t) s = __dadd_rn(s, src[t]);
-            const double d = __dsqrt_rn(s);
-            if (first) mind[j] = d;
-            else {
-                const double o = mind[j];
-                mind[j] = (d != d) ? o : ((o != o) ? d : (d < o ? d : o));
-            }
-        }
-        __syncwarp();
-    }
-}
-
 // deterministic block sums of mind^2 over fixed blocks of 1024 columns
 __global__ void k_block_sumsq(int64_t n, const double *__restrict__ mind, double *__restrict__ bsum)
 {
@@ -110,33 +65,6 @@ int skm_launch_kpp_update(skm_ctx *ctx, const skm_dataset *ds, const double *c_s
         static const char *e = getenv("SKM_KPP_CTAS");           // tuning knob: resident 256-thread CTAs per SM
         const int per_sm = e ? atoi(e) : 0;
         if (per_sm > 0 && blocks > (int64_t)ctx->sm_count * per_sm) blocks = (int64_t)ctx->sm_count * per_sm;
-    }
-    // staged kernel when a 4-warp CTA's squares fit in shared memory (columns of up to ~800 entries)
-    static const bool no_staged = getenv("SKM_KPP_SIMPLE") != nullptr;
-    const int stride = (int)(ds->max_col_nnz > 0 ? ds->max_col_nnz : 1) | 1;
-    const size_t smem = (size_t)4 * 32 * stride * sizeof(double);
-    if (!no_staged && smem <= (size_t)ctx->smem_optin - 1024) {
-        int per_sm = 1;
-        int64_t sblocks;
-        if (ds->store_dtype == SKM_F32) {
-            SKM_CUDA(cudaFuncSetAttribute(k_kpp_update_staged<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            SKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_kpp_update_staged<float>, 128, smem));
-        } else {
-            SKM_CUDA(cudaFuncSetAttribute(k_kpp_update_staged<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            SKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_kpp_update_staged<double>, 128, smem));
-        }
-        if (per_sm < 1) per_sm = 1;
-        sblocks = (int64_t)ctx->sm_count * per_sm;
-        const int64_t need = ((ds->n + 31) / 32 + 3) / 4;
-        if (sblocks > need) sblocks = need;
-        if (ds->store_dtype == SKM_F32)
-            k_kpp_update_staged<float><<<(unsigned)sblocks, 128, smem, ctx->stream>>>(ds->n, stride, ds->colptr, ds->rowidx,
-                                                                                     (const float *)ds->val, c_scaled, first, mind);
-        else
-            k_kpp_update_staged<double><<<(unsigned)sblocks, 128, smem, ctx->stream>>>(ds->n, stride, ds->colptr, ds->rowidx,
-                                                                                      (const double *)ds->val, c_scaled, first, mind);
-        SKM_CHECK_LAUNCH(ctx);
-        return SKM_OK;
     }
     if (ds->store_dtype == SKM_F32)
         k_kpp_update<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>(ds->n, ds->colptr, ds->rowidx,
