@@ -86,3 +86,33 @@ def test_oracle_dense_branch_and_second_pass_restatement():
     for k in (0, 2, 3, 4):
         np.testing.assert_allclose(c2[:, k], X[:, lab == k + 1].mean(axis=1), rtol=1e-12)
     assert np.array_equal(a3, a2)
+
+
+def test_data_file_container_checks(tmp_path):
+    """DataFile mode (kmeans_sparsified.m:180-207): what the file opener accepts, before any GPU work."""
+    f64 = tmp_path / "ok.npy"
+    np.save(f64, np.zeros((6, 4)))
+    A = km._open_data_file(str(f64))
+    assert isinstance(A, np.memmap) and A.shape == (6, 4)
+    assert km._open_data_file(str(tmp_path / "ok")).shape == (6, 4)           # extension optional (:187-189)
+    np.save(tmp_path / "vec.npy", np.zeros(5))
+    with pytest.raises(km.KMeansError, match="bad size"):
+        km._open_data_file(str(tmp_path / "vec.npy"))
+    np.save(tmp_path / "ints.npy", np.zeros((3, 3), dtype=np.int32))
+    with pytest.raises(km.KMeansError, match="float32 or float64"):
+        km._open_data_file(str(tmp_path / "ints.npy"))
+    with pytest.raises(km.KMeansError, match="Cannot find"):
+        km._open_data_file(str(tmp_path / "missing"))
+    (tmp_path / "data.mat").write_bytes(b"MATLAB 7.3 MAT-file")
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(NotImplementedError, match="h5py"):
+            km._open_data_file(str(tmp_path / "data.mat"))
+
+
+def test_driver_accepts_the_iteration_mode_options():
+    X = np.zeros((10, 4))
+    for opt in ("IncrementalUpdate", "BoundedAssign"):
+        with pytest.raises(NotImplementedError):           # recognised option; stops at Sparsify=false as before
+            km.kmeans_sparsified(X, 2, **{opt: False})
