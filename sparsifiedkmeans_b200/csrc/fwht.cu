@@ -191,34 +191,15 @@ __global__ void __launch_bounds__(32 * W) k_fwht_cta(int64_t n, float *__restric
     float *s = reinterpret_cast<float *>(fc_raw);
     constexpr int T = 32 * W, P2 = 1024 * W, G = 32 / W;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    // W <= 4 (at most 128 threads; 96 registers still leave five CTAs per SM): the next column of this CTA is loaded while the
-    // current one is transformed, so a column is in flight for the whole iteration instead of only in its load
-    // phase; wider CTAs would lose residency to the second register set (W = 32 has 64 registers per thread at most)
-    constexpr bool PREFETCH = W <= 4;
-    float nxt[PREFETCH ? 32 : 1];
-    if (PREFETCH && (int64_t)blockIdx.x < n) {
-        const float *g0 = x + (int64_t)blockIdx.x * P2;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) nxt[PREFETCH ? j : 0] = __ldcs(g0 + ((w << 10) | (j << 5) | lane));
-    }
     for (int64_t col = blockIdx.x; col < n; col += gridDim.x) {
         float *g = x + col * P2;
         float v[32];
-        if (PREFETCH) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = nxt[PREFETCH ? j : 0];
-            if (col + gridDim.x < n) {
-                const float *gn = x + (col + gridDim.x) * P2;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) nxt[PREFETCH ? j : 0] = __ldcs(gn + ((w << 10) | (j << 5) | lane));
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __ldcs(g + ((w << 10) | (j << 5) | lane));
-        }
-        if (signs) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= __ldg(signs + ((w << 10) | (j << 5) | lane));
+        for (int j = 0; j < 32; ++j) {
+            const int idx = (w << 10) | (j << 5) | lane;
+            float t = __ldcs(g + idx);
+            if (signs) t *= __ldg(signs + idx);
+            v[j] = t;
         }
         wht_regs_and_lanes<32>(v, lane);
 #pragma unroll
