@@ -31,7 +31,7 @@ def _stale(target: str, deps: list[str]) -> bool:
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "sched16.cuh"),
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "sched16.cuh"), os.path.join(CSRC, "philox.cuh"),
                os.path.join(HERE, "..", "include", "skm_b200.h")]
     objs, jobs = [], []
     for src in SOURCES:

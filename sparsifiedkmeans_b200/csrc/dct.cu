@@ -14,6 +14,7 @@
 // (Philox, same contract as the Hadamard path) fused with the gather that writes CSC directly, so
 // the mixed dense chunk never leaves the device.
 #include "common.cuh"
+#include "philox.cuh"
 #include <algorithm>
 #include <dlfcn.h>
 #include <math.h>
@@ -84,21 +85,6 @@ void dct_matrix(int64_t p, const double *signs, double scale, bool inverse, std:
 }
 
 // ---- general-p row sampler + gather ------------------------------------------------------------
-__device__ __forceinline__ uint32_t philox4(uint64_t seed, uint64_t col, uint32_t draw, uint32_t attempt)
-{
-    uint32_t c0 = draw, c1 = attempt, c2 = (uint32_t)col, c3 = (uint32_t)(col >> 32);
-    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    return c0;
-}
-
 // One CTA per column: m distinct rows of [0,p), uniform over m-subsets (rejection; draw i proposes
 // floor(philox * p / 2^32), the smallest draw index wins a contested row, the others redraw -- a pure
 // function of (seed, global column)), then the rows are emitted ascending with value y / (m/p)
@@ -133,7 +119,7 @@ __global__ void k_sample_gather(int p, int64_t n, int m, const float *__restrict
             while (__syncthreads_or(pending)) {
                 int r = -1;
                 if (pending) {
-                    r = (int)__umulhi(philox4(seed, (uint64_t)(col0 + col), (uint32_t)draw, attempt), (uint32_t)p);
+                    r = (int)__umulhi(skm_philox_draw(seed, (uint64_t)(col0 + col), (uint32_t)draw, attempt), (uint32_t)p);
                     if ((bits[r >> 5] >> (r & 31)) & 1u) { r = -1; ++attempt; }
                     else atomicMin(&owner[r], draw);
                 }

@@ -8,6 +8,7 @@
 // the fp32 one is the fast path (with the sign flip fused on load, the 1/sqrt(p2) division
 // fused on store, and optionally the fixed-count row sample fused on store).
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace {
 
@@ -283,21 +284,6 @@ int fwht_f32_fast(skm_ctx *ctx, int64_t m, int64_t n, float *x, const float *sig
 // closed source, so the draws come from Philox4x32-10 keyed by the seed and counted by
 // (global column, draw index, attempt): the sample of a column does not depend on how columns
 // are sharded over GPUs or scheduled over threads.
-__device__ __forceinline__ uint32_t philox_draw(uint64_t seed, uint64_t col, uint32_t draw, uint32_t attempt)
-{
-    uint32_t c0 = draw, c1 = attempt, c2 = (uint32_t)col, c3 = (uint32_t)(col >> 32);
-    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    return c0;
-}
-
 // Marks m distinct uniformly random rows of [0, P2) in `bits` (P2/32 words, already zero).
 // `owner` is scratch of P2 ints shared by the T cooperating threads; barrier_any(pred) must
 // synchronise those T threads and return whether pred holds for any of them.  Draw i proposes
@@ -314,7 +300,7 @@ __device__ __forceinline__ void mark_random_rows(uint32_t *bits, int *owner, int
     while (barrier_any(pending)) {
         int r = -1;
         if (pending) {
-            r = (int)(philox_draw(seed, (uint64_t)col, (uint32_t)draw, attempt) & (uint32_t)(P2 - 1));
+            r = (int)(skm_philox_draw(seed, (uint64_t)col, (uint32_t)draw, attempt) & (uint32_t)(P2 - 1));
             if ((bits[r >> 5] >> (r & 31)) & 1u) { r = -1; ++attempt; }     // taken in an earlier round
             else atomicMin(&owner[r], draw);
         }

@@ -534,7 +534,7 @@ def second_pass(X, centers=None, assign_in=None, scale: float = 1.0, want_assign
         if a_in.shape[0] != n:
             raise ValueError("assign_in must have one label per column")
         if K is None:
-            K = int(a_in.max()) if a_in.size else 1
+            K = max(1, int(a_in.max())) if a_in.size else 1
     if K is None:
         raise ValueError("need centers and/or assign_in")
     out = {}
