@@ -438,6 +438,11 @@ def kmeans_sparsified(X=None, K=None, **opts):
         res = second_pass(Xd, centers=C if nargout > 6 else None, assign_in=IDX, scale=scale_eps,
                           want_assign=nargout > 6, want_dist=nargout > 6, ctx=ctx)
         OUTPUT["TimeSecondPass_Overall"] = time.perf_counter() - t1
+        # the reference times its two in-core passes separately (:551, :560); here both happen in ONE streamed
+        # pass over the data, so the same wall time is reported under both names
+        OUTPUT["TimeSecondPass_Centers"] = OUTPUT["TimeSecondPass_Overall"]
+        if nargout > 6:
+            OUTPUT["TimeSecondPass_Assignments"] = OUTPUT["TimeSecondPass_Overall"]
         C2 = res["centers"]
         if C2.shape[1] < Kb:                                                          # labels never reached Kb
             C2 = np.concatenate([C2, np.zeros((p, Kb - C2.shape[1]))], axis=1)
@@ -452,6 +457,7 @@ def kmeans_sparsified(X=None, K=None, **opts):
                     # the reference sums the ONE-pass `distances` here (not distances_twoPass), :567
                     SUMD2[ki] = np.sum(distances[IDX2 == ki + 1] ** 2)
                 two.append(SUMD2)
+                OUTPUT["TimeSecondPass_SUMD"] = 0.0
     if not o["ColumnSamples"]:                                                        # :586-605
         C = C.T
         if two is not None:
