@@ -136,6 +136,15 @@ int  skm_dataset_create_csc(skm_ctx *ctx, int64_t p, int64_t n,
                             const void *jc, int jc_type, const void *ir, int ir_type,
                             const void *val, int val_type, int store_dtype, int on_device,
                             skm_dataset **out);
+/* In-place production of an SKM_F32 dataset: allocate the device CSC arrays (int64 colptr[n+1], int32 rowidx[nnz],
+ * float val[nnz]), let the caller's own kernels fill them (skm_dataset_csc_ptrs returns the device pointers), then
+ * skm_dataset_commit validates them (sorted rows in range, colptr[n] == nnz) and builds the streamed images.  A
+ * shard that fills most of the HBM never exists twice this way (skm_dataset_create_csc with on_device copies). */
+int  skm_dataset_alloc_csc(skm_ctx *ctx, int64_t p, int64_t n, int64_t nnz, skm_dataset **out);
+int  skm_dataset_csc_ptrs(skm_dataset *ds, void **colptr, void **rowidx, void **val);
+int  skm_dataset_commit(skm_dataset *ds);
+/* min(X(:)) and max(X(:)) over all p*n elements, implicit zeros included (Start='uniform', kmeans_sparsified.m:388-390). */
+int  skm_dataset_minmax(skm_dataset *ds, double *mn, double *mx);
 void skm_dataset_destroy(skm_dataset *ds);
 int  skm_dataset_get_info(const skm_dataset *ds, skm_dataset_info *info);
 /* Verification / statistics of the streamed (SELL-32) image the fast assignment kernel reads.
@@ -277,6 +286,11 @@ int   skm_second_pass(skm_ctx *ctx, int64_t p, int64_t n, const void *x, int x_t
  * the local columns. */
 int   skm_kpp_update(skm_dataset *ds, const double *center /* host p */, int has_gamma,
                      double gamma, int first, double *sum_d2);
+/* Same for the gamma-less call of private/Arthur_initialization.m:26 (unbiasedInitialization = false): the
+ * chosen centres stay SPARSE there, so findClusterAssignments takes its sparse-centres branch
+ * (private/findClusterAssignments.m:70-74): the sum runs over supp(X(:,j)) /\ supp(center) only -- exact zeros
+ * of `center` are structural zeros. */
+int   skm_kpp_update_sparse(skm_dataset *ds, const double *center /* host p */, int first, double *sum_d2);
 /* Smallest local column index j with cumsum(mind^2)[j] > target (clamped to n-1). */
 int   skm_kpp_pick(skm_dataset *ds, double target, int64_t *j);
 int   skm_kpp_get_mindist(skm_dataset *ds, double *mind /* host n */);

@@ -63,6 +63,10 @@ SIGNATURES = {
     "skm_hadamard": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "skm_dataset_create_csc": (_int, [_vp, _i64, _i64, _vp, _int, _vp, _int, _vp, _int, _int, _int,
                                       C.POINTER(_vp)]),
+    "skm_dataset_alloc_csc": (_int, [_vp, _i64, _i64, _i64, C.POINTER(_vp)]),
+    "skm_dataset_csc_ptrs": (_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "skm_dataset_commit": (_int, [_vp]),
+    "skm_dataset_minmax": (_int, [_vp, C.POINTER(_dbl), C.POINTER(_dbl)]),
     "skm_dataset_destroy": (None, [_vp]),
     "skm_dataset_get_info": (_int, [_vp, C.POINTER(DatasetInfo)]),
     "skm_dataset_get_column": (_int, [_vp, _i64, _vp]),
@@ -97,6 +101,7 @@ SIGNATURES = {
     "skm_second_pass": (_int, [_vp, _i64, _i64, _vp, _int, _int, _dbl, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64,
                                C.POINTER(_i64)]),
     "skm_kpp_update": (_int, [_vp, _vp, _int, _dbl, _int, C.POINTER(_dbl)]),
+    "skm_kpp_update_sparse": (_int, [_vp, _vp, _int, C.POINTER(_dbl)]),
     "skm_kpp_pick": (_int, [_vp, _dbl, C.POINTER(_i64)]),
     "skm_kpp_get_mindist": (_int, [_vp, _vp]),
     "skm_mix_hadamard": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _int, _vp]),

@@ -300,6 +300,108 @@ extern "C" int skm_dataset_create_csc(skm_ctx *ctx, int64_t p, int64_t n, const 
     return SKM_OK;
 }
 
+// ---- in-place production: the caller (a generator or a preconditioning kernel of its own) writes the CSC arrays
+// straight into the dataset's buffers, so a shard that fills most of the HBM never exists twice ----
+extern "C" int skm_dataset_alloc_csc(skm_ctx *ctx, int64_t p, int64_t n, int64_t nnz, skm_dataset **out)
+{
+    SKM_TRY(enter(ctx));
+    SKM_REQUIRE(out, "out is NULL");
+    *out = nullptr;
+    SKM_REQUIRE(p >= 0 && n >= 0 && nnz >= 0, "negative dimensions");
+    SKM_REQUIRE(p < 2147483647LL, "p must be below 2^31-1");
+    skm_dataset *ds = new (std::nothrow) skm_dataset();
+    if (!ds) { skm_set_error("out of host memory"); return SKM_ERR_NOMEM; }
+    memset(ds, 0, sizeof *ds);
+    ds->ctx = ctx; ds->p = p; ds->n = n; ds->nnz = nnz; ds->store_dtype = SKM_F32;
+    ds->uncommitted = true;
+    int rc = SKM_OK;
+    do {
+        if ((rc = dev_alloc((void **)&ds->colptr, sizeof(int64_t) * (n + 1), "colptr"))) break;
+        if ((rc = dev_alloc((void **)&ds->rowidx, sizeof(int32_t) * nnz, "rowidx"))) break;
+        if ((rc = dev_alloc(&ds->val, sizeof(float) * nnz, "val"))) break;
+    } while (0);
+    if (rc != SKM_OK) { skm_dataset_destroy(ds); return rc; }
+    *out = ds;
+    return SKM_OK;
+}
+
+extern "C" int skm_dataset_csc_ptrs(skm_dataset *ds, void **colptr, void **rowidx, void **val)
+{
+    SKM_REQUIRE(ds, "NULL argument");
+    if (colptr) *colptr = ds->colptr;
+    if (rowidx) *rowidx = ds->rowidx;
+    if (val) *val = ds->val;
+    return SKM_OK;
+}
+
+extern "C" int skm_dataset_commit(skm_dataset *ds)
+{
+    SKM_REQUIRE(ds, "NULL argument");
+    SKM_TRY(enter(ds->ctx));
+    if (!ds->uncommitted) { skm_set_error("skm_dataset_commit: the dataset is already committed"); return SKM_ERR_STATE; }
+    SKM_CUDA(cudaDeviceSynchronize());                     // the producer may have written on any stream
+    int64_t last = 0;
+    SKM_TRY(d2h_sync(ds->ctx, &last, ds->colptr + ds->n, sizeof last));
+    SKM_REQUIRE(last == ds->nnz, "skm_dataset_commit: colptr[n] = %lld but the dataset was allocated for %lld entries",
+                (long long)last, (long long)ds->nnz);
+    SKM_TRY(dataset_finish(ds));
+    ds->uncommitted = false;
+    return SKM_OK;
+}
+
+// min / max over ALL p*n elements of the sparse matrix (implicit zeros included), the min(X(:)) / max(X(:)) of
+// Start = 'uniform' (kmeans_sparsified.m:388-390)
+namespace {
+template <typename VT>
+__global__ void k_minmax(int64_t nnz, const VT *__restrict__ val, double *__restrict__ out /* [2] init +inf,-inf */)
+{
+    double mn = __longlong_as_double(0x7ff0000000000000LL), mx = -mn;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride) {
+        const double v = (double)val[i];
+        if (v < mn) mn = v;
+        if (v > mx) mx = v;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        // doubles of one sign order like their integer images; do the two signs separately
+        unsigned long long *o0 = (unsigned long long *)out, *o1 = o0 + 1;
+        unsigned long long old = *o0, assumed;
+        do { assumed = old; if (!(mn < __longlong_as_double((long long)assumed))) break;
+             old = atomicCAS(o0, assumed, (unsigned long long)__double_as_longlong(mn)); } while (old != assumed);
+        old = *o1;
+        do { assumed = old; if (!(mx > __longlong_as_double((long long)assumed))) break;
+             old = atomicCAS(o1, assumed, (unsigned long long)__double_as_longlong(mx)); } while (old != assumed);
+    }
+}
+}  // namespace
+
+extern "C" int skm_dataset_minmax(skm_dataset *ds, double *mn, double *mx)
+{
+    SKM_REQUIRE(ds && mn && mx, "NULL argument");
+    skm_ctx *ctx = ds->ctx;
+    SKM_TRY(enter(ctx));
+    const double inf = INFINITY;
+    double h[2] = {inf, -inf};
+    if (ds->nnz > 0) {
+        DevBuf d;
+        SKM_TRY(d.alloc(sizeof h));
+        SKM_TRY(h2d(ctx, d.ptr, h, sizeof h));
+        const int64_t blocks = std::min<int64_t>((ds->nnz + 255) / 256, (int64_t)ctx->sm_count * 8);
+        if (ds->store_dtype == SKM_F32) k_minmax<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>(ds->nnz, (const float *)ds->val, d.as<double>());
+        else k_minmax<double><<<(unsigned)blocks, 256, 0, ctx->stream>>>(ds->nnz, (const double *)ds->val, d.as<double>());
+        SKM_CHECK_LAUNCH(ctx);
+        SKM_TRY(d2h_sync(ctx, h, d.ptr, sizeof h));
+    }
+    if (ds->nnz < ds->p * ds->n) { if (!(h[0] < 0.0)) h[0] = fmin(h[0], 0.0); if (!(h[1] > 0.0)) h[1] = fmax(h[1], 0.0); }
+    *mn = h[0]; *mx = h[1];
+    return SKM_OK;
+}
+
 extern "C" int skm_dataset_get_info(const skm_dataset *ds, skm_dataset_info *info)
 {
     SKM_REQUIRE(ds && info, "NULL argument");
@@ -392,6 +494,7 @@ static int skm_lloyd_create_ex(skm_dataset *ds, int64_t K, int want_f64_dist, sk
     SKM_TRY(enter(ds->ctx));
     SKM_REQUIRE(K >= 1, "K must be >= 1");
     SKM_REQUIRE(K < (1 << 24), "K too large");
+    if (ds->uncommitted) { skm_set_error("the dataset was allocated with skm_dataset_alloc_csc but never committed"); return SKM_ERR_STATE; }
     skm_lloyd *L = new (std::nothrow) skm_lloyd();
     if (!L) { skm_set_error("out of host memory"); return SKM_ERR_NOMEM; }
     memset(L, 0, sizeof *L);
@@ -1161,8 +1264,19 @@ extern "C" int skm_dataset_from_dense_host(skm_ctx *ctx, int64_t p, int64_t p2, 
 // ---------------------------------------------------------------------------
 // k-means++
 // ---------------------------------------------------------------------------
+static int kpp_update_common(skm_dataset *ds, const double *center, int has_gamma, double gamma, int first,
+                             int masked, double *sum_d2);
 extern "C" int skm_kpp_update(skm_dataset *ds, const double *center, int has_gamma, double gamma, int first,
                               double *sum_d2)
+{
+    return kpp_update_common(ds, center, has_gamma, gamma, first, 0, sum_d2);
+}
+extern "C" int skm_kpp_update_sparse(skm_dataset *ds, const double *center, int first, double *sum_d2)
+{
+    return kpp_update_common(ds, center, 0, 0.0, first, 1, sum_d2);
+}
+static int kpp_update_common(skm_dataset *ds, const double *center, int has_gamma, double gamma, int first,
+                             int masked, double *sum_d2)
 {
     SKM_REQUIRE(ds && center, "NULL argument");
     skm_ctx *ctx = ds->ctx;
@@ -1179,7 +1293,7 @@ extern "C" int skm_kpp_update(skm_dataset *ds, const double *center, int has_gam
     DevBuf dc;
     SKM_TRY(dc.alloc(sizeof(double) * std::max<int64_t>(p, 1)));
     SKM_TRY(h2d(ctx, dc.ptr, c.data(), sizeof(double) * p));
-    SKM_TRY(skm_launch_kpp_update(ctx, ds, dc.as<double>(), first, ds->kpp_mind, nullptr));
+    SKM_TRY(skm_launch_kpp_update(ctx, ds, dc.as<double>(), first, ds->kpp_mind, masked));
     SKM_TRY(skm_launch_scan_sq(ctx, n, ds->kpp_mind, ds->kpp_cum));
     std::vector<double> bs(nb);
     SKM_TRY(d2h_sync(ctx, bs.data(), ds->kpp_cum, sizeof(double) * nb));

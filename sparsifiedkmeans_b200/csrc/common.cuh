@@ -139,6 +139,7 @@ struct skm_dataset {
     double  *kpp_mind;                  // [n]
     double  *kpp_cum;                   // [n] inclusive scan of mind^2
     int64_t  device_bytes;
+    bool     uncommitted;               // skm_dataset_alloc_csc without skm_dataset_commit yet
 };
 
 struct skm_lloyd {
@@ -292,5 +293,5 @@ int skm_launch_sample_rows(skm_ctx *ctx, int64_t p2, int64_t n, int64_t m, uint6
 
 // kpp.cu
 int skm_launch_kpp_update(skm_ctx *ctx, const skm_dataset *ds, const double *c_scaled /* dev [p] */,
-                          int first, double *mind, double *sum_out_dev);
+                          int first, double *mind, int masked = 0);
 int skm_launch_scan_sq(skm_ctx *ctx, int64_t n, const double *mind, double *cum);

@@ -12,7 +12,7 @@ namespace {
 template <typename VT>
 __global__ void k_kpp_update(int64_t n, const int64_t *__restrict__ colptr,
                              const int32_t *__restrict__ rowidx, const VT *__restrict__ val,
-                             const double *__restrict__ c, int first, double *__restrict__ mind)
+                             const double *__restrict__ c, int first, int masked, double *__restrict__ mind)
 {
     // thread per column, grid-stride.  Measured 2.3-2.4 TB/s algorithmic whatever the number of resident warps
     // (8 ... 64 per SM, tools/debug/kpp_probe.py): the walk is a dependent chain per thread (index load -> centre
@@ -24,7 +24,11 @@ __global__ void k_kpp_update(int64_t n, const int64_t *__restrict__ colptr,
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
         double s = 0.0;
         for (int64_t t = colptr[j]; t < colptr[j + 1]; ++t) {
-            const double d = __dsub_rn((double)val[t], c[rowidx[t]]);
+            const double cv = c[rowidx[t]];
+            // sparse-centre form (findClusterAssignments.m:70-74, Arthur_initialization.m:26 without gamma): the
+            // sum runs over supp(x_j) /\ supp(c) only -- X(ind,:) keeps the ascending row order
+            if (masked && cv == 0.0) continue;
+            const double d = __dsub_rn((double)val[t], cv);
             s = __dadd_rn(s, __dmul_rn(d, d));
         }
         const double d = __dsqrt_rn(s);
@@ -56,9 +60,8 @@ __global__ void k_block_sumsq(int64_t n, const double *__restrict__ mind, double
 }  // namespace
 
 int skm_launch_kpp_update(skm_ctx *ctx, const skm_dataset *ds, const double *c_scaled, int first,
-                          double *mind, double *unused)
+                          double *mind, int masked)
 {
-    (void)unused;
     if (ds->n == 0) return SKM_OK;
     int64_t blocks = (ds->n + 255) / 256;
     {
@@ -68,10 +71,10 @@ int skm_launch_kpp_update(skm_ctx *ctx, const skm_dataset *ds, const double *c_s
     }
     if (ds->store_dtype == SKM_F32)
         k_kpp_update<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>(ds->n, ds->colptr, ds->rowidx,
-                                                                      (const float *)ds->val, c_scaled, first, mind);
+                                                                      (const float *)ds->val, c_scaled, first, masked, mind);
     else
         k_kpp_update<double><<<(unsigned)blocks, 256, 0, ctx->stream>>>(ds->n, ds->colptr, ds->rowidx,
-                                                                       (const double *)ds->val, c_scaled, first, mind);
+                                                                       (const double *)ds->val, c_scaled, first, masked, mind);
     SKM_CHECK_LAUNCH(ctx);
     return SKM_OK;
 }

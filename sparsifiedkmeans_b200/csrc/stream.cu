@@ -56,12 +56,41 @@ int64_t host_index(const void *a, int type, int64_t i)
 
 }  // namespace
 
+static int step_host_impl(skm_ctx *ctx, int64_t p, int64_t n, const void *jc, int jc_type,
+                          const void *ir, int ir_type, const void *val, int val_type,
+                          const double *centers, int64_t K, int has_gamma, double gamma_dist,
+                          double gamma_update, int ml_correction, int64_t chunk_cols,
+                          double *centers_out, int32_t *assign_out, double *dist_out,
+                          skm_iter_stats *stats, skm_reduce_fn reduce, void *reduce_user);
+
 extern "C" int skm_lloyd_step_host(skm_ctx *ctx, int64_t p, int64_t n, const void *jc, int jc_type,
                                    const void *ir, int ir_type, const void *val, int val_type,
                                    const double *centers, int64_t K, int has_gamma, double gamma_dist,
                                    double gamma_update, int ml_correction, int64_t chunk_cols,
                                    double *centers_out, int32_t *assign_out, double *dist_out,
                                    skm_iter_stats *stats, skm_reduce_fn reduce, void *reduce_user)
+{
+    const int rc = step_host_impl(ctx, p, n, jc, jc_type, ir, ir_type, val, val_type, centers, K, has_gamma, gamma_dist,
+                                  gamma_update, ml_correction, chunk_cols, centers_out, assign_out, dist_out, stats, reduce,
+                                  reduce_user);
+    if (rc != SKM_OK && ctx) {
+        // an error exit may leave the H2D copy of the next chunk in flight on the copy stream, reading the
+        // caller's host buffers, and result copies pending on the compute stream: drain both before returning
+        // so that "no host pointer is retained after a call returns" also holds on failure
+        StreamCache *sc = (StreamCache *)ctx->stream_cache;
+        if (sc && sc->copy_stream) cudaStreamSynchronize(sc->copy_stream);
+        cudaStreamSynchronize(ctx->stream);
+        cudaGetLastError();
+    }
+    return rc;
+}
+
+static int step_host_impl(skm_ctx *ctx, int64_t p, int64_t n, const void *jc, int jc_type,
+                          const void *ir, int ir_type, const void *val, int val_type,
+                          const double *centers, int64_t K, int has_gamma, double gamma_dist,
+                          double gamma_update, int ml_correction, int64_t chunk_cols,
+                          double *centers_out, int32_t *assign_out, double *dist_out,
+                          skm_iter_stats *stats, skm_reduce_fn reduce, void *reduce_user)
 {
     SKM_REQUIRE(ctx && jc && centers && centers_out, "NULL argument");
     SKM_CUDA(cudaSetDevice(ctx->device));

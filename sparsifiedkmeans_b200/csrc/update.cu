@@ -287,8 +287,13 @@ __global__ void k_finalize(int64_t p, int64_t K, const double *__restrict__ part
         double nw = old;
         const double cnt = counts[k];
         if (cnt > 0.0) {
-            if (ml) nw = __ddiv_rn(__dmul_rn(gamma, S[idx]), __dadd_rn(N[idx], 1e-16));
-            else    nw = __ddiv_rn(S[idx], cnt);
+            // N (a sum of ones) is exact in fp64, also after the incremental +/- updates and the all-reduce;
+            // a cell no member touches is a structural zero: the reference's S is exactly 0 there and
+            // gamma*0/(0+1e-16) = 0.  The incremental path can leave a rounding residue in S for such a
+            // cell ((a+b)-a-b != 0), which must not be divided by 1e-16.
+            const double s = (N[idx] == 0.0) ? 0.0 : S[idx];
+            if (ml) nw = __ddiv_rn(__dmul_rn(gamma, s), __dadd_rn(N[idx], 1e-16));
+            else    nw = __ddiv_rn(s, cnt);
         }
         centers_old[idx] = old;
         centers[idx] = nw;

@@ -42,6 +42,7 @@ class CudaShardEngine:
         # both modes are per-shard decisions (each rank keeps its own sums and bounds); the all-reduce buffer
         # is a copy of the kept sums, so the collective is issued by every rank in every iteration either way
         self.L = Lloyd(ds, K, incremental=incremental, bounded=bounded)
+        self._modes = (incremental, bounded)
         self.n_local, self.p, self.K = ds.n, ds.p, int(K)
         self._ext = None
 
@@ -55,6 +56,7 @@ class CudaShardEngine:
     def set_centers(self, C): self.L.set_centers(C)
     def get_centers(self): return self.L.get_centers()
     def assign(self, gamma_dist): self.L.assign(gamma_dist)
+    def assign_sparse(self, gamma_dist): self.L.assign_sparse(gamma_dist)
     def finalize(self, gamma, ml): return self.L.finalize(gamma, ml)
     def refresh_diff(self): return self.L.refresh_diff()
     def counts(self): return self.L.counts()
@@ -70,6 +72,15 @@ class CudaShardEngine:
     # k-means++ support
     def kpp_update(self, center, gamma, first): return self.ds.kpp_update(center, gamma, first)
     def kpp_pick(self, target): return self.ds.kpp_pick(target)
+
+    def drop_centers(self, keep):
+        """EmptyAction='drop' (kmeans_sparsified.m:454-459): continue with the centres `keep` only."""
+        from .engine import Lloyd
+        cen = self.L.get_centers()[:, keep]
+        self.L.close()
+        self.K = int(len(keep))
+        self.L = Lloyd(self.ds, self.K, incremental=self._modes[0], bounded=self._modes[1])
+        self.L.set_centers(cen)
 
     def close(self):
         self.L.close()
@@ -112,15 +123,22 @@ class ShardedLloyd:
         if dist is None or dist.get_world_size(self.group) == 1:
             return obj
         box = [obj]
-        dist.broadcast_object_list(box, src=src, group=self.group)
+        # `src` is a rank of self.group; broadcast_object_list wants the global rank
+        gsrc = dist.get_global_rank(self.group, src) if self.group is not None else src
+        dist.broadcast_object_list(box, src=gsrc, group=self.group)
         return box[0]
 
     # -- one iteration ---------------------------------------------------------
-    def step(self, gamma_dist, gamma_update, ml_correction=True, empty_action="singleton"):
+    def step(self, gamma_dist, gamma_update, ml_correction=True, empty_action="singleton", centers_sparse=False):
         """K1, K2, all-reduce, K3, then the reference's EmptyAction (kmeans_sparsified.m:432-445).
+        centers_sparse: take the sparse-centres branch of the operator (findClusterAssignments.m:63-75), as the
+        reference does while the centres are stored sparse (kmeans_sparsified.m:460-464).
         Returns the IterStats of the iteration (identical on every rank)."""
         e = self.e
-        e.assign(gamma_dist)
+        if centers_sparse:
+            e.assign_sparse(gamma_dist)
+        else:
+            e.assign(gamma_dist)
         part = e.accumulate()
         self._allreduce(part)
         st = e.finalize(gamma_update, ml_correction)
@@ -145,17 +163,30 @@ class ShardedLloyd:
                     e.set_center_column(int(k), col)
                 st2 = e.refresh_diff()
                 st.dff, st.has_nan = st2.dff, st2.has_nan
-            elif action != "drop":
+            elif action == "drop":
+                # kmeans_sparsified.m:454-459: the empty centres are removed and K shrinks.  Every rank sees the same
+                # global counts, so every rank drops the same columns.
+                if not hasattr(e, "drop_centers"):
+                    raise NotImplementedError("EmptyAction='drop' needs an engine with drop_centers(keep)")
+                keep = np.flatnonzero(e.counts() > 0)
+                e.drop_centers(keep)
+            else:
                 raise ValueError("invalid EmptyAction choice")
         return st
 
     def run(self, centers, gamma_dist, gamma_update, max_iter=100, tol=1e-6, ml_correction=True,
-            empty_action="singleton"):
-        """Iterate to convergence; returns (iterations, last IterStats)."""
+            empty_action="singleton", centers_sparse=False):
+        """Iterate to convergence; returns (iterations, last IterStats).  centers_sparse=True starts in the
+        sparse-centres branch (centres that are columns of X: Start='sample' / k-means++ without denseCenters)
+        and leaves it once more than 99% of the centre entries are non-zero (kmeans_sparsified.m:460-464)."""
         self.e.set_centers(centers)
         st, its = None, 0
         for its in range(1, max_iter + 1):
-            st = self.step(gamma_dist, gamma_update, ml_correction, empty_action)
+            st = self.step(gamma_dist, gamma_update, ml_correction, empty_action, centers_sparse)
+            if centers_sparse:
+                cen = self.e.get_centers()
+                if np.count_nonzero(cen) / max(cen.size, 1) > 0.99:
+                    centers_sparse = False
             if st.dff < tol:
                 break
             if st.has_nan:

@@ -167,6 +167,38 @@ class Dataset:
         return cls(ctx, h)
 
     @classmethod
+    def alloc_csc(cls, p: int, n: int, nnz: int, ctx: Context | None = None):
+        """In-place production (skm_dataset_alloc_csc): returns (pending, colptr_ptr, rowidx_ptr, val_ptr); the
+        caller's kernels fill the device arrays (int64[n+1], int32[nnz], float32[nnz]) and then call
+        `pending.commit()` to get the Dataset."""
+        ctx = ctx or default_context()
+        h = C.c_void_p()
+        check(ctx._lib.skm_dataset_alloc_csc(ctx.handle, int(p), int(n), int(nnz), C.byref(h)))
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(ctx._lib.skm_dataset_csc_ptrs(h, C.byref(a), C.byref(b), C.byref(c)))
+
+        class _Pending:
+            def __init__(self):
+                self.h = h
+
+            def commit(self_inner):
+                if self_inner.h is None:
+                    raise RuntimeError("already committed or released")
+                hh, self_inner.h = self_inner.h, None
+                try:
+                    check(ctx._lib.skm_dataset_commit(hh))
+                except Exception:
+                    ctx._lib.skm_dataset_destroy(hh)
+                    raise
+                return cls(ctx, hh)
+
+            def release(self_inner):
+                if self_inner.h is not None:
+                    ctx._lib.skm_dataset_destroy(self_inner.h)
+                    self_inner.h = None
+        return _Pending(), int(a.value or 0), int(b.value or 0), int(c.value or 0)
+
+    @classmethod
     def from_fwht_sample(cls, p2: int, n: int, m: int, x_ptr: int, signs_ptr: int, rows_ptr: int | None,
                          ctx: Context | None = None, seed: int = 0, col0: int = 0):
         """Fused precondition + row sample on the device (skm_fwht_sample_f32): x is a dense
@@ -285,11 +317,25 @@ class Dataset:
         return out.reshape(self.n, K).T
 
     # -- k-means++ ------------------------------------------------------------
-    def kpp_update(self, center, gamma=None, first: bool = False) -> float:
+    def minmax(self) -> tuple[float, float]:
+        """min(X(:)), max(X(:)) over all p*n elements, implicit zeros included (skm_dataset_minmax)."""
+        a, b = C.c_double(), C.c_double()
+        check(self._lib.skm_dataset_minmax(self.handle, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def kpp_update(self, center, gamma=None, first: bool = False, sparse_center: bool = False) -> float:
+        """Fold the masked distance to one new centre into the running minimum; returns the local sum of
+        D^2.  sparse_center=True is the gamma-less call of Arthur_initialization.m:26, where the centre stays
+        sparse and the sum runs over supp(x) /\ supp(centre) only (findClusterAssignments.m:70-74)."""
         c = np.ascontiguousarray(center, dtype=np.float64).reshape(-1)
         if c.shape[0] != self.p:
             raise ValueError("centre must have p entries")
         tot = C.c_double()
+        if sparse_center:
+            if gamma is not None:
+                raise ValueError("the sparse-centre form has no gamma (Arthur_initialization.m:26-29)")
+            check(self._lib.skm_kpp_update_sparse(self.handle, _ptr(c), int(first), C.byref(tot)))
+            return tot.value
         check(self._lib.skm_kpp_update(self.handle, _ptr(c), int(gamma is not None),
                                        float(gamma if gamma is not None else 0.0), int(first), C.byref(tot)))
         return tot.value

@@ -7,9 +7,10 @@ Same option names, defaults and error behaviour as the reference's inputParser
 per-cluster sums and the centre update run on the GPU through libskm_b200; this file only
 sequences them the way kmeans_sparsified.m:213-607 does.
 
-Scope: the sparsified path (`Sparsify=True`) with the Hadamard sketch
-(or 'none').  The dense path (Sparsify=False), the DCT sketch, loading from disk (`DataFile`)
-are outside the hot path and raise NotImplementedError.  The two-pass outputs (`nargout` 6..9:
+Scope: the sparsified path (`Sparsify=True`) with the Hadamard sketch, the DCT
+sketch (p not a power of two, :226-231) or 'none', from memory or from a file on disk (`DataFile`, a
+memory-mapped .npy here; the reference reads -v7.3 .mat through matfile).  The dense path
+(Sparsify=False) is outside the hot path and raises NotImplementedError.  The two-pass outputs (`nargout` 6..9:
 centers_twoPass, assignments_twoPass, distances_twoPass, SUMD_twoPass; kmeans_sparsified.m:525-571)
 come from one streamed pass over the original data (skm_second_pass).
 
@@ -40,6 +41,15 @@ _DEFAULTS = dict(
 )
 _EXTRA = dict(Seed=None, Signs=None, SampleRows=None, StartIndices=None, Store="f32", Device=0,
               MixDtype="f64", nargout=5, Context=None, Pipeline="auto", IncrementalUpdate=True, BoundedAssign=True)
+
+
+class SkmWarning(UserWarning):
+    """warning('id','msg') of the reference; `identifier` carries the id (e.g. kmeans_sparsified:dropCluster,
+    kmeans_sparsified.m:433)."""
+
+    def __init__(self, msg, identifier=""):
+        super().__init__(msg)
+        self.identifier = identifier
 
 
 class KMeansError(RuntimeError):
@@ -110,7 +120,9 @@ def Arthur_initialization(ds: Dataset, K: int, gamma, rng=None, first=None, unif
 
     chosen = [int(first) if first is not None else int(rng.integers(n))]           # :35
     for _ in range(K - 1):
-        tot = ds.kpp_update(ds.get_column(chosen[-1]), gamma, first=(len(chosen) == 1))
+        # with gamma the reference densifies the centres (full(ref), :28); without, they stay sparse and
+        # findClusterAssignments takes its sparse-centres branch (:26, findClusterAssignments.m:70-74)
+        tot = ds.kpp_update(ds.get_column(chosen[-1]), gamma, first=(len(chosen) == 1), sparse_center=gamma is None)
         if not (tot > 0):                                                          # :44-48 all-zero distances
             pick = lambda: min(int(draw() * n), n - 1)                              # noqa: E731
         else:
@@ -202,11 +214,21 @@ def kmeans_sparsified(X=None, K=None, **opts):
     if isinstance(sketch, str) and sketch.lower() == "auto":
         sketch = "Hadamard" if p == _nextpow2_size(p) else "DCT"
         OUTPUT["SketchType"] = sketch
+    H_user = Ht_user = None
+    if isinstance(sketch, (list, tuple)):                                             # :263-270 cell of two handles
+        if len(sketch) == 2 and callable(sketch[0]) and callable(sketch[1]):
+            H_user, Ht_user = sketch
+            sketch = "function handles"
+        else:
+            raise KMeansError("If SketchType is a cell, then both entries should be function handles for forward "
+                              "and adjoint transform")
     if not isinstance(sketch, str):
-        raise NotImplementedError("function-handle sketches are outside the hot path")
+        raise KMeansError('bad type for "SketchType"')
     sk = sketch.lower()
     p2 = p
-    if sk == "hadamard":
+    if H_user is not None:
+        sk = "handles"
+    elif sk == "hadamard":
         p2 = _nextpow2_size(p)
         OUTPUT["SlowHadamard"] = False
     elif sk == "dct":
@@ -214,7 +236,7 @@ def kmeans_sparsified(X=None, K=None, **opts):
             raise NotImplementedError("the DCT sketch is applied as a dense p x p product; p <= 32768")
     elif sk not in ("nothing", "none"):
         raise KMeansError('bad type for "SketchType"')
-    if sk in ("hadamard", "dct"):
+    if sk in ("hadamard", "dct", "handles"):
         d = o["Signs"]
         if d is None:
             d = np.ones(p2) if o["FORCE_BUG"] else np.sign(rng.standard_normal(p2))    # :283-287
@@ -229,6 +251,8 @@ def kmeans_sparsified(X=None, K=None, **opts):
     def mix(A):                                                                       # :295
         if d is None:
             return np.asarray(A, dtype=np.float64)
+        if sk == "handles":                                                           # user transform on the host
+            return np.asarray(H_user(d.reshape(-1, 1) * np.asarray(A, dtype=np.float64)), dtype=np.float64)
         if sk == "dct":
             from .engine import dct_mix
             return dct_mix(A, d, False, ctx)                                          # H = dct, :257
@@ -238,6 +262,8 @@ def kmeans_sparsified(X=None, K=None, **opts):
     def unmix(C):                                                                     # :296
         if d is None:
             return C
+        if sk == "handles":
+            return d.reshape(-1, 1) * np.asarray(Ht_user(C), dtype=np.float64)
         if sk == "dct":
             from .engine import dct_mix
             return dct_mix(C, d, True, ctx)                                           # Ht = idct, :258
@@ -251,9 +277,11 @@ def kmeans_sparsified(X=None, K=None, **opts):
     if pipeline == "auto":
         # all-GPU precondition + sample when nothing pins the random rows and the sizes allow it
         ok = (o["SampleRows"] is None and 32 <= p2 <= 32768) if sk == "hadamard" else (sk == "dct")
+        if sk == "handles":
+            ok = False                                   # a user transform runs on the host
         pipeline = "device" if (d is not None and ok and o["Store"] == "f32") else "host"
     if pipeline == "device":
-        if d is None or (sk == "hadamard" and o["SampleRows"] is not None):
+        if d is None or sk == "handles" or (sk == "hadamard" and o["SampleRows"] is not None):
             raise ValueError("Pipeline='device' needs the Hadamard sketch with on-device row sampling, or the DCT sketch")
         t1 = time.perf_counter()
         seed = int(rng.integers(0, 2 ** 63 - 1))
@@ -308,9 +336,7 @@ def kmeans_sparsified(X=None, K=None, **opts):
                     centers = columns(ind)
                     centers_sparse = True
                 elif s == "uniform":
-                    if Xs is None:
-                        raise NotImplementedError("Start='uniform' needs Pipeline='host'")
-                    mn, mx = float(Xs.min()), float(Xs.max())
+                    mn, mx = (float(Xs.min()), float(Xs.max())) if Xs is not None else ds.minmax()   # :388-389
                     centers = (mx - mn) * rng.random((p2, K)) - mn                     # :390 (sign as in the reference)
                 elif s in ("arthur", "++", "kmeans++", "k-means++", "k-means-++"):
                     if o["StartIndices"] is not None:
@@ -327,7 +353,8 @@ def kmeans_sparsified(X=None, K=None, **opts):
                     st = st.T
                 centers = mix(st)                                                     # :401-405
                 if R > 1:
-                    warnings.warn("initialization is specified, so running more than 1 replicate is not helpful")
+                    warnings.warn(SkmWarning("initialization is specified, so running more than 1 replicate is not helpful",
+                                             "kmeans_sparsified:deterministicCenters"))
             if o["denseCenters"]:
                 centers_sparse = False                                                # :412-414
             OUTPUT["replicateTimesJustInitialization"][trial] = time.perf_counter() - t1
@@ -358,7 +385,7 @@ def kmeans_sparsified(X=None, K=None, **opts):
                 stt = L.finalize(gamma, ml)                                           # :447-450
                 if stt.n_empty:
                     action = str(o["EmptyAction"]).lower()
-                    warnings.warn("cluster has lost all its members")                 # :433
+                    warnings.warn(SkmWarning("cluster has lost all its members", "kmeans_sparsified:dropCluster"))   # :433
                     counts = L.counts()
                     empty = np.flatnonzero(counts == 0)
                     if action == "singleton":                                         # :434-437
