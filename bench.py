@@ -7,13 +7,21 @@
 A step is ONE Lloyd iteration over the resident sparsified matrix: K1 masked distance +
 argmin (+ fp64 re-evaluation of uncertified columns), K2 per-cluster sums/counts, (N>1: one
 NCCL all-reduce of the partials), K3 centre finalisation, and the read-back of the iteration
-statistics the host needs for the stop rule.  Workload at N=1: BASELINE.json configs[1]
+statistics the host needs for the stop rule.  Headline workload: BASELINE.json configs[1]
 (n=1e7, p=784, K=10, 10% nnz => 78 stored entries per point, fp32); for N>1 every rank holds
 a shard of that shape (weak scaling, columns sharded by rank).  Inputs are synthetic, generated
-directly in sparsified form on the device and are far larger than L2,
-so no explicit flush is needed between iterations.
+directly in sparsified form on the device, a pure function of (seed,
+global column) so every GPU count sees the same matrix, and are far larger than L2, so no
+explicit flush is needed between iterations.
 
-Prints ONE JSON line (rank 0).
+The ONE JSON line (rank 0) carries, beside the contract keys for the headline workload:
+  parity          the headline run's assignments / centres against the compiled reference on every rank
+  config3         the north-star shape (p=1024, K=64, 51/col, 1.25e7 columns per GPU): iteration, K1 roofline
+                  with the DRAM traffic summed over all launches of the pass, parity on every rank
+  unstructured    the near-tie workload of SURVEY.md 8d at the headline shape: fp64 re-evaluations and their cost
+  strong_scaling  n = 1e8, K = 64 split over the N GPUs (N = 1: the whole matrix on one GPU)
+  trajectory      k-means++ start -> convergence, default iteration vs bounded assignment + incremental update,
+                  assignments compared iteration by iteration
 """
 from __future__ import annotations
 
@@ -42,10 +50,12 @@ CONFIGS = {
     "published_mnist3": dict(n=9_631_605, p=784, K=3, m=39,
                              label="reference's published run shape: n=9,631,605 p=784 k=3 5% nnz (39/col), synthetic values"),
     "tiny": dict(n=200_000, p=784, K=10, m=78, label="tiny debug shape"),
+    "tiny3": dict(n=200_000, p=1024, K=64, m=51, label="tiny debug shape (config 3)"),
 }
 METRIC = "points assigned/sec per Lloyd iter"
 UNIT = "points/s"
 GEN_CHUNK = 500_000
+STRONG_TOTAL = 100_000_000
 
 
 def _peaks():
@@ -57,32 +67,91 @@ def _peaks():
 
 
 # --------------------------------------------------------------------------- data
-def gen_shard_device(dev, n, p, m, K, col0, seed=2024):
-    """Sparsified mixture shard generated on the GPU: columns [col0, col0+n).  Returns torch
-    tensors (colptr int64 [n+1], rowidx int32 [n*m], val float32 [n*m]) and (mu, start)."""
+def _view(ptr, count, typestr, dev):
+    import torch
+
+    class _Raw:
+        __cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False),
+                                    "version": 2, "strides": None}
+    return torch.as_tensor(_Raw(), device=dev)
+
+
+def model_centres(p, K, kind):
+    """(mu, start) of the synthetic workload in the unscaled domain."""
     import torch
     g0 = torch.Generator(device="cpu").manual_seed(1234)
     mu = torch.randn(p, K, generator=g0, dtype=torch.float64)
     g1 = torch.Generator(device="cpu").manual_seed(99)
-    start = mu + 0.05 * torch.randn(p, K, generator=g1, dtype=torch.float64)
+    noise = torch.randn(p, K, generator=g1, dtype=torch.float64)
+    if kind == "unstructured":
+        return mu, 0.1 * noise                              # centres 0.1*N(0,1): near-ties everywhere
+    return mu, mu + 0.05 * noise
+
+
+def fill_shard(ctx, dev, colptr, rowidx, val, n, p, m, K, col0, kind="mixture", seed=2024):
+    """Write the sparsified shard [col0, col0+n) into the given device arrays (torch views).
+    Rows: the library's Philox sampler (m distinct ascending rows, a function of (seed, global column));
+    values: mixture (mu[row, j mod K] + 0.1 N(0,1)) * p/m, or unstructured N(0,1) * p/m, rounded to fp32."""
+    import torch
+    from sparsifiedkmeans_b200.engine import sample_rows, sample_rows_general
+    rp = rowidx.data_ptr()
+    pow2 = p >= 32 and (p & (p - 1)) == 0
+    step = 5_000_000
+    for c0 in range(0, n, step):
+        c = min(step, n - c0)
+        if pow2:
+            sample_rows(p, c, m, seed, col0 + c0, rp + 4 * c0 * m, ctx)
+        else:
+            sample_rows_general(p, c, m, seed, col0 + c0, rp + 4 * c0 * m, ctx)
+    ctx.synchronize()
+    mu, start = model_centres(p, K, kind)
     mu_d = mu.to(dev, torch.float32)
-    rowidx = torch.empty(n * m, dtype=torch.int32, device=dev)
-    val = torch.empty(n * m, dtype=torch.float32, device=dev)
     scale = float(p) / float(m)
     for c0 in range(0, n, GEN_CHUNK):
         c = min(GEN_CHUNK, n - c0)
-        g = torch.Generator(device=dev).manual_seed(seed + (col0 + c0) // GEN_CHUNK)
-        keys = torch.rand(c, p, generator=g, device=dev)
-        rows = keys.topk(m, dim=1, largest=False).indices
-        del keys
-        rows, _ = rows.sort(dim=1)
-        lab = (torch.arange(col0 + c0, col0 + c0 + c, device=dev) % K)
-        v = mu_d[rows, lab[:, None]] + 0.1 * torch.randn(c, m, generator=g, device=dev)
-        rowidx[c0 * m:(c0 + c) * m] = rows.reshape(-1).to(torch.int32)
+        g = torch.Generator(device=dev).manual_seed(seed * 1_000_003 + (col0 + c0) // GEN_CHUNK)
+        if kind == "unstructured":
+            v = torch.randn(c, m, generator=g, device=dev)
+        else:
+            rows = rowidx[c0 * m:(c0 + c) * m].view(c, m).long()
+            lab = (torch.arange(col0 + c0, col0 + c0 + c, device=dev) % K)
+            v = mu_d[rows, lab[:, None]] + 0.1 * torch.randn(c, m, generator=g, device=dev)
+            del rows, lab
         val[c0 * m:(c0 + c) * m] = (v * scale).reshape(-1)
-        del rows, v, lab
-    colptr = torch.arange(n + 1, dtype=torch.int64, device=dev) * m
-    return colptr, rowidx, val, mu.numpy(), start.numpy()
+        del v
+    colptr.copy_(torch.arange(n + 1, dtype=torch.int64, device=dev) * m)
+    torch.cuda.synchronize()
+    return mu.numpy(), start.numpy()
+
+
+def gen_shard_device(dev, n, p, m, K, col0, seed=2024, kind="mixture", ctx=None):
+    """The shard as plain torch tensors (colptr int64 [n+1], rowidx int32 [n*m], val float32 [n*m]) and (mu, start)."""
+    import torch
+    from sparsifiedkmeans_b200 import default_context
+    ctx = ctx or default_context(dev.index or 0)
+    colptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    rowidx = torch.empty(n * m, dtype=torch.int32, device=dev)
+    val = torch.empty(n * m, dtype=torch.float32, device=dev)
+    mu, start = fill_shard(ctx, dev, colptr, rowidx, val, n, p, m, K, col0, kind, seed)
+    return colptr, rowidx, val, mu, start
+
+
+def gen_dataset(ctx, dev, n, p, m, K, col0, kind="mixture", seed=2024):
+    """Sparsified shard [col0, col0+n) generated on the GPU straight into the dataset's own buffers
+    (skm_dataset_alloc_csc / commit, so a shard that fills most of the HBM never exists twice).
+    Returns (Dataset, (colptr, rowidx, val) torch views of its CSC arrays, mu, start)."""
+    from sparsifiedkmeans_b200 import Dataset
+    pend, cp, rp, vp = Dataset.alloc_csc(p, n, n * m, ctx=ctx)
+    try:
+        colptr = _view(cp, n + 1, "<i8", dev)
+        rowidx = _view(rp, n * m, "<i4", dev)
+        val = _view(vp, n * m, "<f4", dev)
+        mu, start = fill_shard(ctx, dev, colptr, rowidx, val, n, p, m, K, col0, kind, seed)
+        ds = pend.commit()
+    except Exception:
+        pend.release()
+        raise
+    return ds, (colptr, rowidx, val), mu, start
 
 
 def gen_sample_cpu(n, p, m, K, seed=2024):
@@ -142,9 +211,9 @@ class CpuLloyd:
         else:
             a, dmin = self.cport.assign(self.p, nn, jci, iri, xs, cscaled)
         _, S, N, counts = self.cport.centroid_update(self.p, nn, self.K, jci, iri, xs, a, gamma, centers, True)
-        return S, N, counts, float(np.sum(dmin * dmin))
+        return S, N, counts, float(np.sum(dmin * dmin)), a
 
-    def iterate(self, centers, gamma):
+    def iterate(self, centers, gamma, want_assign=False):
         from concurrent.futures import ThreadPoolExecutor
         cscaled = centers / gamma
         with ThreadPoolExecutor(self.threads) as ex:
@@ -155,6 +224,8 @@ class CpuLloyd:
         new = centers.copy()
         ok = counts > 0
         new[:, ok] = gamma * S[:, ok] / (N[:, ok] + 1e-16)
+        if want_assign:
+            return new, np.concatenate([pt[4] for pt in parts])
         return new
 
 
@@ -260,97 +331,302 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- GPU arm
-def run_ours(args):
+class Rig:
+    """Per-process plumbing shared by the legs: device, library context, stream view, collectives."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        from sparsifiedkmeans_b200 import Context
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback "
+                             "(use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device(f"cuda:{self.local}")
+        if self.world > 1:
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+                os.environ["NCCL_DEBUG"] = "WARN"           # keep stdout to the one JSON line
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.ctx = Context(self.local)
+        self.ext = torch.cuda.ExternalStream(self.ctx.stream, device=self.dev)
+        self.ev0 = torch.cuda.Event(enable_timing=True)
+        self.ev1 = torch.cuda.Event(enable_timing=True)
+
+    def fence(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce_partials(self, Lo):
+        if self.world > 1:
+            with self.torch.cuda.stream(self.ext):
+                self.dist.all_reduce(Lo.partials_tensor())
+
+    def max_over_ranks(self, v):
+        t = self.torch.tensor([float(v)], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, v):
+        t = self.torch.tensor([float(v)], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def timed(self, fn, steps):
+        """ms per step of `fn`, CUDA events on the library stream, fenced on both sides, max over ranks."""
+        self.fence()
+        self.ev0.record(self.ext)
+        last = None
+        for _ in range(steps):
+            last = fn()
+        self.ev1.record(self.ext)
+        self.fence()
+        return self.max_over_ranks(self.ev0.elapsed_time(self.ev1)) / steps, last
+
+
+def k1_roofline(rig, L, tim, n, m, steps):
+    """Roofline of the dominant kernel (K1: fused distance + argmin) from the library's own CUDA-event timing
+    around the whole assignment pass (all launches of a K-chunked plan)."""
+    peak, peak_src = _peaks()
+    k1_ms, k1_groups = tim["assign"]
+    k1_ms_avg = k1_ms / max(k1_groups, 1)
+    alg_bytes = n * (m * 8 + 8)                         # SURVEY.md 8d: m*(4+4) + 4 + 4 per point
+    achieved = alg_bytes / (k1_ms_avg * 1e-3) / 1e9 if k1_ms_avg > 0 else None
+    name = L.kernel_name
+    traffic, launches_per_pass = None, None
+    try:   # DRAM bytes per pass from the committed ncu --set full captures: per-point figure of ONE launch x launches x points
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            ent = json.load(f)[name]
+        launches_per_pass = int(ent.get("launches_per_pass", 1))
+        traffic = ent["dram_bytes_per_point"] * launches_per_pass * n
+    except Exception:
+        pass
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak if achieved else None,
+            "traffic": traffic, "traffic_note": "ncu dram bytes of one launch x launches per pass x points",
+            "kernel": name, "launches_per_pass": launches_per_pass, "ms_per_launch": k1_ms_avg,
+            "ms_per_pass": k1_ms_avg, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+            "step_breakdown_ms": {k: v[0] / steps for k, v in tim.items() if v[1]}}
+
+
+def parity_block(rig, L, views, n_local, p, m, K, gamma, n_check=100_000):
+    """The last iteration of the run against the compiled reference (oracle/_ref), on EVERY rank: the first
+    n_check local columns are copied to the host with their assignments, the reference's own
+    SparseMatrixMinusCluster + MATLAB min are run on them against the centres the GPU assigned against, and the
+    assignments must be identical.  Then one extra sharded Lloyd step over just those columns (all ranks, one
+    all-reduce) is compared with the oracle's centre update over the union of the slices (<= 1e-6 relative)."""
     import torch
-    import torch.distributed as dist
-    from sparsifiedkmeans_b200 import Context, Dataset, Lloyd
-    from sparsifiedkmeans_b200._lib import SKM_F32, SKM_I32, SKM_I64
+    from oracle import cport, refmex
+    from sparsifiedkmeans_b200 import Dataset, Lloyd
+    colptr, rowidx, val = views
+    nc = int(min(n_check, n_local))
+    jc = colptr[:nc + 1].cpu().numpy().astype(np.uint64)
+    ir = rowidx[:nc * m].cpu().numpy().astype(np.uint64)
+    x = val[:nc * m].cpu().numpy().astype(np.float64)
+    c_used = L.get_centers_old()                           # the centres the last K1 pass assigned against
+    a_gpu, _ = L.assignments(want_dist=False)
+    use_ref = refmex.ref_available()
+    if use_ref:
+        D = refmex.SparseMatrixMinusCluster(p, nc, jc, ir, x, c_used / gamma)
+        _, a_ref = cport.colmin(D)
+    else:
+        a_ref, _ = cport.assign(p, nc, jc.astype(np.int64), ir.astype(np.int64), x, c_used / gamma)
+    mism = int(np.count_nonzero(a_ref != a_gpu[:nc]))
+    total_mism = int(rig.sum_over_ranks(mism))
+    # sharded step on the slices only: CUDA + all-reduce against the oracle on the union
+    ds2 = Dataset.from_csc(p, nc, jc.astype(np.int64), ir.astype(np.int32), x.astype(np.float32), store="f32", ctx=rig.ctx)
+    L2 = Lloyd(ds2, K)
+    L2.set_centers(c_used)
+    L2.step(gamma, gamma, True, reduce=rig.reduce_partials)
+    got = L2.get_centers()
+    L2.close(); ds2.close()
+    err = None
+    if rig.world > 1:
+        parts = [None] * rig.world
+        rig.dist.all_gather_object(parts, (ir, x))
+    else:
+        parts = [(ir, x)]
+    if rig.rank == 0:
+        ir_all = np.concatenate([q[0] for q in parts]).astype(np.int64)
+        x_all = np.concatenate([q[1] for q in parts])
+        n_all = nc * rig.world
+        jc_all = np.arange(n_all + 1, dtype=np.int64) * m
+        a_all, _ = cport.assign(p, n_all, jc_all, ir_all, x_all, c_used / gamma)
+        want, _, _, _ = cport.centroid_update(p, n_all, K, jc_all, ir_all, x_all, a_all, gamma, c_used, True)
+        err = float(np.max(np.abs(got - want)) / max(np.max(np.abs(want)), 1e-300))
+    return {"ranks": rig.world, "columns_checked": nc * rig.world, "assignment_mismatches": total_mism,
+            "centroid_rel_err": err, "centroid_columns": nc * rig.world,
+            "checker": "oracle/_ref (compiled reference SparseMatrixMinusCluster.c) + oracle min / centre update"
+                       if use_ref else "oracle port (reference library absent)"}
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback "
-                         "(use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device(f"cuda:{local}")
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-            os.environ["NCCL_DEBUG"] = "WARN"           # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=dev)
-    cfg = CONFIGS[args.config]
-    n, p, K, m = (args.n or cfg["n"]), cfg["p"], cfg["K"], cfg["m"]
+
+def run_lloyd(rig, cfg, n, kind, steps, warmup, want_parity=True, want_modes=False, keep=False):
+    """One workload: generate the shard, warm up, time `steps` iterations (default mode), K1 roofline, parity."""
+    from sparsifiedkmeans_b200 import Lloyd
+    p, K, m = cfg["p"], cfg["K"], cfg["m"]
     gamma = m / p
-
-    ctx = Context(local)
-    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
-    colptr, rowidx, val, mu, start = gen_shard_device(dev, n, p, m, K, col0=rank * n)
-    torch.cuda.synchronize()
-
-    # pinned host copy for the end-to-end leg (made before the device tensors are released)
-    # columns per end-to-end step: everything on one GPU; under torchrun a bounded sample per rank, so that the
-    # pinned host copies of all ranks together stay well inside the box's memory (throughput does not depend on it)
-    n_e2e = min(n, args.e2e_n) if args.e2e_n else (n if world == 1 else min(n, 4_000_000))
-    h_colptr = torch.empty(n_e2e + 1, dtype=torch.int64, pin_memory=True)
-    h_rowidx = torch.empty(n_e2e * m, dtype=torch.int32, pin_memory=True)
-    h_val = torch.empty(n_e2e * m, dtype=torch.float32, pin_memory=True)
-    h_colptr.copy_(colptr[:n_e2e + 1]); h_rowidx.copy_(rowidx[:n_e2e * m]); h_val.copy_(val[:n_e2e * m])
-    torch.cuda.synchronize()
-
-    ds = Dataset.from_device_csc(p, n, colptr.data_ptr(), SKM_I64, rowidx.data_ptr(), SKM_I32,
-                                 val.data_ptr(), SKM_F32, store="f32", ctx=ctx)
-    del colptr, rowidx, val
-    torch.cuda.empty_cache()
+    t_g0 = time.perf_counter()
+    ds, views, mu, start = gen_dataset(rig.ctx, rig.dev, n, p, m, K, col0=rig.rank * n, kind=kind)
+    t_gen = time.perf_counter() - t_g0
     L = Lloyd(ds, K)
     L.set_centers(start)
 
-    def reduce_partials(Lo):
-        if world > 1:
-            with torch.cuda.stream(ext):
-                dist.all_reduce(Lo.partials_tensor())
-
     def step():
-        return L.step(gamma, gamma, True, reduce=reduce_partials)
+        return L.step(gamma, gamma, True, reduce=rig.reduce_partials)
 
-    for _ in range(max(args.warmup, 3)):
+    rech = []
+    for _ in range(max(warmup, 3)):
         st = step()
-    ctx.synchronize()
-    ctx.timing_enable(True)
-    ctx.timing_read()
-
-    def fence():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local) if rank == 0 else None
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = ctx.launch_count
-    fence()
+        rech.append(int(st.n_rechecked))
+    rig.ctx.synchronize()
+    rig.ctx.timing_enable(True)
+    rig.ctx.timing_read()
+    launches0 = rig.ctx.launch_count
     t_w0 = time.perf_counter()
-    ev0.record(ext)
-    for _ in range(args.steps):
-        st = step()
-    ev1.record(ext)
-    fence()
+    ms_step, st = rig.timed(step, steps)
     t_w1 = time.perf_counter()
-    ms_total = ev0.elapsed_time(ev1)
-    launches = ctx.launch_count - launches0
-    tim = ctx.timing_read()
-    ctx.timing_enable(False)
-    clocks = sampler.stop(t_w0, t_w1) if sampler else None
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    value = world * n / (ms_step * 1e-3)
+    launches = rig.ctx.launch_count - launches0
+    tim = rig.ctx.timing_read()
+    rig.ctx.timing_enable(False)
+    out = {"workload": cfg["label"] if kind == "mixture" else cfg["label"].replace("Gaussian mixture", "UNSTRUCTURED N(0,1) values, centres 0.1 N(0,1) (near-ties)"),
+           "n_per_gpu": n, "p": p, "k": K, "nnz_per_col": m, "ms_per_step": ms_step,
+           "value": rig.world * n / (ms_step * 1e-3), "unit": UNIT, "steps": steps,
+           "roofline": k1_roofline(rig, L, tim, n, m, steps), "gpu_launches": int(launches),
+           "rechecked_last_step": int(st.n_rechecked), "rechecked_warmup_steps": rech,
+           "recheck_ms_per_step": tim["recheck"][0] / steps, "objective": st.objective,
+           "dataset_gb": ds.device_bytes / 1e9, "generate_and_build_s": t_gen}
+    if want_parity:
+        try:
+            out["parity"] = parity_block(rig, L, views, n, p, m, K, gamma)
+        except Exception as e:
+            out["parity"] = {"error": repr(e)}
+    extra = dict(L=L, ds=ds, views=views, start=start, mu=mu, gamma=gamma, window=(t_w0, t_w1), tim=tim, st=st)
+    if not keep:
+        L.close(); ds.close()
+        extra = dict(window=(t_w0, t_w1), tim=tim, st=st, start=start, gamma=gamma)
+    return out, extra
 
-    # ---- roofline of the dominant kernel (K1: fused distance + argmin) ----
-    peak, peak_src = _peaks()
+
+def modes_at_fixed_point(rig, L, n, m, steps, gamma):
+    """The same iteration with the opt-in modes at the synthetic mixture's fixed point (steady-state cost)."""
+    alg_bytes = n * (m * 8 + 8)
+
+    def timed_mode(incr, bounded):
+        try:
+            L.set_update_mode(incr)
+            L.set_assign_mode(bounded)
+            step = lambda: L.step(gamma, gamma, True, reduce=rig.reduce_partials)      # noqa: E731
+            for _ in range(3):
+                step()
+            rig.ctx.timing_enable(True); rig.ctx.timing_read()
+            ms_i, sti = rig.timed(step, steps)
+            tm = rig.ctx.timing_read(); rig.ctx.timing_enable(False)
+            kind, nch = L.last_update()
+            k1i = tm["assign"][0] / steps
+            return {"ms_per_step": ms_i, "value": rig.world * n / (ms_i * 1e-3), "unit": UNIT, "last_update": kind,
+                    "columns_moved_last_step": nch, "columns_reevaluated_last_step": L.last_assign_flagged(),
+                    "assign_ms": k1i, "assign_algorithmic_GBps": alg_bytes / (k1i * 1e-3) / 1e9 if k1i else None,
+                    "objective": sti.objective}
+        except Exception as e:                              # never let the extra legs break the contract line
+            return {"error": repr(e)}
+        finally:
+            L.set_update_mode(False)
+            L.set_assign_mode(False)
+    incremental = timed_mode(True, False)
+    incremental["note"] = "opt-in skm_lloyd_set_update_mode(1) at the synthetic mixture's fixed point (steady state)"
+    bounded = timed_mode(True, True)
+    bounded["note"] = "opt-in skm_lloyd_set_assign_mode(1) + set_update_mode(1), same fixed point; see `trajectory` for whole runs"
+    return incremental, bounded
+
+
+def trajectory_leg(rig, ds, cfg, n, max_iter=40, tol=1e-6, kind="mixture"):
+    """k-means++ start -> convergence (kmeans_sparsified.m:417-486 stop rule, at most max_iter iterations), run
+    twice from the same start: the default iteration (every centre for every column, sums recomputed) and the
+    stateful modes (bounded assignment + incremental update).  Per iteration: device ms, columns the bounds could
+    not keep, columns that changed cluster, and an order-independent checksum of the assignments that must agree
+    between the two runs."""
+    import torch
+    from sparsifiedkmeans_b200 import Lloyd
+    from sparsifiedkmeans_b200.distributed import CudaShardEngine, sharded_arthur_initialization
+    p, K, m = cfg["p"], cfg["K"], cfg["m"]
+    gamma = m / p
+    eng = CudaShardEngine(ds, K)
+    u = np.random.default_rng(5).random(64 * K + 64)
+    t0 = time.perf_counter()
+    idx, start = sharded_arthur_initialization(eng, K, gamma, n * rig.world, rig.rank * n, first=12345 % (n * rig.world),
+                                               uniforms=iter(u))
+    rig.torch.cuda.synchronize()
+    t_init = time.perf_counter() - t0
+    eng.close()
+    weights = None
+
+    def run(incr, bounded):
+        nonlocal weights
+        L = Lloyd(ds, K, incremental=incr, bounded=bounded)
+        L.set_centers(start)
+        a_view = _view(L._lib.skm_lloyd_assign_ptr(L.handle), n, "<i4", rig.dev)
+        if weights is None:
+            weights = (torch.arange(n, device=rig.dev, dtype=torch.int64) % 1_000_003) + 1
+        its, ms, flagged, moved, sums, objs = 0, [], [], [], [], []
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for its in range(1, max_iter + 1):
+            rig.fence()
+            ev[0].record(rig.ext)
+            st = L.step(gamma, gamma, True, reduce=rig.reduce_partials)
+            ev[1].record(rig.ext)
+            rig.fence()
+            ms.append(rig.max_over_ranks(ev[0].elapsed_time(ev[1])))
+            with torch.cuda.stream(rig.ext):
+                cs = int(((a_view.long() + 1) * weights).sum().item())
+            sums.append(cs)
+            objs.append(st.objective)
+            flagged.append(L.last_assign_flagged())
+            moved.append(L.last_update()[1])
+            if st.dff < tol or st.has_nan:
+                break
+        L.close()
+        return dict(iterations=its, ms=ms, flagged=flagged, moved=moved, sums=sums, obj=objs, dff=st.dff)
+
+    base = run(False, False)
+    fast = run(True, True)
+    k = min(base["iterations"], fast["iterations"])
+    same = sum(1 for i in range(k) if base["sums"][i] == fast["sums"][i])
+    all_same = rig.sum_over_ranks(0 if (same == k and base["iterations"] == fast["iterations"]) else 1) == 0
+    tb, tf = float(np.sum(base["ms"])), float(np.sum(fast["ms"]))
+    return {"workload": f"{kind}, p={p} k={K} {m}/col, {n} columns per GPU, k-means++ start",
+            "kmeanspp_seconds": t_init, "max_iter": max_iter, "tol": tol,
+            "default": {"iterations": base["iterations"], "total_ms": tb, "ms_per_iteration": base["ms"],
+                        "objective_last": base["obj"][-1], "dff_last": base["dff"]},
+            "bounded_incremental": {"iterations": fast["iterations"], "total_ms": tf, "ms_per_iteration": fast["ms"],
+                                    "columns_reevaluated": fast["flagged"], "columns_moved": fast["moved"],
+                                    "objective_last": fast["obj"][-1], "dff_last": fast["dff"]},
+            "speedup": tb / tf if tf > 0 else None,
+            "iterations_with_identical_assignments": same, "iterations_compared": k,
+            "identical_on_all_ranks": bool(all_same)}
+
+
+def run_ours(args):
+    rig = Rig()
+    torch, dist = rig.torch, rig.dist
+    world, rank, dev, ctx = rig.world, rig.rank, rig.dev, rig.ctx
+    cfg = CONFIGS[args.config]
+    n, p, K, m = (args.n or cfg["n"]), cfg["p"], cfg["K"], cfg["m"]
+    gamma = m / p
+    sampler = ClockSampler(rig.local) if rank == 0 else None
+
+    # ------------------------------------------------------------------ headline workload
+    main, X = run_lloyd(rig, cfg, n, "mixture", args.steps, args.warmup, want_parity=not args.no_parity, keep=True)
+    L, ds, views, start = X["L"], X["ds"], X["views"], X["start"]
+    clocks = sampler.stop(*X["window"]) if sampler else None
+    roofline = main["roofline"]
     # live device-to-device copy rate on this box, for orientation only (read + write bytes / time); the
     # roofline denominator stays MEASURED_PEAKS.json (or the recipe's fallback)
-    copy_gbs = None
     try:
         a = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
         b_ = torch.empty_like(a)
@@ -362,69 +638,26 @@ def run_ours(args):
             b_.copy_(a)
         c1.record()
         torch.cuda.synchronize()
-        copy_gbs = 5 * 2 * a.numel() / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        roofline["d2d_copy_gbs_this_run"] = 5 * 2 * a.numel() / (c0.elapsed_time(c1) * 1e-3) / 1e9
         del a, b_
     except Exception:
         pass
-    k1_ms, k1_groups = tim["assign"]
-    k1_ms_avg = k1_ms / max(k1_groups, 1)
-    alg_bytes = n * (m * 8 + 8)                         # m*(4+4) + 4 + 4 per point
-    achieved = alg_bytes / (k1_ms_avg * 1e-3) / 1e9
-    traffic = None
-    try:   # DRAM bytes per launch from the committed ncu --set full capture (per-point figure x points)
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f)[L.kernel_name]["dram_bytes_per_point"] * n      # keyed by the kernel the plan runs
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": L.kernel_name, "ms_per_launch": k1_ms_avg,
-                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "d2d_copy_gbs_this_run": copy_gbs,
-                "step_breakdown_ms": {k: v[0] / args.steps for k, v in tim.items() if v[1]}}
+    incremental, bounded_leg = modes_at_fixed_point(rig, L, n, m, args.steps, gamma)
 
-    # ---- same iteration with the opt-in modes (not the headline: the synthetic mixture is at its fixed point
-    # here, so no column changes cluster -- K2 reduces to the comparison pass and every bound holds; reported
-    # so the modes can be told apart from the recompute-everything iteration above) ----
-    def timed_mode(incr, bounded):
-        try:
-            L.set_update_mode(incr)
-            L.set_assign_mode(bounded)
-            for _ in range(3):
-                step()
-            fence()
-            ctx.timing_enable(True); ctx.timing_read()
-            ev0.record(ext)
-            for _ in range(args.steps):
-                sti = step()
-            ev1.record(ext)
-            fence()
-            tm = ctx.timing_read(); ctx.timing_enable(False)
-            ti = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(ti, op=dist.ReduceOp.MAX)
-            ms_i = float(ti.item()) / args.steps
-            kind, nch = L.last_update()
-            k1i = tm["assign"][0] / args.steps
-            return {"ms_per_step": ms_i, "value": world * n / (ms_i * 1e-3), "unit": UNIT, "last_update": kind,
-                    "columns_moved_last_step": nch, "columns_reevaluated_last_step": L.last_assign_flagged(),
-                    "assign_ms": k1i, "assign_algorithmic_GBps": alg_bytes / (k1i * 1e-3) / 1e9 if k1i else None,
-                    "objective": sti.objective}
-        except Exception as e:                              # never let the extra legs break the contract line
-            return {"error": str(e)}
-        finally:
-            L.set_update_mode(False)
-            L.set_assign_mode(False)
-    incremental = timed_mode(True, False)
-    incremental["note"] = "opt-in skm_lloyd_set_update_mode(1); the synthetic mixture is at its fixed point here"
-    bounded_leg = timed_mode(True, True)
-    bounded_leg["note"] = "opt-in skm_lloyd_set_assign_mode(1) + set_update_mode(1), same fixed point"
-
-    stream_gb = ds.stream_bytes / 1e9
-    # ---- end to end: host buffers in, host results out, every step ----
+    # pinned host copy for the end-to-end leg: everything on one GPU; under torchrun a bounded sample per rank, so
+    # that the pinned host copies of all ranks together stay well inside the box's memory
     e2e = None
+    stream_gb = ds.stream_bytes / 1e9
     if args.e2e_steps > 0:
+        colptr, rowidx, val = views
+        n_e2e = min(n, args.e2e_n) if args.e2e_n else (n if world == 1 else min(n, 4_000_000))
+        h_colptr = torch.empty(n_e2e + 1, dtype=torch.int64, pin_memory=True)
+        h_rowidx = torch.empty(n_e2e * m, dtype=torch.int32, pin_memory=True)
+        h_val = torch.empty(n_e2e * m, dtype=torch.float32, pin_memory=True)
+        h_colptr.copy_(colptr[:n_e2e + 1]); h_rowidx.copy_(rowidx[:n_e2e * m]); h_val.copy_(val[:n_e2e * m])
+        torch.cuda.synchronize()
         hj, hi, hv = h_colptr.numpy(), h_rowidx.numpy(), h_val.numpy()
-        from sparsifiedkmeans_b200 import lloyd_step_host
+        from sparsifiedkmeans_b200 import Dataset, Lloyd, lloyd_step_host
         # the same host matrix with 2-byte row indices (p <= 65536): the most compact format the ABI accepts
         h_row16 = torch.empty(n_e2e * m, dtype=torch.uint16, pin_memory=True) if p <= 65536 else None
         if h_row16 is not None:
@@ -438,16 +671,7 @@ def run_ours(args):
                                                   want_assign=True, want_dist=False, ctx=ctx, reduce=red)
                 return a, newc
             e2e_step()
-            fence()
-            ev0.record(ext)
-            for _ in range(args.e2e_steps):
-                e2e_step()
-            ev1.record(ext)
-            fence()
-            tt = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e_ms = float(tt.item()) / args.e2e_steps
+            e_ms, _ = rig.timed(e2e_step, args.e2e_steps)
             h2d = hj.nbytes + rows_np.nbytes + hv.nbytes + start.nbytes
             d2h = n_e2e * 4 + start.nbytes
             return {"value": world * n_e2e / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
@@ -461,38 +685,113 @@ def run_ours(args):
         else:
             e2e = e2e_i32
 
-        # Whole-job variant (reported beside the per-step number above, never instead of it): what one
-        # kmeans_sparsified call does with the handle API of INTEGRATION.md level 2 -- upload X from pinned host
-        # memory ONCE, build the device images, run `steps` Lloyd iterations (centres in, statistics out, every
-        # iteration), read assignments, distances and centres back.  Everything is inside the timed region
-        # (host wall clock around synchronous calls); throughput = columns x iterations / time.
+    # ------------------------------------------------------------------ trajectory on the headline shape
+    legs = {}
+    if not args.no_extra:
+        try:
+            legs["trajectory_config2"] = trajectory_leg(rig, ds, cfg, n, max_iter=args.traj_iters)
+        except Exception as e:
+            legs["trajectory_config2"] = {"error": repr(e)}
+
+    # Whole-job variant (reported beside the per-step number above, never instead of it): what one
+    # kmeans_sparsified call does with the handle API of INTEGRATION.md level 2 -- upload X from pinned host
+    # memory ONCE, build the device images, run `steps` Lloyd iterations (centres in, statistics out, every
+    # iteration), read assignments, distances and centres back.  Everything is inside the timed region
+    # (host wall clock around synchronous calls); throughput = columns x iterations / time.
+    L.close(); ds.close()
+    L = ds = None
+    del views, X
+    torch.cuda.empty_cache()
+    if args.e2e_steps > 0 and world == 1:
         try:
             rows_np = h_row16.numpy() if h_row16 is not None else hi
+
             def whole_job():
+                t = [time.perf_counter()]
                 ds2 = Dataset.from_csc(p, n_e2e, hj, rows_np, hv, store="f32", ctx=ctx)
+                t.append(time.perf_counter())
                 L2 = Lloyd(ds2, K)
                 L2.set_centers(start)
-                for _ in range(args.steps):
+                L2.step(gamma, gamma, True)                       # includes the one-off entry-order build
+                t.append(time.perf_counter())
+                for _ in range(args.steps - 1):
                     L2.step(gamma, gamma, True)
+                t.append(time.perf_counter())
                 a2, d2 = L2.assignments()
                 c2 = L2.get_centers()
+                t.append(time.perf_counter())
                 L2.close(); ds2.close()
-                return a2, c2
-            if world == 1:
-                L.close(); ds.close()                          # make room: the job builds its own images
-                ds = L = None
-                whole_job()
-                torch.cuda.synchronize()
-                tj0 = time.perf_counter()
-                whole_job()
-                torch.cuda.synchronize()
-                tj = time.perf_counter() - tj0
-                e2e["whole_job_variant"] = {
-                    "value": n_e2e * args.steps / tj, "unit": UNIT, "seconds": tj, "iterations": args.steps,
-                    "columns": n_e2e, "h2d_bytes_once": int(hj.nbytes + rows_np.nbytes + hv.nbytes),
-                    "what": "upload from pinned host memory + device image build + iterations + read-back, all timed"}
+                return np.diff(t)
+            whole_job()
+            torch.cuda.synchronize()
+            tj0 = time.perf_counter()
+            parts = whole_job()
+            torch.cuda.synchronize()
+            tj = time.perf_counter() - tj0
+            e2e["whole_job_variant"] = {
+                "value": n_e2e * args.steps / tj, "unit": UNIT, "seconds": tj, "iterations": args.steps,
+                "columns": n_e2e, "h2d_bytes_once": int(hj.nbytes + rows_np.nbytes + hv.nbytes),
+                "seconds_upload_and_images": float(parts[0]), "seconds_first_iteration_with_layout": float(parts[1]),
+                "seconds_other_iterations": float(parts[2]), "seconds_read_back": float(parts[3]),
+                "what": "upload from pinned host memory + device image build + iterations + read-back, all timed"}
         except Exception as ex:
-            e2e["whole_job_variant"] = {"error": str(ex)}
+            e2e["whole_job_variant"] = {"error": repr(ex)}
+    if args.e2e_steps > 0:
+        del h_colptr, h_rowidx, h_val, h_row16, hj, hi, hv
+    torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------ the other driver-visible legs
+    if not args.no_extra:
+        xs = max(5, args.steps // 2)
+        # (c) unstructured near-tie workload at the headline shape
+        try:
+            un, Xu = run_lloyd(rig, cfg, n, "unstructured", xs, 3, want_parity=not args.no_parity, keep=True)
+            legs["unstructured"] = un
+            try:
+                legs["trajectory_unstructured"] = trajectory_leg(rig, Xu["ds"], cfg, n, max_iter=args.traj_iters, kind="unstructured")
+            except Exception as e:
+                legs["trajectory_unstructured"] = {"error": repr(e)}
+            Xu["L"].close(); Xu["ds"].close()
+            del Xu
+        except Exception as e:
+            legs["unstructured"] = {"error": repr(e)}
+        torch.cuda.empty_cache()
+        # (a) the north-star shape, 1.25e7 columns per GPU (N = 8: config 3 proper, n = 1e8)
+        c3 = CONFIGS["config3"] if args.config != "tiny" else CONFIGS["tiny3"]
+        n3 = c3["n"]
+        try:
+            l3, X3 = run_lloyd(rig, c3, n3, "mixture", xs, 3, want_parity=not args.no_parity, keep=True)
+            inc3, bnd3 = modes_at_fixed_point(rig, X3["L"], n3, c3["m"], xs, c3["m"] / c3["p"])
+            l3["incremental_update"], l3["bounded_assign"] = inc3, bnd3
+            X3["L"].close()
+            legs["config3"] = l3
+            try:
+                legs["trajectory_config3"] = trajectory_leg(rig, X3["ds"], c3, n3, max_iter=args.traj_iters)
+            except Exception as e:
+                legs["trajectory_config3"] = {"error": repr(e)}
+            X3["ds"].close()
+            del X3
+        except Exception as e:
+            legs["config3"] = {"error": repr(e)}
+        torch.cuda.empty_cache()
+        # (d) strong scaling: n = 1e8 (config 3) split over the N GPUs; N = 8 is the config3 leg itself
+        total = STRONG_TOTAL if args.config != "tiny" else 8 * n3
+        try:
+            if total // world == n3 and "error" not in legs["config3"]:
+                s = {k: legs["config3"][k] for k in ("ms_per_step", "value", "n_per_gpu")}
+                s["same_run_as"] = "config3"
+            else:
+                ls, _ = run_lloyd(rig, c3, total // world, "mixture", 5, 3, want_parity=False)
+                s = {k: ls[k] for k in ("ms_per_step", "value", "n_per_gpu", "dataset_gb", "generate_and_build_s")}
+                s["k1_ms_per_pass"] = ls["roofline"]["ms_per_pass"]
+                s["k1_frac_of_hbm_peak"] = ls["roofline"]["frac"]
+            s["n_total"] = total
+            s["scaling"] = "strong"
+            s["what"] = "one Lloyd iteration over n_total columns (p=1024, K=64, 51/col) sharded over n_gpus GPUs"
+            legs["strong_scaling"] = s
+        except Exception as e:
+            legs["strong_scaling"] = {"error": repr(e), "n_total": total}
+        torch.cuda.empty_cache()
 
     if rank == 0:
         cpu = None
@@ -500,8 +799,8 @@ def run_ours(args):
             r, sample, kind, cores = cpu_rate(cfg, args.cpu_seconds, os.cpu_count() or 1)
             cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["label"], "n_per_gpu": n, "p": p, "k": K, "nnz_per_col": m,
                        "l2": "inputs (%.1f GB streamed per iteration) far exceed the 126 MB L2; no flush needed"
@@ -509,13 +808,13 @@ def run_ours(args):
                        "update": "per-cluster sums recomputed from all columns every iteration (reference semantics)",
                        "parallelism": f"columns sharded over {world} GPU(s), one all-reduce of per-cluster partials per iteration"
                                       if world > 1 else "single GPU"},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": roofline, "cpu_baseline": cpu, "incremental_update": incremental, "bounded_assign": bounded_leg,
-            "rechecked_last_step": st.n_rechecked, "objective": st.objective,
+            "e2e": e2e, "gpu_launches": main["gpu_launches"], "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "parity": main.get("parity"),
+            "incremental_update": incremental, "bounded_assign": bounded_leg,
+            "rechecked_last_step": main["rechecked_last_step"], "objective": main["objective"],
         }
+        out.update(legs)
         print(json.dumps(out))
-    if L is not None:
-        L.close(); ds.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -532,6 +831,9 @@ def main():
     ap.add_argument("--e2e-n", type=int, default=0, help="columns per end-to-end step (default: all)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="headline workload only (skip config3 / unstructured / strong / trajectory legs)")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--traj-iters", type=int, default=100)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -295,6 +295,62 @@ int   skm_kpp_update_sparse(skm_dataset *ds, const double *center /* host p */, 
 int   skm_kpp_pick(skm_dataset *ds, double target, int64_t *j);
 int   skm_kpp_get_mindist(skm_dataset *ds, double *mind /* host n */);
 
+/* ---- several GPUs driven by ONE host process -----------------------------------
+ * The reference is one MATLAB process calling its MEX gateway on the main thread; a MATLAB session cannot be
+ * torchrun.  skm_multi owns one context and one host worker thread per device, shards the columns of X in
+ * contiguous blocks (device g owns [g*n/G, (g+1)*n/G)) and replaces the per-iteration all-reduce + K3 by one
+ * kernel per device that reads every peer's partials [S | N | counts | sumsq] through NVLink peer memory, sums
+ * them in device order (bit-identical centres on every device) and finalises the centres in the same pass.
+ * All calls are synchronous for the caller and may be made from any single host thread.  (One process per GPU
+ * with an NCCL all-reduce of skm_lloyd_partials() remains available: sparsifiedkmeans_b200/distributed.py.) */
+typedef struct skm_multi         skm_multi;
+typedef struct skm_multi_dataset skm_multi_dataset;
+typedef struct skm_multi_lloyd   skm_multi_lloyd;
+
+/* ndev <= 0: every visible device; devices == NULL: devices 0..ndev-1. */
+int      skm_multi_create(int ndev, const int *devices, skm_multi **out);
+void     skm_multi_destroy(skm_multi *m);
+int      skm_multi_ndev(const skm_multi *m);
+skm_ctx *skm_multi_ctx(skm_multi *m, int i);
+int      skm_multi_peer_access(const skm_multi *m);   /* 1: partials are read through peer memory; 0: staged copies */
+
+/* skm_dataset_create_csc for a host matrix, column blocks uploaded concurrently (one worker per device). */
+int  skm_multi_dataset_create_csc(skm_multi *m, int64_t p, int64_t n, const void *jc, int jc_type,
+                                  const void *ir, int ir_type, const void *val, int val_type,
+                                  int store_dtype, skm_multi_dataset **out);
+/* Adopt ndev datasets built any other way (shards[g] on skm_multi_ctx(m, g), in column order, e.g. from
+ * skm_dataset_from_dense_host with col0 = the block's first column); ownership moves to the result. */
+int  skm_multi_dataset_from_shards(skm_multi *m, skm_dataset *const *shards, skm_multi_dataset **out);
+void skm_multi_dataset_destroy(skm_multi_dataset *md);
+skm_dataset *skm_multi_dataset_shard(skm_multi_dataset *md, int i, int64_t *col0);
+int  skm_multi_dataset_get_info(const skm_multi_dataset *md, skm_dataset_info *info);   /* totals over the shards */
+int  skm_multi_dataset_get_column(skm_multi_dataset *md, int64_t j /* global */, double *out);
+/* k-means++ rounds over the shards (private/Arthur_initialization.m:39-53); sparse_center selects
+ * skm_kpp_update_sparse.  skm_multi_kpp_pick returns the GLOBAL column whose cumulative D^2 passes target. */
+int  skm_multi_kpp_update(skm_multi_dataset *md, const double *center, int has_gamma, double gamma, int first,
+                          int sparse_center, double *sum_d2);
+int  skm_multi_kpp_pick(skm_multi_dataset *md, double target, int64_t *j);
+
+int  skm_multi_lloyd_create(skm_multi_dataset *md, int64_t K, skm_multi_lloyd **out);
+void skm_multi_lloyd_destroy(skm_multi_lloyd *L);
+int  skm_multi_lloyd_set_modes(skm_multi_lloyd *L, int update_mode, int assign_mode);   /* skm_lloyd_set_*_mode per shard */
+int  skm_multi_lloyd_set_centers(skm_multi_lloyd *L, const double *centers /* host p x K */);
+int  skm_multi_lloyd_set_center_column(skm_multi_lloyd *L, int64_t k, const double *col);
+int  skm_multi_lloyd_get_centers(skm_multi_lloyd *L, double *centers);
+int  skm_multi_lloyd_get_centers_old(skm_multi_lloyd *L, double *centers);
+int  skm_multi_lloyd_get_centers_of(skm_multi_lloyd *L, int device_index, double *centers);
+/* One Lloyd iteration (kmeans_sparsified.m:420-471): K1 + K2 on every shard concurrently, then the fused
+ * peer-memory reduction + K3 on every device.  sparse_centers != 0 takes the sparse-centres branch of the
+ * operator (private/findClusterAssignments.m:63-75).  stats are global. */
+int  skm_multi_lloyd_step(skm_multi_lloyd *L, int has_gamma, double gamma_dist, double gamma_update,
+                          int ml_correction, int sparse_centers, skm_iter_stats *stats);
+int  skm_multi_lloyd_refresh_diff(skm_multi_lloyd *L, skm_iter_stats *stats);
+int  skm_multi_lloyd_get_counts(skm_multi_lloyd *L, int64_t *counts /* host K, global */);
+/* assignments (1-based) / distances of all n columns, in column order */
+int  skm_multi_lloyd_get_assignments(skm_multi_lloyd *L, int32_t *assign_out, double *dist_out);
+int  skm_multi_lloyd_argmax_distance(skm_multi_lloyd *L, double *maxdist, int64_t *j /* global, first occurrence */);
+int  skm_multi_lloyd_launch_count(skm_multi_lloyd *L, int64_t *launches);
+
 /* ---- preconditioning on device (kmeans_sparsified.m:238-248,286-295) ------ */
 
 /* Y = hadamard(D * [X; 0]) / sqrt(p2) for a dense p x n host matrix (fp64 in,

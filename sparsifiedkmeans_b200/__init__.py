@@ -10,6 +10,7 @@ from .engine import (Context, Dataset, IterStats, Lloyd, dct_mix, default_contex
 from .find_cluster_assignments import findClusterAssignments                  # noqa: F401
 from .kmeans import (Arthur_initialization, KMeansError, kmeans_sparsified,    # noqa: F401
                      randsample_block, randsample_fixedNumberEntries)
+from .multi import MultiContext, MultiDataset, MultiLloyd                      # noqa: F401
 from .ops import (SparseMatrixColumnNormSq, SparseMatrixInnerProduct,         # noqa: F401
                   SparseMatrixMinusCluster, hadamard, hadamard_pthreads)
 

@@ -104,6 +104,33 @@ SIGNATURES = {
     "skm_kpp_update_sparse": (_int, [_vp, _vp, _int, C.POINTER(_dbl)]),
     "skm_kpp_pick": (_int, [_vp, _dbl, C.POINTER(_i64)]),
     "skm_kpp_get_mindist": (_int, [_vp, _vp]),
+    "skm_multi_create": (_int, [_int, _vp, C.POINTER(_vp)]),
+    "skm_multi_destroy": (None, [_vp]),
+    "skm_multi_ndev": (_int, [_vp]),
+    "skm_multi_ctx": (_vp, [_vp, _int]),
+    "skm_multi_peer_access": (_int, [_vp]),
+    "skm_multi_dataset_create_csc": (_int, [_vp, _i64, _i64, _vp, _int, _vp, _int, _vp, _int, _int, C.POINTER(_vp)]),
+    "skm_multi_dataset_from_shards": (_int, [_vp, _vp, C.POINTER(_vp)]),
+    "skm_multi_dataset_destroy": (None, [_vp]),
+    "skm_multi_dataset_shard": (_vp, [_vp, _int, C.POINTER(_i64)]),
+    "skm_multi_dataset_get_info": (_int, [_vp, C.POINTER(DatasetInfo)]),
+    "skm_multi_dataset_get_column": (_int, [_vp, _i64, _vp]),
+    "skm_multi_kpp_update": (_int, [_vp, _vp, _int, _dbl, _int, _int, C.POINTER(_dbl)]),
+    "skm_multi_kpp_pick": (_int, [_vp, _dbl, C.POINTER(_i64)]),
+    "skm_multi_lloyd_create": (_int, [_vp, _i64, C.POINTER(_vp)]),
+    "skm_multi_lloyd_destroy": (None, [_vp]),
+    "skm_multi_lloyd_set_modes": (_int, [_vp, _int, _int]),
+    "skm_multi_lloyd_set_centers": (_int, [_vp, _vp]),
+    "skm_multi_lloyd_set_center_column": (_int, [_vp, _i64, _vp]),
+    "skm_multi_lloyd_get_centers": (_int, [_vp, _vp]),
+    "skm_multi_lloyd_get_centers_old": (_int, [_vp, _vp]),
+    "skm_multi_lloyd_get_centers_of": (_int, [_vp, _int, _vp]),
+    "skm_multi_lloyd_step": (_int, [_vp, _int, _dbl, _dbl, _int, _int, C.POINTER(IterStats)]),
+    "skm_multi_lloyd_refresh_diff": (_int, [_vp, C.POINTER(IterStats)]),
+    "skm_multi_lloyd_get_counts": (_int, [_vp, _vp]),
+    "skm_multi_lloyd_get_assignments": (_int, [_vp, _vp, _vp]),
+    "skm_multi_lloyd_argmax_distance": (_int, [_vp, C.POINTER(_dbl), C.POINTER(_i64)]),
+    "skm_multi_lloyd_launch_count": (_int, [_vp, C.POINTER(_i64)]),
     "skm_mix_hadamard": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _int, _vp]),
     "skm_fwht_sample_f32": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, C.c_uint64, _i64, C.POINTER(_vp)]),
     "skm_dataset_from_dense_host": (_int, [_vp, _i64, _i64, _i64, _vp, _int, _vp, _i64, C.c_uint64, _i64, _i64,

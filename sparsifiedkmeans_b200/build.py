@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIBDIR, "libskm_b200.so")
-SOURCES = ["api.cu", "convert.cu", "exact.cu", "assign_fast.cu", "update.cu", "fwht.cu", "kpp.cu", "csr.cu", "stream.cu", "dense.cu", "dct.cu", "bounded.cu"]
+SOURCES = ["api.cu", "convert.cu", "exact.cu", "assign_fast.cu", "update.cu", "fwht.cu", "kpp.cu", "csr.cu", "stream.cu", "dense.cu", "dct.cu", "bounded.cu", "multi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -56,7 +56,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
                 if verbose and out:
                     print(out)
     if jobs or force or _stale(LIB_PATH, objs):
-        run([NVCC, "-shared", "-o", LIB_PATH, *objs, "-Xcompiler", "-fPIC", "-ldl"])
+        run([NVCC, "-shared", "-o", LIB_PATH, *objs, "-Xcompiler", "-fPIC", "-ldl", "-lpthread"])
     return LIB_PATH
 
 

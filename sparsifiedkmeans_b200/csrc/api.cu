@@ -475,7 +475,7 @@ extern "C" void skm_lloyd_destroy(skm_lloyd *L)
     cudaFree(L->best2); cudaFree(L->flagged); cudaFree(L->nflag); cudaFree(L->partials);
     cudaFree(L->stats);
     cudaFree(L->acc_local); cudaFree(L->assign_prev); cudaFree(L->changed); cudaFree(L->nchanged);
-    cudaFree(L->lb); cudaFree(L->centers_prev); cudaFree(L->table_t); cudaFree(L->shift);
+    cudaFree(L->lb); cudaFree(L->centers_prev); cudaFree(L->table_t); cudaFree(L->shift); cudaFree(L->nchanged_pred);
     if (L->h_stats) cudaFreeHost(L->h_stats);
     if (L->h_counts) cudaFreeHost(L->h_counts);
     delete L;
@@ -586,6 +586,7 @@ extern "C" int skm_lloyd_set_assign_mode(skm_lloyd *L, int mode)
         SKM_TRY(dev_alloc((void **)&L->centers_prev, sizeof(double) * p * K, "centers_prev"));
         SKM_TRY(dev_alloc((void **)&L->table_t, sizeof(float) * K * (p + 1), "table_t"));
         SKM_TRY(dev_alloc((void **)&L->shift, sizeof(float) * (K + 4), "shift"));
+        SKM_TRY(dev_alloc((void **)&L->nchanged_pred, 16, "predict counter"));
     }
     L->assign_mode = mode;
     L->lb_valid = false;
@@ -633,6 +634,19 @@ extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
             SKM_TRY(skm_launch_center_shift(ctx, ds->p, L->K, L->centers, L->centers_prev, has_gamma, gamma, L->shift));
         }
         L->gamma_prev = gnow;
+        if (usable && !L->dist_is_f64) {
+            // a-priori test (12 bytes per column, no entry read): how many columns are CERTAIN to keep their centre
+            // after this move?  While the centres still move a lot that is next to none, and the bounded pass
+            // would only be an extra pass in front of the full one.
+            SkmTimed t(ctx, SKM_T_PREP);
+            unsigned long long *cnt = reinterpret_cast<unsigned long long *>(L->nchanged_pred);
+            SKM_TRY(skm_launch_bound_predict(ctx, ds->n, L->K, L->lb, L->dist_f32, L->assign, L->shift, cnt));
+            unsigned long long hcnt = 0;
+            SKM_CUDA(cudaMemcpyAsync(&hcnt, cnt, sizeof hcnt, cudaMemcpyDeviceToHost, ctx->stream));
+            SKM_CUDA(cudaStreamSynchronize(ctx->stream));
+            L->last_predicted_keep = (int64_t)hcnt;
+            if ((int64_t)hcnt < ds->n / 2) usable = false;
+        }
         if (usable) {
             int64_t nfl = 0;
             {

@@ -21,6 +21,7 @@
 // in shared memory for as many centres as fit, the rest is read through L1/L2.
 #include "common.cuh"
 #include <math.h>
+#include <algorithm>
 
 namespace {
 
@@ -161,6 +162,29 @@ __global__ void k_center_shift(int64_t p, const double *__restrict__ cnew, doubl
     }
 }
 
+// A-priori count of the columns the bounded pass is certain to keep: the masked distance is a seminorm of the
+// centre, so the new distance to the own centre is at most dist_j + shift[a_j]; if even that stays below the
+// lowered bound the column keeps its centre.  One pass over 12 bytes per column (no entry is read) tells the
+// caller whether the bounded pass is worth launching at all after this move of the centres.
+__global__ void k_bound_predict(int64_t n, int K, const float *__restrict__ lb, const float *__restrict__ dist,
+                                const int32_t *__restrict__ assign, const float *__restrict__ shift,
+                                unsigned long long *__restrict__ count)
+{
+    const float dmax = shift[K], dsec = shift[K + 1];
+    const int imax = (int)shift[K + 2];
+    unsigned int local = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        int a = assign[j];
+        if ((unsigned)a >= (unsigned)K) a = 0;
+        const float mv = (a == imax) ? dsec : dmax;
+        local += (dist[j] + shift[a]) * (1.f + 2.0e-6f) < (lb[j] - mv);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, (unsigned long long)local);
+}
+
 __global__ void k_shift_top2(int64_t K, float *__restrict__ shift)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -201,6 +225,17 @@ int skm_launch_center_shift(skm_ctx *ctx, int64_t p, int64_t K, const double *ce
     k_center_shift<<<(unsigned)K, 256, 0, ctx->stream>>>(p, centers, centers_prev, has_gamma, gamma, shift);
     SKM_CHECK_LAUNCH(ctx);
     k_shift_top2<<<1, 32, 0, ctx->stream>>>(K, shift);
+    SKM_CHECK_LAUNCH(ctx);
+    return SKM_OK;
+}
+
+int skm_launch_bound_predict(skm_ctx *ctx, int64_t n, int64_t K, const float *lb, const float *dist, const int32_t *assign,
+                             const float *shift, unsigned long long *count_dev)
+{
+    SKM_CUDA(cudaMemsetAsync(count_dev, 0, sizeof(unsigned long long), ctx->stream));
+    if (n == 0) return SKM_OK;
+    const int64_t blocks = std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
+    k_bound_predict<<<(unsigned)blocks, 256, 0, ctx->stream>>>(n, (int)K, lb, dist, assign, shift, count_dev);
     SKM_CHECK_LAUNCH(ctx);
     return SKM_OK;
 }

@@ -180,6 +180,8 @@ struct skm_lloyd {
     double   gamma_prev;     // and the scaling they were divided by (NaN: none)
     float   *table_t;        // [K][p+1] fp32 centres, one row per centre (bounded kernel)
     float   *shift;          // [K + 4] per-centre movement; then max, second max, argmax
+    void    *nchanged_pred;  // device counter of the a-priori keep test
+    int64_t  last_predicted_keep;   // columns the a-priori test proved to keep their centre (-1: not run)
     int64_t  last_bounded_flagged;   // columns the bounds could not keep (-1: the pass evaluated everything)
     int      bounded_skip, bounded_backoff;   // passes to sit out after a bounded pass that kept too few columns
     bool     assigned, accumulated;
@@ -262,6 +264,8 @@ int  skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, cons
 // bounded.cu
 int skm_launch_center_shift(skm_ctx *ctx, int64_t p, int64_t K, const double *centers, double *centers_prev,
                             int has_gamma, double gamma, float *shift /* [K+4] */);
+int skm_launch_bound_predict(skm_ctx *ctx, int64_t n, int64_t K, const float *lb, const float *dist, const int32_t *assign,
+                             const float *shift, unsigned long long *count_dev);
 int skm_launch_build_table_t(skm_ctx *ctx, int64_t p, int64_t K, const double *ct, float *table_t, float *cmax);
 int skm_launch_assign_bounded(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const float *table_t, const float *cmax,
                               const float *shift, const int32_t *assign, float *lb, float *dist,

@@ -318,6 +318,61 @@ __global__ void k_finalize(int64_t p, int64_t K, const double *__restrict__ part
     }
 }
 
+// Multi-device K3 (multi.cu): the all-reduce of the partials is fused into the finalisation.  parts[g] points at
+// device g's [S | N | counts | sumsq] -- peer memory over NVLink for g != this device -- and the sums run in
+// device order, so every device computes bit-identical centres whatever the timing.  tail receives the reduced
+// [counts | sumsq] for the statistics read-back.
+__global__ void k_finalize_peers(int64_t p, int64_t K, int ndev, const double *const *__restrict__ parts, double gamma,
+                                 int ml, double *__restrict__ centers, double *__restrict__ centers_old,
+                                 double *__restrict__ stats, double *__restrict__ tail)
+{
+    const int64_t pk = p * K;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double d2 = 0.0;
+    int nan = 0;
+    if (idx < pk) {
+        const int64_t k = idx / p;
+        double S = 0.0, N = 0.0, cnt = 0.0;
+        for (int g = 0; g < ndev; ++g) {
+            const double *q = parts[g];
+            S += q[idx]; N += q[pk + idx]; cnt += q[2 * pk + k];
+        }
+        const double old = centers[idx];
+        double nw = old;
+        if (cnt > 0.0) {
+            const double s = (N == 0.0) ? 0.0 : S;                       // structural zero, see k_finalize
+            if (ml) nw = __ddiv_rn(__dmul_rn(gamma, s), __dadd_rn(N, 1e-16));
+            else    nw = __ddiv_rn(s, cnt);
+        }
+        centers_old[idx] = old;
+        centers[idx] = nw;
+        const double d = old - nw;
+        d2 = d * d;
+        nan = (nw != nw);
+    }
+    if (blockIdx.x == 0)
+        for (int64_t i = threadIdx.x; i <= K; i += blockDim.x) {
+            double t = 0.0;
+            for (int g = 0; g < ndev; ++g) t += parts[g][2 * pk + i];
+            tail[i] = t;
+        }
+    __shared__ double red[32];
+    __shared__ int rnan;
+    if (threadIdx.x == 0) rnan = 0;
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d2;
+    if (nan) rnan = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+        atomicAdd(&stats[0], s);
+        if (rnan) stats[1] = 1.0;
+    }
+}
+
 // centre change without an update (after the host patched columns for EmptyAction)
 __global__ void k_diff(int64_t total, const double *__restrict__ centers,
                        const double *__restrict__ centers_old, double *__restrict__ stats)
@@ -494,6 +549,19 @@ int skm_launch_finalize(skm_ctx *ctx, int64_t p, int64_t K, const double *partia
                                                              centers_old, stats);
     else
         k_diff<<<(unsigned)blocks, 256, 0, ctx->stream>>>(total, centers, centers_old, stats);
+    SKM_CHECK_LAUNCH(ctx);
+    return SKM_OK;
+}
+
+int skm_launch_finalize_peers(skm_ctx *ctx, int64_t p, int64_t K, int ndev, const double *const *parts_dev,
+                              double gamma, int ml_correction, double *centers, double *centers_old,
+                              double *stats, double *tail)
+{
+    SKM_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 8, ctx->stream));
+    const int64_t total = p * K;
+    const int64_t blocks = total > 0 ? (total + 255) / 256 : 1;
+    k_finalize_peers<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p, K, ndev, parts_dev, gamma, ml_correction, centers,
+                                                               centers_old, stats, tail);
     SKM_CHECK_LAUNCH(ctx);
     return SKM_OK;
 }

@@ -326,7 +326,7 @@ class Dataset:
     def kpp_update(self, center, gamma=None, first: bool = False, sparse_center: bool = False) -> float:
         """Fold the masked distance to one new centre into the running minimum; returns the local sum of
         D^2.  sparse_center=True is the gamma-less call of Arthur_initialization.m:26, where the centre stays
-        sparse and the sum runs over supp(x) /\ supp(centre) only (findClusterAssignments.m:70-74)."""
+        sparse and the sum runs over the intersection of supp(x) and supp(centre) only (findClusterAssignments.m:70-74)."""
         c = np.ascontiguousarray(center, dtype=np.float64).reshape(-1)
         if c.shape[0] != self.p:
             raise ValueError("centre must have p entries")

@@ -39,7 +39,7 @@ _DEFAULTS = dict(
     SparsityIgnoreUpsampling=False, FORCE_BUG=False, tryBuiltinMex=True, unbiasedDistance=True,
     unbiasedInitialization=True, denseCenters=False,
 )
-_EXTRA = dict(Seed=None, Signs=None, SampleRows=None, StartIndices=None, Store="f32", Device=0,
+_EXTRA = dict(Seed=None, Signs=None, SampleRows=None, StartIndices=None, Store="f32", Device=0, Devices=None,
               MixDtype="f64", nargout=5, Context=None, Pipeline="auto", IncrementalUpdate=True, BoundedAssign=True)
 
 
@@ -193,7 +193,17 @@ def kmeans_sparsified(X=None, K=None, **opts):
         raise NotImplementedError("Sparsify=false (dense K-means through pdist2) is outside the sparsified hot path")
     import scipy.sparse as sp
     rng = np.random.default_rng(o["Seed"])
-    ctx: Context = o["Context"] or default_context(int(o["Device"]))
+    # Devices=[0,1,...] (or an int count): the columns are sharded over several GPUs of this box and driven from
+    # this one process (skm_multi_*, multi.py); everything below runs unchanged on the sharded handles
+    mctx = None
+    if o["Devices"] is not None and not (isinstance(o["Devices"], (list, tuple)) and len(o["Devices"]) == 1):
+        from .multi import MultiContext, MultiDataset, MultiLloyd
+        mctx = o["Devices"] if isinstance(o["Devices"], MultiContext) else MultiContext(o["Devices"])
+    elif o["Devices"] is not None:
+        o["Device"] = int(o["Devices"][0])
+    ctx: Context = o["Context"] or (mctx.contexts[0] if mctx is not None else default_context(int(o["Device"])))
+    own_mctx = mctx is not None and not isinstance(o["Devices"], type(mctx))
+    OUTPUT_devices = mctx.devices if mctx is not None else [ctx.device]
     OUTPUT = {"LoadFromDisk": load_from_disk, "Options": {k: o[k] for k in _DEFAULTS}, "Sparsify": True}
 
     if np.iscomplexobj(X):
@@ -285,7 +295,9 @@ def kmeans_sparsified(X=None, K=None, **opts):
             raise ValueError("Pipeline='device' needs the Hadamard sketch with on-device row sampling, or the DCT sketch")
         t1 = time.perf_counter()
         seed = int(rng.integers(0, 2 ** 63 - 1))
-        if sk == "dct":
+        if mctx is not None:
+            ds = MultiDataset.from_dense_host(Xd, d, small_p, seed=seed, mctx=mctx, dct=(sk == "dct"), rows=o["SampleRows"])
+        elif sk == "dct":
             ds = Dataset.from_dense_host_dct(Xd, d, small_p, seed=seed, rows=o["SampleRows"], ctx=ctx)
         else:
             ds = Dataset.from_dense_host(Xd, d, small_p, seed=seed, ctx=ctx)      # applies *(1+2eps) itself
@@ -303,8 +315,12 @@ def kmeans_sparsified(X=None, K=None, **opts):
         Xs = randsample_fixedNumberEntries(Xm, small_p, np.asarray(rows))             # :334
         del Xm
         OUTPUT["TimeToSample"] = time.perf_counter() - t1
-        ds = Dataset.from_scipy(Xs, store=o["Store"], ctx=ctx)
+        ds = (MultiDataset.from_scipy(Xs, store=o["Store"], mctx=mctx) if mctx is not None
+              else Dataset.from_scipy(Xs, store=o["Store"], ctx=ctx))
     OUTPUT["Pipeline"] = pipeline
+    OUTPUT["Devices"] = OUTPUT_devices
+    make_lloyd = (lambda Kx, inc, bnd: MultiLloyd(ds, Kx, incremental=inc, bounded=bnd)) if mctx is not None else \
+                 (lambda Kx, inc, bnd: Lloyd(ds, Kx, incremental=inc, bounded=bnd))
     if display in ("iter", "final"):
         print(f"Randomly mixing of type {sketch}")
         print("Randomly taking %.1f%% of the data; actual dataset is %.1f%% sparse"
@@ -369,7 +385,7 @@ def kmeans_sparsified(X=None, K=None, **opts):
             big = ds.nnz >= 2_000_000
             bounded = bool(o["BoundedAssign"]) and ds.store_dtype == "f32" and big
             incremental = bool(o["IncrementalUpdate"]) and big
-            L = Lloyd(ds, Kt, incremental=incremental, bounded=bounded)
+            L = make_lloyd(Kt, incremental, bounded)
             L.set_centers(centers)
             its = 0
             dff = obj = math.nan
@@ -404,7 +420,7 @@ def kmeans_sparsified(X=None, K=None, **opts):
                         _, distances = L.assignments()
                         L.close()
                         Kt = keep.size
-                        L = Lloyd(ds, Kt, incremental=incremental, bounded=bounded)
+                        L = make_lloyd(Kt, incremental, bounded)
                         L.set_centers(cen)
                         assignments = np.zeros(0, dtype=np.int32)                     # :457 assignments = []
                         dropped_last = True
@@ -490,6 +506,8 @@ def kmeans_sparsified(X=None, K=None, **opts):
         if two is not None:
             two[0] = two[0].T
     OUTPUT["TimeOverall"] = time.perf_counter() - t0
+    if own_mctx:
+        mctx.close()
     if two is None:
         return IDX, C, SUMD, D, OUTPUT
     return (IDX, C, SUMD, D, OUTPUT, *two)

@@ -17,7 +17,7 @@ def big(ctx):
     from sparsifiedkmeans_b200 import Dataset, Lloyd
     from sparsifiedkmeans_b200._lib import SKM_F32, SKM_I32, SKM_I64
     dev = torch.device("cuda:0")
-    colptr, rowidx, val, mu, start = bench.gen_shard_device(dev, N, P, M, K, col0=0)
+    colptr, rowidx, val, mu, start = bench.gen_shard_device(dev, N, P, M, K, col0=0, ctx=ctx)
     torch.cuda.synchronize()
     # host copies of three slices (head, middle, tail) for the oracle
     slices = {}
