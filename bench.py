@@ -348,8 +348,8 @@ class Rig:
         torch.cuda.set_device(self.local)
         self.dev = torch.device(f"cuda:{self.local}")
         if self.world > 1:
-            if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-                os.environ["NCCL_DEBUG"] = "WARN"           # keep stdout to the one JSON line
+            # keep stdout to the one JSON line: whatever NCCL logs (its version banner at WARN/VERSION/INFO) goes to stderr
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             dist.init_process_group("nccl", device_id=self.dev)
         self.ctx = Context(self.local)
         self.ext = torch.cuda.ExternalStream(self.ctx.stream, device=self.dev)

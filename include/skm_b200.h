@@ -79,6 +79,11 @@ int         skm_ctx_sync(skm_ctx *ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t     skm_ctx_launch_count(const skm_ctx *ctx);
 
+/* Chunks of skm_second_pass the tensor-core filter (tcgen05 tf32 product + exact evaluation of its candidates)
+ * handled so far on this context, and chunks after which it was switched off for the rest of a call because more
+ * than an eighth of the points stayed uncertain (data without cluster structure). */
+int         skm_ctx_tc_chunks(const skm_ctx *ctx, int64_t *kept, int64_t *dropped);
+
 /* Per-kernel device timing with CUDA events on the context stream (off by default).
  * skm_ctx_timing_read synchronises, writes the summed milliseconds and launch-group counts
  * of the 8 slots {assign, recheck, accumulate, finalize, prep, fwht, kpp, upload} since the
@@ -384,10 +389,11 @@ int   skm_dataset_from_dense_host(skm_ctx *ctx, int64_t p, int64_t p2, int64_t n
 
 /* y = dct(D .* x) (inverse == 0: mix, :295) or y = D .* idct(x) (inverse != 0: unmix, :296) for a dense
  * p x n HOST matrix, column-major, fp64; dct is MATLAB's orthonormal DCT-II along columns.  signs
- * (+-1, length p) may be NULL.  Applied as one dense product on the GPU (cuBLAS, loaded on first use). */
+ * (+-1, length p) may be NULL.  Applied as one dense fp64 product on the GPU (hand-written tiled kernel). */
 int   skm_dct_mix(skm_ctx *ctx, int64_t p, int64_t n, const double *x, const double *signs, int inverse, double *y);
 /* skm_dataset_from_dense_host for the DCT sketch (no zero-padding: p2 = p): chunks cross PCIe, are
- * multiplied by T*diag(signs)*(1+2eps) in fp32 and m rows per column are kept, divided by m/p.
+ * multiplied by T*diag(signs)*(1+2eps) on the tensor cores (tcgen05 tf32, both operands split in tf32-exact halves:
+ * 3xTF32, fp32 accuracy) and m rows per column are kept, divided by m/p.
  * rows_host: int32[m*n] explicit 0-based rows per column (any order, distinct) or NULL = drawn on the
  * device (Philox4x32-10 keyed by seed, counted by the global column col0+j). */
 int   skm_dataset_from_dense_host_dct(skm_ctx *ctx, int64_t p, int64_t n, const void *x, int x_type,

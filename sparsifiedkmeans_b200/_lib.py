@@ -55,6 +55,7 @@ SIGNATURES = {
     "skm_ctx_device": (_int, [_vp]),
     "skm_ctx_sync": (_int, [_vp]),
     "skm_ctx_launch_count": (_i64, [_vp]),
+    "skm_ctx_tc_chunks": (_int, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "skm_ctx_timing_enable": (_int, [_vp, _int]),
     "skm_ctx_timing_read": (_int, [_vp, _vp, _vp]),
     "skm_sparse_matrix_minus_cluster": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _int, _dbl, _vp]),

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <new>
@@ -64,8 +65,8 @@ extern "C" int skm_ctx_create(int device, void *cuda_stream, skm_ctx **out)
     ctx->timing = false;
     ctx->stream_cache = nullptr;
     ctx->stream_cache_free = nullptr;
-    ctx->blas = nullptr;
-    ctx->blas_free = nullptr;
+    ctx->tc_chunks = 0;
+    ctx->tc_chunks_dropped = 0;
     ctx->ev = nullptr;
     memset(ctx->ev_count, 0, sizeof ctx->ev_count);
     if (cudaMalloc((void **)&ctx->d_flag, 16 * sizeof(int)) != cudaSuccess ||
@@ -84,7 +85,6 @@ extern "C" void skm_ctx_destroy(skm_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->stream_cache && ctx->stream_cache_free) ctx->stream_cache_free(ctx->stream_cache);
-    if (ctx->blas && ctx->blas_free) ctx->blas_free(ctx->blas);
     if (ctx->d_flag) cudaFree(ctx->d_flag);
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
     if (ctx->ev) {
@@ -99,6 +99,13 @@ extern "C" void skm_ctx_destroy(skm_ctx *ctx)
 extern "C" void *skm_ctx_stream(skm_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 extern "C" int skm_ctx_device(const skm_ctx *ctx) { return ctx ? ctx->device : -1; }
 extern "C" int64_t skm_ctx_launch_count(const skm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int skm_ctx_tc_chunks(const skm_ctx *ctx, int64_t *kept, int64_t *dropped)
+{
+    SKM_REQUIRE(ctx, "ctx is NULL");
+    if (kept) *kept = ctx->tc_chunks;
+    if (dropped) *dropped = ctx->tc_chunks_dropped;
+    return SKM_OK;
+}
 extern "C" int skm_ctx_sync(skm_ctx *ctx)
 {
     SKM_REQUIRE(ctx, "ctx is NULL");
@@ -181,11 +188,15 @@ static int d2h_sync(skm_ctx *ctx, void *dst, const void *src, size_t bytes)
 // ---------------------------------------------------------------------------
 static size_t type_size(int t) { return t == SKM_U16 ? 2 : ((t == SKM_F32 || t == SKM_I32) ? 4 : 8); }
 
+static bool skm_trace_on();
+static double skm_now();
 extern "C" void skm_dataset_destroy(skm_dataset *ds)
 {
     if (!ds) return;
     cudaSetDevice(ds->ctx->device);
     cudaStreamSynchronize(ds->ctx->stream);
+    const double td0 = skm_trace_on() ? skm_now() : 0.0;
+    struct Tr { double t0; ~Tr() { if (skm_trace_on()) fprintf(stderr, "[skm trace] %-28s %8.2f ms\n", "dataset_destroy", 1e3 * (skm_now() - t0)); } } tr{td0};
     cudaFree(ds->colptr);
     cudaFree(ds->rowidx);
     cudaFree(ds->val);
@@ -202,16 +213,27 @@ extern "C" void skm_dataset_destroy(skm_dataset *ds)
     delete ds;
 }
 
+#include <chrono>
+static bool skm_trace_on() { static const bool on = getenv("SKM_TRACE") != nullptr; return on; }
+static double skm_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+#define SKM_TRACE_POINT(label, t0)                                                             \
+    do { if (skm_trace_on()) { cudaDeviceSynchronize(); const double t1__ = skm_now();         \
+         fprintf(stderr, "[skm trace] %-28s %8.2f ms\n", label, 1e3 * (t1__ - (t0))); (t0) = t1__; } } while (0)
+
 // takes ownership of colptr/rowidx/val (device, final types)
 static int dataset_finish(skm_dataset *ds)
 {
     skm_ctx *ctx = ds->ctx;
+    double t0 = skm_now();
     SKM_TRY(skm_validate_csc(ctx, ds->p, ds->n, ds->nnz, ds->colptr, ds->rowidx, &ds->max_col_nnz));
+    SKM_TRACE_POINT("validate", t0);
     ds->device_bytes = (int64_t)sizeof(int64_t) * (ds->n + 1) + (int64_t)sizeof(int32_t) * ds->nnz +
                        (int64_t)type_size(ds->store_dtype) * ds->nnz;
     if (ds->store_dtype == SKM_F32) {
         SKM_TRY(skm_build_sell(ds));
+        SKM_TRACE_POINT("build_sell (widths, alloc)", t0);
         SKM_TRY(skm_build_csr(ds));
+        SKM_TRACE_POINT("build_csr", t0);
     }
     return SKM_OK;
 }
@@ -253,10 +275,12 @@ extern "C" int skm_dataset_create_csc(skm_ctx *ctx, int64_t p, int64_t n, const 
     ds->p = p; ds->n = n; ds->nnz = nnz;
     ds->store_dtype = store_dtype;
     int rc = SKM_OK;
+    double tt0 = skm_now();
     do {
         if ((rc = dev_alloc((void **)&ds->colptr, sizeof(int64_t) * (n + 1), "colptr"))) break;
         if ((rc = dev_alloc((void **)&ds->rowidx, sizeof(int32_t) * nnz, "rowidx"))) break;
         if ((rc = dev_alloc(&ds->val, type_size(store_dtype) * nnz, "val"))) break;
+        SKM_TRACE_POINT("alloc csc", tt0);
         // stage raw arrays (host -> device) unless they already live on the device
         DevBuf sj, si, sv;
         const void *dj = jc, *di = ir, *dv = val;
@@ -293,6 +317,7 @@ extern "C" int skm_dataset_create_csc(skm_ctx *ctx, int64_t p, int64_t n, const 
         if (dv && nnz && (rc = skm_launch_convert_value(ctx, dv, val_type, nnz, ds->val, store_dtype))) break;
         cudaError_t e = cudaStreamSynchronize(ctx->stream);      // staging buffers die here
         if (e != cudaSuccess) { skm_set_error("upload failed: %s", cudaGetErrorString(e)); rc = SKM_ERR_CUDA; break; }
+        SKM_TRACE_POINT("h2d + convert", tt0);
         rc = dataset_finish(ds);
     } while (0);
     if (rc != SKM_OK) { skm_dataset_destroy(ds); return rc; }
@@ -645,7 +670,7 @@ extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
             SKM_CUDA(cudaMemcpyAsync(&hcnt, cnt, sizeof hcnt, cudaMemcpyDeviceToHost, ctx->stream));
             SKM_CUDA(cudaStreamSynchronize(ctx->stream));
             L->last_predicted_keep = (int64_t)hcnt;
-            if ((int64_t)hcnt < ds->n / 2) usable = false;
+            if ((int64_t)hcnt < ds->n - ds->n / 4) usable = false;      // the pass pays off only if few columns need the full evaluation
         }
         if (usable) {
             int64_t nfl = 0;

@@ -21,6 +21,7 @@
 // in shared memory for as many centres as fit, the rest is read through L1/L2.
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 #include <algorithm>
 
 namespace {
@@ -44,6 +45,16 @@ struct BoundedParams {
 // PADTAIL: the last batch of a column is padded with (zero row, 0) entries instead of a serial tail.  It pays
 // when part of the table is read through L2 (K = 64: 1.52 -> 1.39 ms) and costs when everything is in shared
 // memory and the kernel already runs at the HBM rate (K = 10: 0.98 -> 1.07 ms), so the launcher picks.
+// 128-bit streaming load that bypasses L1 allocation: whatever L1 the shared-memory carve-out leaves belongs to the
+// table rows that do not fit in shared memory (K = 64: 9 of 64), which would otherwise be evicted by the stream
+__device__ __forceinline__ int4 ld_stream(const int4 *p)
+{
+    int4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 template <int THREADS, bool PADTAIL>
 __global__ void __launch_bounds__(THREADS) k_assign_bounded(const BoundedParams P)
 {
@@ -87,7 +98,7 @@ __global__ void __launch_bounds__(THREADS) k_assign_bounded(const BoundedParams 
         // a latency-bound kernel needs more bytes in flight per warp, not more warps)
         if (PADTAIL) {
             const int4 padq = make_int4(P.p, 0, P.p, 0);
-            auto fetch = [&](int t) -> int4 { return t < w2 ? __ldcs(src + t * 32) : padq; };
+            auto fetch = [&](int t) -> int4 { return t < w2 ? ld_stream(src + t * 32) : padq; };
             int4 n0 = fetch(0), n1 = fetch(1), n2 = fetch(2), n3 = fetch(3);
             for (int t2 = 0; t2 < w2; t2 += 4) {
                 const int4 q0 = n0, q1 = n1, q2 = n2, q3 = n3;
@@ -101,13 +112,13 @@ __global__ void __launch_bounds__(THREADS) k_assign_bounded(const BoundedParams 
             int t2 = 0;
             int4 n0, n1, n2, n3;
             if (w2 >= 4) {
-                n0 = __ldcs(src + 0 * 32); n1 = __ldcs(src + 1 * 32); n2 = __ldcs(src + 2 * 32); n3 = __ldcs(src + 3 * 32);
+                n0 = ld_stream(src + 0 * 32); n1 = ld_stream(src + 1 * 32); n2 = ld_stream(src + 2 * 32); n3 = ld_stream(src + 3 * 32);
             }
             for (; t2 + 4 <= w2; t2 += 4) {
                 const int4 q0 = n0, q1 = n1, q2 = n2, q3 = n3;
                 if (t2 + 8 <= w2) {
-                    n0 = __ldcs(src + (t2 + 4) * 32); n1 = __ldcs(src + (t2 + 5) * 32);
-                    n2 = __ldcs(src + (t2 + 6) * 32); n3 = __ldcs(src + (t2 + 7) * 32);
+                    n0 = ld_stream(src + (t2 + 4) * 32); n1 = ld_stream(src + (t2 + 5) * 32);
+                    n2 = ld_stream(src + (t2 + 6) * 32); n3 = ld_stream(src + (t2 + 7) * 32);
                 }
                 one(q0.x, __int_as_float(q0.y)); one(q0.z, __int_as_float(q0.w));
                 one(q1.x, __int_as_float(q1.y)); one(q1.z, __int_as_float(q1.w));
@@ -115,7 +126,7 @@ __global__ void __launch_bounds__(THREADS) k_assign_bounded(const BoundedParams 
                 one(q3.x, __int_as_float(q3.y)); one(q3.z, __int_as_float(q3.w));
             }
             for (; t2 < w2; ++t2) {
-                const int4 q = __ldcs(src + t2 * 32);
+                const int4 q = ld_stream(src + t2 * 32);
                 one(q.x, __int_as_float(q.y)); one(q.z, __int_as_float(q.w));
             }
         }
@@ -267,6 +278,15 @@ int skm_launch_assign_bounded(skm_ctx *ctx, const skm_dataset *ds, int64_t K, co
     const size_t budget = (size_t)ctx->smem_optin - 2048;
     int64_t ksm = (int64_t)(budget / row_bytes);
     if (ksm > K) ksm = K;
+    // When the table does not fit, the rows left out are gathered through L1 (the stream bypasses it, ld_stream):
+    // leave them the L1 that a 196 KB carve-out keeps free instead of filling shared memory to the brim
+    // (K = 64, p = 1024: 48 rows in shared memory 1.08 ms, 55 rows 1.28 ms, 52 rows 1.46 ms; profiles/r2_bounded_ksm.md)
+    if (ksm < K) ksm = std::min<int64_t>(ksm, (int64_t)((193 * 1024) / row_bytes));
+    if (ksm < 1) ksm = 1;
+    {
+        static const char *e = getenv("SKM_BOUNDED_KSM");          // tuning knob: centres kept in shared memory
+        if (e && atoi(e) > 0 && atoi(e) < ksm) ksm = atoi(e);
+    }
     // leave room for two CTAs per SM when the whole table is small
     const size_t smem = (size_t)ksm * row_bytes;
     P.ksm = (int)ksm;

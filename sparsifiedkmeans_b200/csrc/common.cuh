@@ -64,8 +64,8 @@ struct skm_ctx {
     int          ev_count[SKM_T_SLOTS];
     void        *stream_cache;              // staging buffers of skm_lloyd_step_host, reused across calls
     void       (*stream_cache_free)(void *);
-    void        *blas;                      // lazily loaded cuBLAS binding (DCT sketch only), dct.cu
-    void       (*blas_free)(void *);
+    int64_t      tc_chunks;                 // chunks the tensor-core filter of the second pass ran on (and kept)
+    int64_t      tc_chunks_dropped;         // chunks after which it was switched off (too many uncertain points)
 };
 
 // RAII: records a start event now and a stop event at scope exit when timing is enabled
@@ -283,6 +283,18 @@ int skm_launch_move_changed(skm_ctx *ctx, const skm_dataset *ds, int64_t K, cons
                             const int32_t *changed, const int *nchanged, int64_t nchanged_host, double *acc);
 int skm_launch_argmax(skm_ctx *ctx, int64_t n, const float *dist32, const double *dist64,
                       double *out_val, int64_t *out_idx);
+
+// tcgemm.cu: tensor-core (tcgen05, tf32) filter + exact evaluation of the candidates for the dense second pass
+bool   skm_tc_dense_usable(int64_t p, int64_t K);
+size_t skm_tc_scratch_bytes(int64_t p, int64_t K, int64_t nc);
+int    skm_launch_tc_prep(skm_ctx *ctx, int64_t p, int64_t K, const double *ct /* [p+1][K] */, void *scratch);
+int    skm_launch_dense_assign_tc(skm_ctx *ctx, int64_t p, int64_t nc, int64_t K, const float *x32, void *scratch,
+                                  const float *cmax, int32_t *assign, float *dist, int32_t *flagged, int *nflag);
+
+int    skm_launch_cast_split(skm_ctx *ctx, int64_t nc, int64_t p, int64_t p_pad, const void *x, int x_type, double scale,
+                             float *hi, float *lo);
+int    skm_launch_tc_dct(skm_ctx *ctx, int64_t p, int64_t p_pad, int64_t nc, const float *xh, const float *xl,
+                         const float *mh, const float *ml, float *y, int64_t ldy);
 
 // fwht.cu
 int skm_launch_fwht_f64(skm_ctx *ctx, int64_t m, int64_t n, double *x_inplace,

@@ -8,65 +8,20 @@
 //   T[k][i] = w_k cos(pi (2i+1) k / (2p)),  w_0 = sqrt(1/p), w_k = sqrt(2/p);  idct is T'.
 // For p without a fast power-of-two structure the transform is applied as ONE dense product with
 // the p x p matrix M = T * diag(d) * (1+2eps) (signs and the reference's *(1+2eps), :292, folded in
-// on the host in fp64): a plain library GEMM (cuBLAS, loaded lazily with dlopen so nothing else in
-// the library depends on it), fp32 for the data pipeline, fp64 for the small centre matrices.
-// The hand-written part is what follows the product: the fixed-count row sampler for arbitrary p
-// (Philox, same contract as the Hadamard path) fused with the gather that writes CSC directly, so
-// the mixed dense chunk never leaves the device.
+// on the host in fp64).  The data pipeline runs it on the tensor cores: tcgen05.mma kind::tf32 with both
+// operands split into tf32-exact halves and three products per tile (3xTF32, fp32 accuracy; k_tc_dct in
+// tcgemm.cu, TMA-fed, TMEM accumulators); the small fp64 products of mix/unmix on p x K centre matrices use
+// a plain tiled fp64 kernel.  No library GEMM is involved.  What follows the product is the fixed-count row
+// sampler for arbitrary p (Philox, same contract as the Hadamard path) fused with the gather that writes CSC
+// directly, so the mixed dense chunk never leaves the device.
 #include "common.cuh"
 #include "philox.cuh"
 #include <algorithm>
-#include <dlfcn.h>
 #include <math.h>
 #include <string.h>
 #include <vector>
 
 namespace {
-
-// ---- minimal cuBLAS binding (v2 API) ----------------------------------------------------------
-typedef void *blas_handle;
-typedef int (*fn_create)(blas_handle *);
-typedef int (*fn_destroy)(blas_handle);
-typedef int (*fn_set_stream)(blas_handle, cudaStream_t);
-typedef int (*fn_sgemm)(blas_handle, int, int, int, int, int, const float *, const float *, int, const float *, int,
-                        const float *, float *, int);
-typedef int (*fn_dgemm)(blas_handle, int, int, int, int, int, const double *, const double *, int, const double *, int,
-                        const double *, double *, int);
-struct Blas {
-    void *lib = nullptr;
-    blas_handle h = nullptr;
-    fn_create create = nullptr; fn_destroy destroy = nullptr; fn_set_stream set_stream = nullptr;
-    fn_sgemm sgemm = nullptr; fn_dgemm dgemm = nullptr;
-};
-
-void blas_free(void *p)
-{
-    Blas *b = (Blas *)p;
-    if (!b) return;
-    if (b->h && b->destroy) b->destroy(b->h);
-    delete b;                                             // the library handle stays loaded for the process
-}
-
-int blas_get(skm_ctx *ctx, Blas **out)
-{
-    if (ctx->blas) { *out = (Blas *)ctx->blas; return SKM_OK; }
-    Blas *b = new Blas();
-    const char *names[] = {"libcublas.so.12", "/usr/local/cuda/lib64/libcublas.so.12", "libcublas.so"};
-    for (const char *nm : names) { b->lib = dlopen(nm, RTLD_NOW | RTLD_LOCAL); if (b->lib) break; }
-    if (!b->lib) { delete b; skm_set_error("the DCT sketch needs cuBLAS (libcublas.so.12 not found: %s)", dlerror()); return SKM_ERR_UNSUPPORTED; }
-    b->create = (fn_create)dlsym(b->lib, "cublasCreate_v2");
-    b->destroy = (fn_destroy)dlsym(b->lib, "cublasDestroy_v2");
-    b->set_stream = (fn_set_stream)dlsym(b->lib, "cublasSetStream_v2");
-    b->sgemm = (fn_sgemm)dlsym(b->lib, "cublasSgemm_v2");
-    b->dgemm = (fn_dgemm)dlsym(b->lib, "cublasDgemm_v2");
-    if (!b->create || !b->destroy || !b->set_stream || !b->sgemm || !b->dgemm) { delete b; skm_set_error("cuBLAS symbols missing"); return SKM_ERR_UNSUPPORTED; }
-    if (b->create(&b->h) != 0) { delete b; skm_set_error("cublasCreate failed"); return SKM_ERR_CUDA; }
-    if (b->set_stream(b->h, ctx->stream) != 0) { blas_free(b); skm_set_error("cublasSetStream failed"); return SKM_ERR_CUDA; }
-    ctx->blas = b;
-    ctx->blas_free = blas_free;
-    *out = b;
-    return SKM_OK;
-}
 
 // M (column-major p x p) = T * diag(d) * scale (forward) or its transpose-inverse diag(d) * T' (inverse)
 void dct_matrix(int64_t p, const double *signs, double scale, bool inverse, std::vector<double> &M)
@@ -171,26 +126,46 @@ int launch_sample_gather(skm_ctx *ctx, int64_t p, int64_t n, int64_t m, const fl
     return SKM_OK;
 }
 
-template <typename T>
-__global__ void k_cast_f32(int64_t count, const T *__restrict__ x, float *__restrict__ y)
+// Y (p x n) = M (p x p) X (p x n), all column-major fp64: 32 x 32 output tile per CTA, one output per thread
+__global__ void __launch_bounds__(1024) k_dgemm_tile(int64_t p, int64_t n, const double *__restrict__ M,
+                                                     const double *__restrict__ X, double *__restrict__ Y)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < count; i += stride) y[i] = (float)x[i];
+    __shared__ double Ms[32][33], Xs[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t k0 = (int64_t)blockIdx.x * 32, j0 = (int64_t)blockIdx.y * 32;
+    double acc = 0.0;
+    for (int64_t i0 = 0; i0 < p; i0 += 32) {
+        // Ms[ii][kk] = M[k0+kk][i0+ii] (coalesced along k), Xs[jj][ii] = X[i0+ii][j0+jj] (coalesced along i)
+        Ms[ty][tx] = (k0 + tx < p && i0 + ty < p) ? M[(i0 + ty) * p + k0 + tx] : 0.0;
+        Xs[ty][tx] = (i0 + tx < p && j0 + ty < n) ? X[(j0 + ty) * p + i0 + tx] : 0.0;
+        __syncthreads();
+#pragma unroll 8
+        for (int ii = 0; ii < 32; ++ii) acc = fma(Ms[ii][tx], Xs[ty][ii], acc);
+        __syncthreads();
+    }
+    if (k0 + tx < p && j0 + ty < n) Y[(j0 + ty) * p + k0 + tx] = acc;
+}
+
+// tf32 (10 explicit mantissa bits) rounding of a float on the host
+float tf32_round_host(float f)
+{
+    uint32_t b;
+    memcpy(&b, &f, 4);
+    if ((b & 0x7f800000u) != 0x7f800000u) b = (b + 0x00000fffu + ((b >> 13) & 1u)) & 0xffffe000u;
+    memcpy(&f, &b, 4);
+    return f;
 }
 
 }  // namespace
 
 // y = dct(D .* x) (inverse == 0) or y = D .* idct(x) (inverse != 0) for a dense p x n HOST matrix,
-// fp64 (cublasDgemm).  signs may be NULL.
+// fp64 (k_dgemm_tile).  signs may be NULL.
 extern "C" int skm_dct_mix(skm_ctx *ctx, int64_t p, int64_t n, const double *x, const double *signs, int inverse, double *y)
 {
     SKM_REQUIRE(ctx && (n == 0 || (x && y)), "NULL argument");
     SKM_CUDA(cudaSetDevice(ctx->device));
     SKM_REQUIRE(p >= 1 && p <= 46340 && n >= 0 && n <= 2147483647LL, "bad dimensions");
     if (n == 0) return SKM_OK;
-    Blas *b;
-    SKM_TRY(blas_get(ctx, &b));
     std::vector<double> M;
     dct_matrix(p, signs, 1.0, inverse != 0, M);
     DevBuf dM, dX, dY;
@@ -199,13 +174,15 @@ extern "C" int skm_dct_mix(skm_ctx *ctx, int64_t p, int64_t n, const double *x, 
     SKM_TRY(dX.alloc(sizeof(double) * p * chunk));
     SKM_TRY(dY.alloc(sizeof(double) * p * chunk));
     SKM_CUDA(cudaMemcpyAsync(dM.ptr, M.data(), sizeof(double) * p * p, cudaMemcpyHostToDevice, ctx->stream));
-    const double one = 1.0, zero = 0.0;
     for (int64_t j0 = 0; j0 < n; j0 += chunk) {
         const int64_t nc = std::min(chunk, n - j0);
         SKM_CUDA(cudaMemcpyAsync(dX.ptr, x + j0 * p, sizeof(double) * p * nc, cudaMemcpyHostToDevice, ctx->stream));
-        if (b->dgemm(b->h, 0, 0, (int)p, (int)nc, (int)p, &one, dM.as<double>(), (int)p, dX.as<double>(), (int)p, &zero,
-                     dY.as<double>(), (int)p) != 0) { skm_set_error("cublasDgemm failed"); return SKM_ERR_CUDA; }
-        ctx->launches++;
+        for (int64_t c0 = 0; c0 < nc; c0 += 65535 * 32) {            // grid.y limit
+            const int64_t cc = std::min<int64_t>(nc - c0, 65535 * 32);
+            k_dgemm_tile<<<dim3((unsigned)((p + 31) / 32), (unsigned)((cc + 31) / 32)), 1024, 0, ctx->stream>>>(
+                p, cc, dM.as<double>(), dX.as<double>() + c0 * p, dY.as<double>() + c0 * p);
+            SKM_CHECK_LAUNCH(ctx);
+        }
         SKM_CUDA(cudaMemcpyAsync(y + j0 * p, dY.ptr, sizeof(double) * p * nc, cudaMemcpyDeviceToHost, ctx->stream));
         SKM_CUDA(cudaStreamSynchronize(ctx->stream));
     }
@@ -226,8 +203,6 @@ extern "C" int skm_dataset_from_dense_host_dct(skm_ctx *ctx, int64_t p, int64_t 
     SKM_REQUIRE(x_type == SKM_F32 || x_type == SKM_F64, "x_type must be SKM_F32 or SKM_F64");
     SKM_REQUIRE(p >= 1 && p <= 32768 && n >= 0, "need 1 <= p <= 32768");
     SKM_REQUIRE(m >= 1 && m <= p, "need 1 <= m <= p");
-    Blas *b;
-    SKM_TRY(blas_get(ctx, &b));
     const size_t xs = x_type == SKM_F32 ? 4 : 8;
     if (chunk_cols <= 0) chunk_cols = std::max<int64_t>(1, (int64_t)(256LL << 20) / (int64_t)(p * 4));
     chunk_cols = std::min<int64_t>(chunk_cols, std::max<int64_t>(n, 1));
@@ -235,11 +210,20 @@ extern "C" int skm_dataset_from_dense_host_dct(skm_ctx *ctx, int64_t p, int64_t 
 
     std::vector<double> M;
     dct_matrix(p, signs, 1.0 + 2.0 * 2.220446049250313e-16, false, M);
-    std::vector<float> M32((size_t)p * p);
-    for (size_t i = 0; i < M32.size(); ++i) M32[i] = (float)M[i];
+    // tf32-exact halves of M, row k (output row) contiguous over the input index, rows padded to a multiple of 4
+    // floats (TMA needs 16-byte row strides): M = M_hi + M_lo to ~22 bits
+    const int64_t p_pad = (p + 3) & ~(int64_t)3;
+    std::vector<float> Mh((size_t)p * p_pad, 0.f), Ml((size_t)p * p_pad, 0.f);
+    for (int64_t i = 0; i < p; ++i)
+        for (int64_t k = 0; k < p; ++k) {
+            const double v = M[(size_t)i * p + k];
+            const float h = tf32_round_host((float)v);
+            Mh[(size_t)k * p_pad + i] = h;
+            Ml[(size_t)k * p_pad + i] = tf32_round_host((float)(v - (double)h));
+        }
 
     int64_t *colptr = nullptr; int32_t *rowidx = nullptr; float *val = nullptr;
-    DevBuf dM, raw[2], x32, y32, drows, bad;
+    DevBuf dMh, dMl, raw[2], xhi, xlo, y32, drows, bad;
     int rc = SKM_OK;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t up[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
@@ -249,11 +233,13 @@ extern "C" int skm_dataset_from_dense_host_dct(skm_ctx *ctx, int64_t p, int64_t 
             cudaMalloc((void **)&val, sizeof(float) * std::max<int64_t>(n * m, 1)) != cudaSuccess) {
             skm_set_error("out of device memory for the sampled matrix"); cudaGetLastError(); rc = SKM_ERR_NOMEM; break;
         }
-        if ((rc = dM.alloc(sizeof(float) * p * p)) || (rc = raw[0].alloc(xs * p * chunk_cols)) || (rc = raw[1].alloc(xs * p * chunk_cols)) ||
+        if ((rc = dMh.alloc(sizeof(float) * p * p_pad)) || (rc = dMl.alloc(sizeof(float) * p * p_pad)) ||
+            (rc = raw[0].alloc(xs * p * chunk_cols)) || (rc = raw[1].alloc(xs * p * chunk_cols)) ||
+            (rc = xhi.alloc(sizeof(float) * p_pad * chunk_cols)) || (rc = xlo.alloc(sizeof(float) * p_pad * chunk_cols)) ||
             (rc = y32.alloc(sizeof(float) * p * chunk_cols)) || (rc = bad.alloc(sizeof(int)))) break;
-        if (x_type == SKM_F64 && (rc = x32.alloc(sizeof(float) * p * chunk_cols))) break;
         if (rows_host && (rc = drows.alloc(sizeof(int32_t) * m * chunk_cols))) break;
-        cudaMemcpyAsync(dM.ptr, M32.data(), sizeof(float) * p * p, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(dMh.ptr, Mh.data(), sizeof(float) * p * p_pad, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(dMl.ptr, Ml.data(), sizeof(float) * p * p_pad, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemsetAsync(bad.ptr, 0, sizeof(int), ctx->stream);
         cudaMemsetAsync(colptr, 0, sizeof(int64_t), ctx->stream);
         if (cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking) != cudaSuccess) { skm_set_error("cudaStreamCreate failed"); rc = SKM_ERR_CUDA; break; }
@@ -266,25 +252,17 @@ extern "C" int skm_dataset_from_dense_host_dct(skm_ctx *ctx, int64_t p, int64_t 
             cudaEventRecord(up[c & 1], copy_stream);
         };
         if (nchunks > 0) issue(0);
-        const float one = 1.f, zero = 0.f;
         for (int64_t c = 0; c < nchunks && rc == SKM_OK; ++c) {
             if (c + 1 < nchunks) issue(c + 1);
             const int64_t j0 = c * chunk_cols, nc = std::min(chunk_cols, n - j0);
             cudaStreamWaitEvent(ctx->stream, up[c & 1], 0);
-            const float *xin = (const float *)raw[c & 1].ptr;
-            if (x_type == SKM_F64) {
-                const int64_t blocks = std::min<int64_t>((p * nc + 255) / 256, (int64_t)ctx->sm_count * 32);
-                k_cast_f32<double><<<(unsigned)blocks, 256, 0, ctx->stream>>>(p * nc, (const double *)raw[c & 1].ptr, x32.as<float>());
-                ctx->launches++;
-                xin = x32.as<float>();
-            }
             {
                 SkmTimed t(ctx, SKM_T_FWHT);
-                if (b->sgemm(b->h, 0, 0, (int)p, (int)nc, (int)p, &one, dM.as<float>(), (int)p, xin, (int)p, &zero, y32.as<float>(), (int)p) != 0) {
-                    skm_set_error("cublasSgemm failed"); rc = SKM_ERR_CUDA; break;
-                }
-                ctx->launches++;
+                // fl32(x) = x_hi + x_lo (tf32-exact halves), then Y = M_hi X_hi + M_hi X_lo + M_lo X_hi on the tensor cores
+                if ((rc = skm_launch_cast_split(ctx, nc, p, p_pad, raw[c & 1].ptr, x_type, 1.0, xhi.as<float>(), xlo.as<float>()))) break;
                 cudaEventRecord(freed[c & 1], ctx->stream);
+                if ((rc = skm_launch_tc_dct(ctx, p, p_pad, nc, xhi.as<float>(), xlo.as<float>(), dMh.as<float>(), dMl.as<float>(),
+                                            y32.as<float>(), p))) break;
                 if (rows_host) cudaMemcpyAsync(drows.ptr, rows_host + j0 * m, sizeof(int32_t) * m * nc, cudaMemcpyHostToDevice, ctx->stream);
                 rc = launch_sample_gather(ctx, p, nc, m, y32.as<float>(), rows_host ? drows.as<int32_t>() : nullptr, seed, col0 + j0,
                                           nullptr, rowidx + j0 * m, val + j0 * m, nullptr, bad.as<int>());

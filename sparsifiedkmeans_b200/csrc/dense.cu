@@ -310,7 +310,7 @@ DensePlan dense_plan(const skm_ctx *ctx, int64_t p, int64_t K)
 static int dense_chunk(skm_ctx *ctx, int64_t p, int64_t nc, int64_t K, const DensePlan &dp, const float *x32,
                        const void *xraw, int x_type, double scale, const float *table, const float *cmax,
                        const double *ct, int32_t *assign, float *dist, int32_t *flagged, int *nflag,
-                       const int32_t *assign_in, double *S)
+                       const int32_t *assign_in, double *S, void *tc_scratch, int64_t *tc_state)
 {
     if (nc == 0) return SKM_OK;
     if (assign_in) {
@@ -330,6 +330,22 @@ static int dense_chunk(skm_ctx *ctx, int64_t p, int64_t nc, int64_t K, const Den
     }
     if (!assign) return SKM_OK;
     SKM_CUDA(cudaMemsetAsync(nflag, 0, sizeof(int), ctx->stream));
+    bool done = false;
+    if (tc_scratch && tc_state[0] >= 0) {
+        // tensor-core filter + exact evaluation of its candidates (tcgemm.cu).  It pays off when the filter leaves
+        // one or two candidates per point; on data without structure most points end up flagged, and after one
+        // such chunk the CUDA-core kernel takes over for the rest of the call.
+        SKM_TRY(skm_launch_dense_assign_tc(ctx, p, nc, K, x32, tc_scratch, cmax, assign, dist, flagged, nflag));
+        int nf = 0;
+        SKM_CUDA(cudaMemcpyAsync(&nf, nflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        SKM_CUDA(cudaStreamSynchronize(ctx->stream));
+        tc_state[1] += 1;
+        if (nf > nc / 8) {
+            tc_state[0] = -1;                                       // stop using the filter for this call
+            ctx->tc_chunks_dropped += 1;
+            SKM_CUDA(cudaMemsetAsync(nflag, 0, sizeof(int), ctx->stream));
+        } else { done = true; ctx->tc_chunks += 1; }
+    }
     const double u = 5.9604644775390625e-08, m = (double)p;
     DenseParams P;
     P.x = x32; P.p = p; P.n = nc; P.table = table; P.ks = dp.ks; P.kc_unused = dp.kc; P.nchunks = dp.nchunks; P.K = (int)K;
@@ -339,13 +355,14 @@ static int dense_chunk(skm_ctx *ctx, int64_t p, int64_t nc, int64_t K, const Den
     P.gb_unit = (float)(2.02 * u * sqrt(m));
     P.ge_unit = (float)(2.1 * u * u * m);
     P.cmax = cmax; P.assign = assign; P.dist = dist; P.flagged = flagged; P.nflag = nflag;
-    int rc;
-    switch (dp.kc) {
-        case 4:  rc = launch_dense_assign<4, 4>(ctx, P, dp.smem); break;
-        case 8:  rc = launch_dense_assign<8, 4>(ctx, P, dp.smem); break;
-        case 12: rc = launch_dense_assign<12, 4>(ctx, P, dp.smem); break;
-        default: rc = launch_dense_assign<16, 4>(ctx, P, dp.smem); break;
-    }
+    int rc = SKM_OK;
+    if (!done)
+        switch (dp.kc) {
+            case 4:  rc = launch_dense_assign<4, 4>(ctx, P, dp.smem); break;
+            case 8:  rc = launch_dense_assign<8, 4>(ctx, P, dp.smem); break;
+            case 12: rc = launch_dense_assign<12, 4>(ctx, P, dp.smem); break;
+            default: rc = launch_dense_assign<16, 4>(ctx, P, dp.smem); break;
+        }
     if (rc != SKM_OK) return rc;
     int64_t blocks = std::min<int64_t>((nc * 32 + 255) / 256, (int64_t)ctx->sm_count * 8);
     if (x_type == SKM_F32)
@@ -378,7 +395,8 @@ extern "C" int skm_second_pass(skm_ctx *ctx, int64_t p, int64_t n, const void *x
     const bool need_cast = !(x_type == SKM_F32 && scale == 1.0 && x_on_device);
 
     DensePlan dp = dense_plan(ctx, p, K);
-    DevBuf raw[2], x32, dcent, ct, table, cmax, d_assign, d_dist, flagged, nflag, d_in, S, counts, badflag;
+    DevBuf raw[2], x32, dcent, ct, table, cmax, d_assign, d_dist, flagged, nflag, d_in, S, counts, badflag, tc_scratch;
+    int64_t tc_state[2] = {0, 0};                               // [0] < 0: filter switched off; [1] chunks it ran on
     if (want_assign) {
         SKM_TRY(dcent.alloc(sizeof(double) * p * K));
         SKM_TRY(ct.alloc(sizeof(double) * (p + 1) * K));
@@ -394,6 +412,10 @@ extern "C" int skm_second_pass(skm_ctx *ctx, int64_t p, int64_t n, const void *x
         fp.kc = dp.kc; fp.ks = dp.ks; fp.nchunks = dp.nchunks; fp.smem = 0; fp.threads = 256; fp.global_table = false;
         fp.mode64 = false; fp.dual8 = false; fp.layout = 0; fp.boff = 0; fp.rows = p + 1;
         SKM_TRY(skm_launch_build_table(ctx, p, K, ct.as<double>(), fp, table.as<float>(), cmax.as<float>()));
+        if (skm_tc_dense_usable(p, K)) {
+            SKM_TRY(tc_scratch.alloc(skm_tc_scratch_bytes(p, K, chunk_cols)));
+            SKM_TRY(skm_launch_tc_prep(ctx, p, K, ct.as<double>(), tc_scratch.ptr));
+        }
     }
     if (want_sums) {
         SKM_TRY(d_in.alloc(sizeof(int32_t) * std::max<int64_t>(n, 1)));
@@ -450,7 +472,8 @@ extern "C" int skm_second_pass(skm_ctx *ctx, int64_t p, int64_t n, const void *x
             SkmTimed t(ctx, SKM_T_ASSIGN);
             rc = dense_chunk(ctx, p, nc, K, dp, xf, xr, x_type, scale, table.as<float>(), cmax.as<float>(), ct.as<double>(),
                              want_assign ? d_assign.as<int32_t>() + j0 : nullptr, want_assign ? d_dist.as<float>() + j0 : nullptr,
-                             flagged.as<int32_t>(), nflag.as<int>(), want_sums ? d_in.as<int32_t>() + j0 : nullptr, S.as<double>());
+                             flagged.as<int32_t>(), nflag.as<int>(), want_sums ? d_in.as<int32_t>() + j0 : nullptr, S.as<double>(),
+                             tc_scratch.ptr, tc_state);
         }
         if (rc == SKM_OK && want_assign)
             cudaMemcpyAsync(nflag_log.as<int>() + c, nflag.ptr, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream);

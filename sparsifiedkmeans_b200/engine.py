@@ -61,6 +61,12 @@ class Context:
     def synchronize(self):
         check(self._lib.skm_ctx_sync(self.handle))
 
+    def tc_chunks(self) -> tuple[int, int]:
+        """(chunks of second_pass handled by the tensor-core filter, chunks after which it was switched off)."""
+        a, b = C.c_int64(), C.c_int64()
+        check(self._lib.skm_ctx_tc_chunks(self.handle, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     TIMING_SLOTS = ("assign", "recheck", "accumulate", "finalize", "prep", "fwht", "kpp", "upload")
 
     def timing_enable(self, on: bool = True):

@@ -344,7 +344,9 @@ def test_bounded_assignment_equals_full_evaluation(ctx, kind, p, n, m, K):
         flagged.append(B.last_assign_flagged())
         if sa.dff == 0.0 and it > 3:
             break
-    assert any(f >= 0 for f in flagged[1:])                       # the bounded pass ran
+    if kind == "mixture":
+        assert any(f >= 0 for f in flagged[1:])                       # the bounded pass ran
+    # (unstructured data: the a-priori test may rightly decide that no bounded pass is worth launching)
     if sa.dff == 0.0:
         # the centres stopped moving in the last update: from the next pass on every bound holds
         for _ in range(12):                                       # a failed bounded pass is followed by a back-off

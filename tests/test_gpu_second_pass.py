@@ -108,3 +108,32 @@ def test_dense_operator_and_kmeans_two_pass_outputs(ctx):
     assert np.all(dists.min(axis=1) < 0.05 * np.linalg.norm(truth, axis=0).mean())
     six = kmeans_sparsified(X.T.copy(), 4, Sparsify=True, SparsityLevel=0.25, Seed=4, nargout=6, Context=ctx)
     assert len(six) == 6
+
+
+@pytest.mark.parametrize("p,n,K,sigma", [(256, 50_000, 64, 0.3), (1024, 20_000, 64, 0.5), (96, 30_000, 17, 0.2),
+                                         (784, 8_000, 100, 0.3), (2048, 3_000, 256, 0.3), (64, 40_000, 16, 1.0)])
+def test_tensor_core_filter_keeps_the_reference_winners(ctx, p, n, K, sigma):
+    """K >= 16: the distance product runs on the tensor cores (tcgen05, tf32) as a filter and the candidates are
+    evaluated exactly (csrc/tcgemm.cu).  Several 128-point tiles per CTA (persistent loop, double-buffered TMEM
+    accumulator), p not a multiple of the 32-float k-block, K not a multiple of 16, several chunks."""
+    from sparsifiedkmeans_b200 import second_pass
+    X, c, lab = _mixture(p, n, K, seed=p + K, sigma=sigma, dtype=np.float32)
+    kept0, dropped0 = ctx.tc_chunks()
+    res = second_pass(X, centers=c, assign_in=None, scale=1.0, chunk_cols=max(n // 3, 1), ctx=ctx)
+    kept1, dropped1 = ctx.tc_chunks()
+    assert (kept1 - kept0) + (dropped1 - dropped0) >= 1, "the tensor-core path did not run"
+    _check_assign(np.asarray(X, dtype=np.float64), c, res["assign"], res["dist"])
+    if sigma <= 0.5:
+        assert kept1 - kept0 >= 3 and res["n_rechecked"] <= n // 8     # clustered data: the filter certifies
+
+
+def test_tensor_core_filter_falls_back_on_unstructured_data(ctx):
+    from sparsifiedkmeans_b200 import second_pass
+    rng = np.random.default_rng(11)
+    p, n, K = 128, 20_000, 32
+    X = rng.standard_normal((p, n)).astype(np.float32)
+    c = 0.1 * rng.standard_normal((p, K))
+    c[:, 9] = c[:, 3]                                            # exact duplicate: ties go to the lower index
+    res = second_pass(X, centers=c, scale=1.0, chunk_cols=5000, ctx=ctx)
+    _check_assign(np.asarray(X, dtype=np.float64), c, res["assign"], res["dist"], n_tie_ok=n)
+    assert not np.any(res["assign"] == 10)

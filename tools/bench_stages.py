@@ -122,7 +122,7 @@ def main():
     n = 250_000 if args.quick else 1_250_000
     if args.only_dense:
         n = 1000
-    colptr, rowidx, val, mu, start = bench.gen_shard_device(dev, n, 784, 78, 100, col0=0)
+    colptr, rowidx, val, mu, start = bench.gen_shard_device(dev, n, 784, 78, 100, col0=0, ctx=ctx)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     ds = Dataset.from_device_csc(784, n, colptr.data_ptr(), SKM_I64, rowidx.data_ptr(), SKM_I32, val.data_ptr(), SKM_F32,
@@ -172,6 +172,29 @@ def main():
             print(json.dumps(out), flush=True)
         del x, mu, lab
         torch.cuda.empty_cache()
+
+    # ---- DCT sketch: dense host matrix -> 3xTF32 product on the tensor cores -> row sample ----
+    for p in (784, 1000):
+        n = 200_000 if args.quick or args.only_dense else 1_000_000
+        Xh = torch.randn(n, p, dtype=torch.float32).pin_memory().numpy().T        # (p, n) view of pinned memory
+        d = np.sign(np.random.default_rng(0).standard_normal(p)); d[d == 0] = 1
+        m = max(1, round(0.1 * p))
+        t0 = time.perf_counter()
+        ds = Dataset.from_dense_host_dct(Xh, d, m, seed=5, ctx=ctx)
+        ctx.synchronize()
+        ds.close()
+        ctx.timing_enable(True); ctx.timing_read()
+        t0 = time.perf_counter()
+        ds = Dataset.from_dense_host_dct(Xh, d, m, seed=5, ctx=ctx)
+        ctx.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        k_ms = ctx.timing_read()["fwht"][0]; ctx.timing_enable(False)
+        ds.close()
+        flops = 3 * 2.0 * p * p * n
+        print(json.dumps({"stage": "DCT sketch: split + 3xTF32 tcgen05 product + row sample (from pinned host memory)", "p": p, "n": n,
+                          "m": m, "wall_ms": wall, "device_ms_split_gemm_sample": k_ms, "tf32_TFLOPs_incl_split_and_sample": flops / k_ms / 1e9,
+                          "pcie_GBps": 4.0 * p * n / 1e9 / wall * 1e3}), flush=True)
+        del Xh
 
 
 if __name__ == "__main__":

@@ -214,8 +214,10 @@ struct Timer {
     float stop() { cudaEventRecord(b); cudaEventSynchronize(b); float ms; cudaEventElapsedTime(&ms, a, b); return ms; }
 };
 
+static bool g_once = false;       // profile mode: every variant runs exactly once (ncu captures)
 template <typename F> static float bench(F &&f, int reps = 5)
 {
+    if (g_once) { Timer t; t.start(); f(); float ms = t.stop(); CK(cudaGetLastError()); return ms; }
     f(); CK(cudaDeviceSynchronize());
     Timer t; t.start();
     for (int i = 0; i < reps; ++i) f();
@@ -237,6 +239,7 @@ int main(int argc, char **argv)
 {
     const int64_t n = argc > 1 ? atoll(argv[1]) : 12500000;
     const int mode = argc > 2 ? atoi(argv[2]) : 0;
+    g_once = argc > 3 && atoi(argv[3]) != 0;
     const int64_t nslices = n / 32;
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
     const int sms = prop.multiProcessorCount;
