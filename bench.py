@@ -685,14 +685,7 @@ def run_ours(args):
         else:
             e2e = e2e_i32
 
-    # ------------------------------------------------------------------ trajectory on the headline shape
     legs = {}
-    if not args.no_extra:
-        try:
-            legs["trajectory_config2"] = trajectory_leg(rig, ds, cfg, n, max_iter=args.traj_iters)
-        except Exception as e:
-            legs["trajectory_config2"] = {"error": repr(e)}
-
     # Whole-job variant (reported beside the per-step number above, never instead of it): what one
     # kmeans_sparsified call does with the handle API of INTEGRATION.md level 2 -- upload X from pinned host
     # memory ONCE, build the device images, run `steps` Lloyd iterations (centres in, statistics out, every
@@ -743,6 +736,16 @@ def run_ours(args):
     # ------------------------------------------------------------------ the other driver-visible legs
     if not args.no_extra:
         xs = max(5, args.steps // 2)
+        # trajectory on the headline shape (the shard is regenerated: same seed, same matrix)
+        try:
+            ds_t, _, _, _ = gen_dataset(ctx, dev, n, p, m, K, col0=rank * n, kind="mixture")
+            try:
+                legs["trajectory_config2"] = trajectory_leg(rig, ds_t, cfg, n, max_iter=args.traj_iters)
+            finally:
+                ds_t.close()
+        except Exception as e:
+            legs["trajectory_config2"] = {"error": repr(e)}
+        torch.cuda.empty_cache()
         # (c) unstructured near-tie workload at the headline shape
         try:
             un, Xu = run_lloyd(rig, cfg, n, "unstructured", xs, 3, want_parity=not args.no_parity, keep=True)

@@ -41,20 +41,54 @@ __global__ void k_csr_scatter(int64_t p, int64_t n, int64_t ntiles, const int64_
                               const int32_t *__restrict__ rowidx, const VT *__restrict__ val,
                               const int64_t *__restrict__ offsets, int2 *__restrict__ csr)
 {
-    extern __shared__ int hist[];                    // per-row cursor inside this tile
+    // per row: the tile's base offset (64-bit) with the cursor in the same word, so one shared-memory atomic
+    // returns the final position (the first version chained shared atomic -> global load of the offset -> store)
+    extern __shared__ unsigned long long cur[];
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int i = threadIdx.x; i < p; i += blockDim.x) cur[i] = (unsigned long long)offsets[(int64_t)i * ntiles + tile];
+        __syncthreads();
+        const int64_t j0 = tile * CSR_TILE, j1 = min(n, j0 + CSR_TILE);
+        // one warp per column keeps the column index available without a search; two columns per trip for
+        // independent work in flight
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        for (int64_t j = j0 + warp; j < j1; j += 2 * nwarps) {
+            const int64_t jb = j + nwarps;
+            const int64_t t0 = colptr[j], t1 = colptr[j + 1];
+            int64_t u0 = 0, u1 = 0;
+            if (jb < j1) { u0 = colptr[jb]; u1 = colptr[jb + 1]; }
+            int64_t t = t0 + lane, u = u0 + lane;
+            while (t < t1 || u < u1) {
+                int ra = -1, rb = -1, xa = 0, xb = 0;
+                if (t < t1) { ra = rowidx[t]; xa = __float_as_int((float)val[t]); }
+                if (u < u1) { rb = rowidx[u]; xb = __float_as_int((float)val[u]); }
+                if (ra >= 0) csr[atomicAdd(&cur[ra], 1ULL)] = make_int2((int)j, xa);
+                if (rb >= 0) csr[atomicAdd(&cur[rb], 1ULL)] = make_int2((int)jb, xb);
+                t += 32; u += 32;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// fallback for very long columns' worth of rows (p * 8 bytes would not fit in shared memory): 32-bit cursors and the
+// tile offsets read from global memory per entry
+template <typename VT>
+__global__ void k_csr_scatter_big(int64_t p, int64_t n, int64_t ntiles, const int64_t *__restrict__ colptr,
+                                  const int32_t *__restrict__ rowidx, const VT *__restrict__ val,
+                                  const int64_t *__restrict__ offsets, int2 *__restrict__ csr)
+{
+    extern __shared__ int hist[];
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int i = threadIdx.x; i < p; i += blockDim.x) hist[i] = 0;
         __syncthreads();
         const int64_t j0 = tile * CSR_TILE, j1 = min(n, j0 + CSR_TILE);
-        // one warp per column keeps the column index available without a search
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
         for (int64_t j = j0 + warp; j < j1; j += nwarps) {
             const int64_t t0 = colptr[j], t1 = colptr[j + 1];
             for (int64_t t = t0 + lane; t < t1; t += 32) {
                 const int r = rowidx[t];
                 const int slot = atomicAdd(&hist[r], 1);
-                const int64_t pos = offsets[(int64_t)r * ntiles + tile] + slot;
-                csr[pos] = make_int2((int)j, __float_as_int((float)val[t]));
+                csr[offsets[(int64_t)r * ntiles + tile] + slot] = make_int2((int)j, __float_as_int((float)val[t]));
             }
         }
         __syncthreads();
@@ -111,9 +145,16 @@ int skm_build_csr(skm_dataset *ds)
     ds->device_bytes += (int64_t)sizeof(int2) * nnz + (int64_t)sizeof(int64_t) * (p + 1);
     k_csr_rowptr<<<(unsigned)((p + 1 + 255) / 256), 256, 0, ctx->stream>>>(p, ntiles, nnz, offsets.as<int64_t>(), ds->rowptr);
     SKM_CHECK_LAUNCH(ctx);
-    SKM_CUDA(cudaFuncSetAttribute(k_csr_scatter<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_csr_scatter<float><<<(unsigned)blocks, 512, smem, ctx->stream>>>(p, n, ntiles, ds->colptr, ds->rowidx,
-                                                                      (const float *)ds->val, offsets.as<int64_t>(), ds->csr);
+    const size_t smem_sc = (size_t)p * sizeof(unsigned long long);
+    if (smem_sc <= (size_t)ctx->smem_optin) {
+        SKM_CUDA(cudaFuncSetAttribute(k_csr_scatter<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sc));
+        k_csr_scatter<float><<<(unsigned)blocks, 512, smem_sc, ctx->stream>>>(p, n, ntiles, ds->colptr, ds->rowidx,
+                                                                          (const float *)ds->val, offsets.as<int64_t>(), ds->csr);
+    } else {
+        SKM_CUDA(cudaFuncSetAttribute(k_csr_scatter_big<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_csr_scatter_big<float><<<(unsigned)blocks, 512, smem, ctx->stream>>>(p, n, ntiles, ds->colptr, ds->rowidx,
+                                                                           (const float *)ds->val, offsets.as<int64_t>(), ds->csr);
+    }
     SKM_CHECK_LAUNCH(ctx);
     // host copy of the row pointers: K2's work list is built from it
     ds->h_rowptr = (int64_t *)malloc(sizeof(int64_t) * (p + 1));

@@ -390,7 +390,9 @@ extern "C" int skm_second_pass(skm_ctx *ctx, int64_t p, int64_t n, const void *x
     const bool want_sums = centers_out != nullptr;
     if (n_rechecked) *n_rechecked = 0;
     const size_t xs = x_type == SKM_F32 ? 4 : 8;
-    if (chunk_cols <= 0) chunk_cols = std::max<int64_t>(1, (int64_t)(256LL << 20) / (int64_t)(p * 4));
+    // chunks of ~256 MB when the data crosses PCIe (double-buffered staging); resident data needs no staging, and
+    // larger launches cut the tail of the persistent tensor-core kernel (a wave of 148 CTAs x 128 points)
+    if (chunk_cols <= 0) chunk_cols = std::max<int64_t>(1, (int64_t)((x_on_device ? 2048LL : 256LL) << 20) / (int64_t)(p * 4));
     chunk_cols = std::min<int64_t>(chunk_cols, std::max<int64_t>(n, 1));
     const bool need_cast = !(x_type == SKM_F32 && scale == 1.0 && x_on_device);
 

@@ -8,6 +8,7 @@
 // the fp32 one is the fast path (with the sign flip fused on load, the 1/sqrt(p2) division
 // fused on store, and optionally the fixed-count row sample fused on store).
 #include "common.cuh"
+#include <stdlib.h>
 #include "philox.cuh"
 
 namespace {
@@ -232,6 +233,90 @@ __global__ void __launch_bounds__(32 * W) k_fwht_cta(int64_t n, float *__restric
     }
 }
 
+// Same transform with the NEXT column prefetched by the TMA while the current one is finished: a column of
+// p2 >= 8192 fills the CTA's shared memory, so only one is resident per SM and, without this, nothing is in flight
+// between the last load of a column and the first load of the next (ncu: profiles/r2_fwht.md).  The column buffer
+// is only busy during the one exchange between the lane stages and the warp stages; as soon as every thread has
+// read its operands back, one thread issues cp.async.bulk for the next column into the same buffer (mbarrier
+// complete_tx), which then overlaps the last butterflies and the stores of the current column.
+template <int W>
+__global__ void __launch_bounds__(32 * W) k_fwht_cta_tma(int64_t n, float *__restrict__ x, const float *__restrict__ signs, float divide_by)
+{
+    extern __shared__ __align__(128) unsigned char fc_raw[];
+    float *s = reinterpret_cast<float *>(fc_raw);
+    __shared__ uint64_t bar;
+    constexpr int T = 32 * W, P2 = 1024 * W, G = 32 / W;
+    constexpr uint32_t BYTES = P2 * 4;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
+    const uint32_t s_a = (uint32_t)__cvta_generic_to_shared(s);
+    auto prefetch = [&](int64_t col) {                        // one thread
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic reads of the buffer come first
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(BYTES) : "memory");
+        const char *src = reinterpret_cast<const char *>(x + col * P2);
+        for (uint32_t off = 0; off < BYTES; off += 32768) {
+            const uint32_t sz = BYTES - off < 32768u ? BYTES - off : 32768u;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(s_a + off), "l"(src + off), "r"(sz), "r"(bar_a) : "memory");
+        }
+    };
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && (int64_t)blockIdx.x < n) prefetch(blockIdx.x);
+    uint32_t parity = 0;
+    for (int64_t col = blockIdx.x; col < n; col += gridDim.x) {
+        float *g = x + col * P2;
+        {
+            uint32_t done = 0, spins = 0;
+            while (!done) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(bar_a), "r"(parity) : "memory");
+                if (!done && ++spins > (1u << 26)) __trap();
+            }
+            parity ^= 1;
+        }
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int idx = (w << 10) | (j << 5) | lane;
+            float t = s[idx];
+            if (signs) t *= __ldg(signs + idx);
+            v[j] = t;
+        }
+        wht_regs_and_lanes<32>(v, lane);
+        __syncthreads();                                       // everyone has read the raw column
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s[(w << 10) | (j << 5) | lane] = v[j];
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+#pragma unroll
+            for (int jw = 0; jw < W; ++jw) v[i * W + jw] = s[(jw << 10) | (i * T + threadIdx.x)];
+        }
+        __syncthreads();                                       // the buffer is free again
+        if (threadIdx.x == 0 && col + gridDim.x < n) prefetch(col + gridDim.x);
+#pragma unroll
+        for (int h = 1; h < W; h <<= 1) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                if (!((q % W) & h)) { const float a = v[q], b = v[q + h]; v[q] = a + b; v[q + h] = a - b; }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+#pragma unroll
+            for (int jw = 0; jw < W; ++jw) {
+                float t = v[i * W + jw];
+                if (divide_by != 0.f) t = __fdiv_rn(t, divide_by);
+                __stcs(g + ((jw << 10) | (i * T + threadIdx.x)), t);
+            }
+        }
+    }
+}
+
 template <int E>
 int launch_fwht_warp(skm_ctx *ctx, int64_t n, float *x, const float *signs, float divide_by)
 {
@@ -247,7 +332,8 @@ template <int W>
 int launch_fwht_cta(skm_ctx *ctx, int64_t n, float *x, const float *signs, float divide_by)
 {
     const size_t smem = (size_t)1024 * W * sizeof(float);
-    auto kern = k_fwht_cta<W>;
+    static const bool no_tma = getenv("SKM_FWHT_NO_TMA") != nullptr;
+    auto kern = (W >= 8 && !no_tma) ? k_fwht_cta_tma<W> : k_fwht_cta<W>;
     SKM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     SKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * W, smem));
