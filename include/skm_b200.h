@@ -220,6 +220,22 @@ int   skm_lloyd_accumulate(skm_lloyd *L);
 int   skm_lloyd_set_assign_mode(skm_lloyd *L, int mode);
 /* Columns the last bounded skm_lloyd_assign had to re-evaluate (-1: that call evaluated every column). */
 int   skm_lloyd_last_assign(skm_lloyd *L, int64_t *n_flagged);
+/* Which kernels the full assignment pass of skm_lloyd_assign runs.  -1 (default): automatic.  1: the tensor-core
+ * plan (SKM_F32 datasets, 2 <= K <= 128, p <= 4096; never chosen automatically: it measured 4.9 ms against 5.35 ms
+ * per pass at K = 64 and needs a fourth image of X): every column is
+ * densified on the fly into an fp16 operand tile and the K scores  sum_{r in supp} (c_rk^2 - 2 x_r c_rk)  come
+ * out of tcgen05.mma (private/SparseMatrixMinusCluster.c:169-182 expanded); that product only FILTERS -- the best
+ * centre is then evaluated exactly (same fp32 sum and rounding guard as the gather kernels), a rigorous bound on
+ * the filter's rounding excludes the others, near-ties are settled among the best three in fp32 and whatever is
+ * left in fp64 in the reference's order.  Assignments are the same as with 0 (the gather kernels of mode 0
+ * evaluate every centre in fp32 for every column). */
+int   skm_lloyd_set_tc_filter(skm_lloyd *L, int mode);
+/* After skm_lloyd_finalize / refresh_diff: columns the exact evaluation of the filter's winner could not keep, and
+ * columns that went on to the fp64 kernel, in the last tensor-core pass (-1: the last pass was not one). */
+int   skm_lloyd_last_tc(skm_lloyd *L, int64_t *not_kept, int64_t *not_resolved);
+/* Test hook: runs the tensor-core pass for the current centres and returns the raw filter scores, scaled back,
+ * as [n][bn] floats (bn = 32, 64 or 128 by K; scores_host must hold n * 128 floats to be safe). */
+int   skm_debug_tc_scores(skm_lloyd *L, int has_gamma, double gamma, float *scores_host, int64_t *bn_out);
 /* How skm_lloyd_accumulate obtains the sums.  0 (default): recompute from all columns every iteration, as
  * the reference does (kmeans_sparsified.m:430-453).  1: incremental -- the per-shard sums of the previous
  * iteration are kept and only the columns whose assignment changed move their entries between clusters

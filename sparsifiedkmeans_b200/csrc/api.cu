@@ -209,6 +209,7 @@ extern "C" void skm_dataset_destroy(skm_dataset *ds)
     cudaFree(ds->unit_row);
     cudaFree(ds->unit_start);
     cudaFree(ds->unit_counter);
+    skm_tsb_free(ds);
     free(ds->h_rowptr);
     delete ds;
 }
@@ -501,6 +502,7 @@ extern "C" void skm_lloyd_destroy(skm_lloyd *L)
     cudaFree(L->stats);
     cudaFree(L->acc_local); cudaFree(L->assign_prev); cudaFree(L->changed); cudaFree(L->nchanged);
     cudaFree(L->lb); cudaFree(L->centers_prev); cudaFree(L->table_t); cudaFree(L->shift); cudaFree(L->nchanged_pred);
+    cudaFree(L->tc_bimg); cudaFree(L->tc_scale); cudaFree(L->tc_cand); cudaFree(L->tc_lb4); cudaFree(L->tc_zshift); cudaFree(L->flagged2);
     if (L->h_stats) cudaFreeHost(L->h_stats);
     if (L->h_counts) cudaFreeHost(L->h_counts);
     delete L;
@@ -524,6 +526,8 @@ static int skm_lloyd_create_ex(skm_dataset *ds, int64_t K, int want_f64_dist, sk
     if (!L) { skm_set_error("out of host memory"); return SKM_ERR_NOMEM; }
     memset(L, 0, sizeof *L);
     L->ds = ds; L->ctx = ds->ctx; L->K = K;
+    L->tc_filter = -1;
+    L->last_tc[0] = L->last_tc[1] = L->last_tc[2] = -1;
     const int64_t p = ds->p, n = ds->n;
     int rc = SKM_OK;
     do {
@@ -620,6 +624,107 @@ extern "C" int skm_lloyd_set_assign_mode(skm_lloyd *L, int mode)
     return SKM_OK;
 }
 
+// ---- tensor-core filter plan (tcsparse.cu) ----
+static bool tc_wanted(const skm_lloyd *L)
+{
+    const skm_dataset *ds = L->ds;
+    if (!skm_tcs_supported(ds->ctx, ds, L->K)) return false;
+    if (L->tc_filter == 0) return false;
+    if (L->tc_filter == 1) return true;
+    // automatic = off: measured 4.9 ms per config-3 shard pass (filter 4.2 + candidate pass) against 5.35 ms for the
+    // gather kernels -- not worth a fourth image of X (profiles/r2_tcsparse.md); SKM_TC_FILTER=1 turns it on
+    static const char *e = getenv("SKM_TC_FILTER");
+    return e && *e && atoi(e) != 0;
+}
+
+static int tc_prepare(skm_lloyd *L)
+{
+    skm_dataset *ds = L->ds;
+    const int64_t p = ds->p, n = ds->n, K = L->K;
+    if (!L->lb) SKM_TRY(dev_alloc((void **)&L->lb, sizeof(float) * n, "lb"));
+    if (!L->table_t) SKM_TRY(dev_alloc((void **)&L->table_t, sizeof(float) * K * (p + 1), "table_t"));
+    if (!L->tc_bimg) SKM_TRY(dev_alloc(&L->tc_bimg, skm_tcs_bimg_bytes(p, K), "centre image"));
+    if (!L->tc_scale) SKM_TRY(dev_alloc((void **)&L->tc_scale, sizeof(float) * 4, "tc scale"));
+    if (!L->tc_cand) SKM_TRY(dev_alloc((void **)&L->tc_cand, sizeof(uint32_t) * n, "tc candidates"));
+    if (!L->tc_lb4) SKM_TRY(dev_alloc((void **)&L->tc_lb4, sizeof(float) * n, "tc bound"));
+    if (!L->flagged2) SKM_TRY(dev_alloc((void **)&L->flagged2, sizeof(int32_t) * n, "flagged2"));
+    if (!L->tc_zshift) {
+        SKM_TRY(dev_alloc((void **)&L->tc_zshift, sizeof(float) * (K + 4), "zero shift"));
+        SKM_CUDA(cudaMemsetAsync(L->tc_zshift, 0, sizeof(float) * (K + 4), ds->ctx->stream));
+    }
+    SKM_TRY(skm_tsb_build(ds));
+    SKM_TRY(skm_sell_ensure_any(ds));
+    return SKM_OK;
+}
+
+// the full assignment pass on the tensor cores: filter -> exact evaluation of the winner (every column) -> exact
+// evaluation of the best three (columns whose runner-up is within the filter's error) -> fp64 (what is left)
+static int tc_assign(skm_lloyd *L, const ExactArgs &ea, float *dbg_scores)
+{
+    skm_dataset *ds = L->ds;
+    skm_ctx *ctx = ds->ctx;
+    {
+        SkmTimed t(ctx, SKM_T_ASSIGN);
+        SKM_TRY(skm_launch_build_table_t(ctx, ds->p, L->K, L->cscaled_t, L->table_t, L->cmax));
+        SKM_TRY(skm_launch_tcs_centres(ctx, ds, L->K, L->cscaled_t, L->cmax, L->tc_scale, L->tc_bimg));
+        SKM_TRY(skm_launch_tcs_filter(ctx, ds, L->K, L->tc_bimg, L->tc_scale, L->cmax, L->assign, L->lb, L->tc_cand, L->tc_lb4,
+                                      dbg_scores));
+        SKM_TRY(skm_launch_assign_bounded(ctx, ds, L->K, L->table_t, L->cmax, L->tc_zshift, L->assign, L->lb, L->dist_f32,
+                                          L->flagged, L->nflag));
+    }
+    {
+        SkmTimed t(ctx, SKM_T_RECHECK);
+        SKM_CUDA(cudaMemcpyAsync(L->nflag + 2, L->nflag, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+        SKM_TRY(skm_launch_tcs_resolve(ctx, ds, L->K, L->table_t, L->cmax, L->flagged, L->nflag, ds->n, L->tc_cand, L->tc_lb4,
+                                       L->assign, L->dist_f32, L->lb, L->flagged2, L->nflag + 1));
+        SKM_TRY(skm_launch_exact_assign(ctx, ea, L->assign, nullptr, L->dist_f32, L->flagged2, L->nflag + 1, ds->n, L->lb));
+        // n_rechecked keeps its meaning: columns that went to the fp64 kernel
+        SKM_CUDA(cudaMemcpyAsync(L->nflag, L->nflag + 1, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    L->last_tc[0] = L->last_tc[1] = -2;               // on the device until read_stats
+    return SKM_OK;
+}
+
+extern "C" int skm_lloyd_set_tc_filter(skm_lloyd *L, int mode)
+{
+    SKM_REQUIRE(L, "NULL argument");
+    SKM_REQUIRE(mode >= -1 && mode <= 1, "tc filter mode must be -1 (automatic), 0 (off) or 1 (on)");
+    if (mode == 1 && !skm_tcs_supported(L->ds->ctx, L->ds, L->K)) {
+        skm_set_error("the tensor-core filter needs an SKM_F32 dataset, 2 <= K <= 128 and p <= 4096");
+        return SKM_ERR_UNSUPPORTED;
+    }
+    L->tc_filter = mode;
+    return SKM_OK;
+}
+
+extern "C" int skm_lloyd_last_tc(skm_lloyd *L, int64_t *not_kept, int64_t *not_resolved)
+{
+    SKM_REQUIRE(L, "NULL argument");
+    if (not_kept) *not_kept = L->last_tc[0];
+    if (not_resolved) *not_resolved = L->last_tc[1];
+    return SKM_OK;
+}
+
+// tests: the raw scores of the filter, scaled back, [n][BN] floats (BN = 32 / 64 / 128 by K), after an assignment pass
+extern "C" int skm_debug_tc_scores(skm_lloyd *L, int has_gamma, double gamma, float *scores_host, int64_t *bn_out)
+{
+    SKM_REQUIRE(L && scores_host, "NULL argument");
+    skm_dataset *ds = L->ds;
+    skm_ctx *ctx = ds->ctx;
+    SKM_TRY(enter(ctx));
+    if (!skm_tcs_supported(ctx, ds, L->K)) { skm_set_error("tensor-core filter not supported for this dataset / K"); return SKM_ERR_UNSUPPORTED; }
+    SKM_TRY(tc_prepare(L));
+    const int64_t bn = skm_tcs_bn(L->K);
+    DevBuf sc;
+    SKM_TRY(sc.alloc(sizeof(float) * (size_t)ds->n * bn));
+    SKM_TRY(skm_launch_prep_centers(ctx, ds->p, L->K, L->centers, has_gamma, gamma, L->cscaled_t, nullptr, nullptr));
+    ExactArgs ea = exact_args(ds, L->K, L->cscaled_t);
+    SKM_TRY(tc_assign(L, ea, sc.as<float>()));
+    L->dist_is_f64 = false; L->assigned = true; L->accumulated = false;
+    if (bn_out) *bn_out = bn;
+    return d2h_sync(ctx, scores_host, sc.ptr, sizeof(float) * (size_t)ds->n * bn);
+}
+
 extern "C" int skm_lloyd_last_assign(skm_lloyd *L, int64_t *n_flagged)
 {
     SKM_REQUIRE(L, "NULL argument");
@@ -636,7 +741,14 @@ extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
     SKM_REQUIRE(!has_gamma || gamma == gamma, "gamma is NaN");
     FastPlan pl;
     const bool fast = ds->store_dtype == SKM_F32 && L->table && skm_fast_plan(ctx, ds->p, L->K, &pl, ds->max_col_nnz);
-    if (fast) SKM_TRY(skm_sell_ensure_layout(ds, pl.layout));            // entry order of the kernel family (one-off)
+    bool use_tc = fast && tc_wanted(L);
+    if (use_tc) {
+        const int rc = tc_prepare(L);                                    // one-off image build; falls back if it does not fit
+        if ((rc == SKM_ERR_NOMEM || rc == SKM_ERR_UNSUPPORTED) && L->tc_filter != 1) use_tc = false;
+        else SKM_TRY(rc);
+    }
+    if (fast && !use_tc) SKM_TRY(skm_sell_ensure_layout(ds, pl.layout)); // entry order of the kernel family (one-off)
+    L->last_tc[0] = L->last_tc[1] = -1;
     {
         SkmTimed t(ctx, SKM_T_PREP);
         SKM_TRY(skm_launch_prep_centers(ctx, ds->p, L->K, L->centers, has_gamma, gamma, L->cscaled_t, nullptr, nullptr));
@@ -699,7 +811,11 @@ extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
             L->bounded_skip = L->bounded_backoff;
         }
     }
-    if (fast) {
+    if (use_tc) {
+        SKM_TRY(tc_assign(L, ea, nullptr));
+        L->dist_is_f64 = false;
+        if (want_bounds) L->lb_valid = true;
+    } else if (fast) {
         {
             SkmTimed t(ctx, SKM_T_ASSIGN);
             SKM_TRY(skm_launch_build_table(ctx, ds->p, L->K, L->cscaled_t, pl, L->table, L->cmax));
@@ -802,8 +918,9 @@ static int read_stats(skm_lloyd *L, skm_iter_stats *stats)
     const int64_t p = L->ds->p, K = L->K;
     std::vector<double> tail(K + 1);
     SKM_CUDA(cudaMemcpyAsync(L->h_stats, L->stats, sizeof(double) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    SKM_CUDA(cudaMemcpyAsync(ctx->h_flag, L->nflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SKM_CUDA(cudaMemcpyAsync(ctx->h_flag, L->nflag, sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     SKM_TRY(d2h_sync(ctx, tail.data(), L->partials + 2 * p * K, sizeof(double) * (K + 1)));
+    if (L->last_tc[0] == -2) { L->last_tc[0] = ctx->h_flag[2]; L->last_tc[1] = ctx->h_flag[1]; }
     int64_t n_empty = 0, npts = 0;
     for (int64_t k = 0; k < K; ++k) {
         L->h_counts[k] = (int64_t)llround(tail[k]);
@@ -897,7 +1014,8 @@ extern "C" const char *skm_lloyd_kernel_name(skm_lloyd *L)
     FastPlan pl;
     const skm_dataset *ds = L->ds;
     if (ds->store_dtype == SKM_F32 && L->table && skm_fast_plan(ds->ctx, ds->p, L->K, &pl, ds->max_col_nnz)) {
-        if (pl.mode64) snprintf(name, sizeof name, "k_assign_fast64<%d>", pl.kc);
+        if (tc_wanted(L) && ds->tsb) snprintf(name, sizeof name, "k_tcs_filter<%d> + k_assign_bounded", skm_tcs_bn(L->K));
+        else if (pl.mode64) snprintf(name, sizeof name, "k_assign_fast64<%d>", pl.kc);
         else snprintf(name, sizeof name, "k_assign_fast<%d>%s%s x%d", pl.kc, pl.global_table ? " (global table)" : "",
                       pl.dual8 ? " (dual table)" : "", pl.nchunks);
     } else snprintf(name, sizeof name, "k_exact_assign");

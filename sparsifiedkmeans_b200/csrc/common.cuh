@@ -138,6 +138,15 @@ struct skm_dataset {
     // k-means++ running minimum distance (allocated on first use)
     double  *kpp_mind;                  // [n]
     double  *kpp_cum;                   // [n] inclusive scan of mind^2
+    // tile/stripe block image for the tensor-core filter (tcsparse.cu), built on first use
+    uint2   *tsb;                       // [nnz] (key, value bits), blocks of (128 columns x 64 rows)
+    int64_t *tsb_ptr;                   // [ntiles * stripes + 1]
+    int64_t  tsb_ntiles;
+    int      tsb_stripes;
+    float    tsb_sigma;                 // power of two the stored values are multiplied by
+    int      tsb_max_block;             // entries of the largest block
+    float   *colnorm2;                  // [n] fp32 |x_j|^2 of the stored values
+    int     *xmax_bits;                 // device int[4]: bits of max |x|, largest block
     int64_t  device_bytes;
     bool     uncommitted;               // skm_dataset_alloc_csc without skm_dataset_commit yet
 };
@@ -184,6 +193,15 @@ struct skm_lloyd {
     int64_t  last_predicted_keep;   // columns the a-priori test proved to keep their centre (-1: not run)
     int64_t  last_bounded_flagged;   // columns the bounds could not keep (-1: the pass evaluated everything)
     int      bounded_skip, bounded_backoff;   // passes to sit out after a bounded pass that kept too few columns
+    // tensor-core filter plan (tcsparse.cu): -1 = automatic, 0 = off, 1 = on
+    int      tc_filter;
+    void    *tc_bimg;        // swizzled fp16 centre image
+    float   *tc_scale;       // [4] sigma, 1/sigma^2, off flag
+    uint32_t *tc_cand;       // [n] second | third << 16
+    float   *tc_lb4;         // [n]
+    float   *tc_zshift;      // [K + 4] zeros (the bounded kernel's movement input)
+    int32_t *flagged2;       // [n]
+    int64_t  last_tc[3];     // columns: not kept by the candidate pass, not resolved among the best three, (unused)
     bool     assigned, accumulated;
     bool     dist_is_f64;    // which of dist_f64 / dist_f32 the last assignment wrote
     int64_t  last_rechecked;
@@ -283,6 +301,21 @@ int skm_launch_move_changed(skm_ctx *ctx, const skm_dataset *ds, int64_t K, cons
                             const int32_t *changed, const int *nchanged, int64_t nchanged_host, double *acc);
 int skm_launch_argmax(skm_ctx *ctx, int64_t n, const float *dist32, const double *dist64,
                       double *out_val, int64_t *out_idx);
+
+// tcsparse.cu: tensor-core (tcgen05, fp16) filter for the sparsified K1 at many centres
+bool   skm_tcs_supported(const skm_ctx *ctx, const skm_dataset *ds, int64_t K);
+int    skm_tcs_bn(int64_t K);
+size_t skm_tcs_bimg_bytes(int64_t p, int64_t K);
+int    skm_tsb_build(skm_dataset *ds);
+void   skm_tsb_free(skm_dataset *ds);
+int    skm_launch_tcs_centres(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const double *ct, const float *cmax,
+                              float *scale, void *bimg);
+int    skm_launch_tcs_filter(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const void *bimg, const float *scale,
+                             const float *cmax, int32_t *assign, float *lb, uint32_t *cand, float *lb4, float *dbg_scores);
+int    skm_launch_tcs_resolve(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const float *table_t, const float *cmax,
+                              const int32_t *flagged_in, const int *nflag_in, int64_t nflag_host, const uint32_t *cand,
+                              const float *lb4, int32_t *assign, float *dist, float *lb, int32_t *flagged_out, int *nflag_out);
+int    skm_sell_ensure_any(skm_dataset *ds);
 
 // tcgemm.cu: tensor-core (tcgen05, tf32) filter + exact evaluation of the candidates for the dense second pass
 bool   skm_tc_dense_usable(int64_t p, int64_t K);

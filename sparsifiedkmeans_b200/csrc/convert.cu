@@ -633,6 +633,22 @@ int skm_sell_ensure_layout(skm_dataset *ds, int mode)
     return SKM_OK;
 }
 
+// Any valid entry order will do (the bounded pass gathers one value per entry, bank conflicts do not matter):
+// keep what is there, or fill the image in stored order -- the cheapest fill.
+int skm_sell_ensure_any(skm_dataset *ds)
+{
+    skm_ctx *ctx = ds->ctx;
+    if (!ds->sell || ds->sell_elems == 0 || ds->nslices == 0 || ds->sell_mode >= 0) return SKM_OK;
+    if (ds->store_dtype != SKM_F32) return skm_sell_ensure_layout(ds, 0);
+    const int64_t blocks = (ds->nslices * 32 + 255) / 256;
+    k_fill_sell<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>(
+        ds->p, ds->n, ds->nslices, ds->colptr, ds->rowidx, (const float *)ds->val, ds->slice_ptr, ds->sell);
+    SKM_CHECK_LAUNCH(ctx);
+    ds->sell_plain = true;
+    ds->sell_mode = 3;                   // stored order: no kernel family asks for it, so a later bind re-lays it out
+    return SKM_OK;
+}
+
 int skm_sell_check(skm_dataset *ds, int64_t out[3])
 {
     skm_ctx *ctx = ds->ctx;
@@ -643,7 +659,7 @@ int skm_sell_check(skm_dataset *ds, int64_t out[3])
     SKM_TRY(r.alloc(3 * sizeof(unsigned long long)));
     SKM_CUDA(cudaMemsetAsync(r.ptr, 0, 3 * sizeof(unsigned long long), ctx->stream));
     int64_t blocks = (ds->nslices * 32 + 255) / 256;
-    k_sell_check<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ds->p, ds->n, ds->nslices, ds->sell_mode >= 1 ? ds->sell_mode : 0,
+    k_sell_check<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ds->p, ds->n, ds->nslices, (ds->sell_mode >= 1 && !ds->sell_plain) ? ds->sell_mode : 0,
                                                            (int)skm_dual_boff(ds->p), ds->colptr, ds->rowidx,
                                                            (const float *)ds->val, ds->slice_ptr, ds->sell,
                                                            r.as<unsigned long long>());

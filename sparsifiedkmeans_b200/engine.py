@@ -383,6 +383,26 @@ class Lloyd:
         check(self._lib.skm_lloyd_last_assign(self.handle, C.byref(v)))
         return int(v.value)
 
+    def set_tc_filter(self, mode):
+        """None: automatic; True / False: force the tensor-core plan of the full assignment pass on / off
+        (skm_lloyd_set_tc_filter); assignments are the same either way."""
+        check(self._lib.skm_lloyd_set_tc_filter(self.handle, -1 if mode is None else (1 if mode else 0)))
+
+    def last_tc(self) -> tuple[int, int]:
+        """(columns the winner's exact evaluation could not keep, columns that went to fp64) of the last
+        tensor-core pass, valid after finalize(); (-1, -1) if the last pass was not one."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        check(self._lib.skm_lloyd_last_tc(self.handle, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def debug_tc_scores(self, gamma=None) -> np.ndarray:
+        """Test hook: raw filter scores [n, bn] of a tensor-core pass with the current centres."""
+        out = np.empty((self.ds.n, 128), dtype=np.float32)
+        bn = C.c_int64(0)
+        check(self._lib.skm_debug_tc_scores(self.handle, int(gamma is not None), float(gamma if gamma is not None else 0.0),
+                                            _ptr(out), C.byref(bn)))
+        return out.reshape(-1)[: self.ds.n * bn.value].reshape(self.ds.n, bn.value)
+
     def set_update_mode(self, incremental: bool):
         """False: per-cluster sums recomputed from all columns every iteration (the reference's way);
         True: only columns whose assignment changed move their entries (skm_lloyd_set_update_mode)."""
