@@ -707,7 +707,7 @@ def run_ours(args):
 
             def whole_job():
                 t = [time.perf_counter()]
-                ds2 = Dataset.from_csc(p, n_e2e, hj, rows_np, hv, store="f32", ctx=ctx)
+                ds2 = Dataset.from_csc(p, n_e2e, hj, rows_np, hv, store="f32", ctx=ctx, K_hint=K)
                 t.append(time.perf_counter())
                 L2 = Lloyd(ds2, K)
                 L2.set_centers(start)

@@ -141,6 +141,14 @@ int  skm_dataset_create_csc(skm_ctx *ctx, int64_t p, int64_t n,
                             const void *jc, int jc_type, const void *ir, int ir_type,
                             const void *val, int val_type, int store_dtype, int on_device,
                             skm_dataset **out);
+/* Same, with the number of centres the caller is going to use (0: unknown).  For large host matrices the upload is
+ * pipelined in column chunks (conversion, validation and the counting pass of the row-major image follow the upload
+ * chunk by chunk); with K_hint > 0 the entry order of the kernel family that serves K centres is built chunk by chunk
+ * while the upload is still in flight instead of at the first skm_lloyd_assign. */
+int  skm_dataset_create_csc_hint(skm_ctx *ctx, int64_t p, int64_t n,
+                                 const void *jc, int jc_type, const void *ir, int ir_type,
+                                 const void *val, int val_type, int store_dtype, int on_device,
+                                 int64_t K_hint, skm_dataset **out);
 /* In-place production of an SKM_F32 dataset: allocate the device CSC arrays (int64 colptr[n+1], int32 rowidx[nnz],
  * float val[nnz]), let the caller's own kernels fill them (skm_dataset_csc_ptrs returns the device pointers), then
  * skm_dataset_commit validates them (sorted rows in range, colptr[n] == nnz) and builds the streamed images.  A

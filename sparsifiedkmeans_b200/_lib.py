@@ -64,6 +64,8 @@ SIGNATURES = {
     "skm_hadamard": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "skm_dataset_create_csc": (_int, [_vp, _i64, _i64, _vp, _int, _vp, _int, _vp, _int, _int, _int,
                                       C.POINTER(_vp)]),
+    "skm_dataset_create_csc_hint": (_int, [_vp, _i64, _i64, _vp, _int, _vp, _int, _vp, _int, _int, _int, _i64,
+                                           C.POINTER(_vp)]),
     "skm_dataset_alloc_csc": (_int, [_vp, _i64, _i64, _i64, C.POINTER(_vp)]),
     "skm_dataset_csc_ptrs": (_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "skm_dataset_commit": (_int, [_vp]),

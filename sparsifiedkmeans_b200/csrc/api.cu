@@ -67,6 +67,20 @@ extern "C" int skm_ctx_create(int device, void *cuda_stream, skm_ctx **out)
     ctx->stream_cache_free = nullptr;
     ctx->tc_chunks = 0;
     ctx->tc_chunks_dropped = 0;
+    ctx->use_pool = false;
+    ctx->bounce[0] = ctx->bounce[1] = nullptr;
+    ctx->bounce_ev[0] = ctx->bounce_ev[1] = nullptr;
+    {
+        int pools = 0;
+        cudaMemPool_t pool;
+        if (!getenv("SKM_NO_POOL") && cudaDeviceGetAttribute(&pools, cudaDevAttrMemoryPoolsSupported, device) == cudaSuccess && pools &&
+            cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            const char *g = getenv("SKM_POOL_RETAIN_GB");
+            uint64_t keep = (uint64_t)((g && *g) ? atof(g) : 48.0) << 30;
+            if (cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess) ctx->use_pool = true;
+        }
+        cudaGetLastError();
+    }
     ctx->ev = nullptr;
     memset(ctx->ev_count, 0, sizeof ctx->ev_count);
     if (cudaMalloc((void **)&ctx->d_flag, 16 * sizeof(int)) != cudaSuccess ||
@@ -87,6 +101,7 @@ extern "C" void skm_ctx_destroy(skm_ctx *ctx)
     if (ctx->stream_cache && ctx->stream_cache_free) ctx->stream_cache_free(ctx->stream_cache);
     if (ctx->d_flag) cudaFree(ctx->d_flag);
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+    for (int i = 0; i < 2; ++i) { if (ctx->bounce[i]) cudaFreeHost(ctx->bounce[i]); if (ctx->bounce_ev[i]) cudaEventDestroy(ctx->bounce_ev[i]); }
     if (ctx->ev) {
         for (int s = 0; s < SKM_T_SLOTS; ++s)
             for (int i = 0; i < SKM_T_RING; ++i) { cudaEventDestroy(ctx->ev[s][i][0]); cudaEventDestroy(ctx->ev[s][i][1]); }
@@ -169,6 +184,65 @@ static int dev_alloc(void **ptr, size_t bytes, const char *what)
     return SKM_OK;
 }
 
+int skm_big_alloc(skm_ctx *ctx, void **ptr, size_t bytes, const char *what)
+{
+    *ptr = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e;
+    if (ctx->use_pool) {
+        e = cudaMallocAsync(ptr, bytes, ctx->stream);
+        if (e != cudaSuccess) {                                  // give back what the pool holds in reserve and retry once
+            cudaGetLastError();
+            cudaMemPool_t pool;
+            cudaStreamSynchronize(ctx->stream);
+            if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+            e = cudaMallocAsync(ptr, bytes, ctx->stream);
+        }
+    } else e = cudaMalloc(ptr, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *ptr = nullptr;
+        skm_set_error("device allocation (%s, %zu bytes) failed: %s", what, bytes, cudaGetErrorString(e));
+        return SKM_ERR_NOMEM;
+    }
+    return SKM_OK;
+}
+
+void skm_big_free(skm_ctx *ctx, void *ptr)
+{
+    if (!ptr) return;
+    if (ctx->use_pool) cudaFreeAsync(ptr, ctx->stream);
+    else cudaFree(ptr);
+}
+
+int skm_d2h_pageable(skm_ctx *ctx, void *dst, const void *src_dev, size_t bytes)
+{
+    const size_t CH = (size_t)8 << 20;
+    if (bytes < 4 * CH) {                                        // small: not worth the staging
+        if (bytes) SKM_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        SKM_CUDA(cudaStreamSynchronize(ctx->stream));
+        return SKM_OK;
+    }
+    for (int i = 0; i < 2; ++i) {
+        if (!ctx->bounce[i]) SKM_CUDA(cudaMallocHost(&ctx->bounce[i], CH));
+        if (!ctx->bounce_ev[i]) SKM_CUDA(cudaEventCreateWithFlags(&ctx->bounce_ev[i], cudaEventDisableTiming));
+    }
+    const size_t nch = (bytes + CH - 1) / CH;
+    for (size_t c = 0; c < nch + 1; ++c) {
+        if (c < nch) {                                           // chunk c crosses PCIe ...
+            const size_t off = c * CH, sz = std::min(CH, bytes - off);
+            SKM_CUDA(cudaMemcpyAsync(ctx->bounce[c & 1], (const char *)src_dev + off, sz, cudaMemcpyDeviceToHost, ctx->stream));
+            SKM_CUDA(cudaEventRecord(ctx->bounce_ev[c & 1], ctx->stream));
+        }
+        if (c > 0) {                                             // ... while chunk c-1 is copied out of the staging buffer
+            const size_t off = (c - 1) * CH, sz = std::min(CH, bytes - off);
+            SKM_CUDA(cudaEventSynchronize(ctx->bounce_ev[(c - 1) & 1]));
+            memcpy((char *)dst + off, ctx->bounce[(c - 1) & 1], sz);
+        }
+    }
+    return SKM_OK;
+}
+
 static int h2d(skm_ctx *ctx, void *dst, const void *src, size_t bytes)
 {
     if (bytes == 0) return SKM_OK;
@@ -188,8 +262,13 @@ static int d2h_sync(skm_ctx *ctx, void *dst, const void *src, size_t bytes)
 // ---------------------------------------------------------------------------
 static size_t type_size(int t) { return t == SKM_U16 ? 2 : ((t == SKM_F32 || t == SKM_I32) ? 4 : 8); }
 
-static bool skm_trace_on();
-static double skm_now();
+#include <chrono>
+static bool skm_trace_on() { static const bool on = getenv("SKM_TRACE") != nullptr; return on; }
+static double skm_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+#define SKM_TRACE_POINT(label, t0)                                                             \
+    do { if (skm_trace_on()) { cudaDeviceSynchronize(); const double t1__ = skm_now();         \
+         fprintf(stderr, "[skm trace] %-28s %8.2f ms\n", label, 1e3 * (t1__ - (t0))); (t0) = t1__; } } while (0)
+
 extern "C" void skm_dataset_destroy(skm_dataset *ds)
 {
     if (!ds) return;
@@ -197,29 +276,26 @@ extern "C" void skm_dataset_destroy(skm_dataset *ds)
     cudaStreamSynchronize(ds->ctx->stream);
     const double td0 = skm_trace_on() ? skm_now() : 0.0;
     struct Tr { double t0; ~Tr() { if (skm_trace_on()) fprintf(stderr, "[skm trace] %-28s %8.2f ms\n", "dataset_destroy", 1e3 * (skm_now() - t0)); } } tr{td0};
-    cudaFree(ds->colptr);
-    cudaFree(ds->rowidx);
-    cudaFree(ds->val);
-    cudaFree(ds->sell);
+    cudaDeviceSynchronize();                       // other streams (a caller's views of the arrays) are done as well
+    double tdd = skm_now();
+    skm_big_free(ds->ctx, ds->colptr);
+    skm_big_free(ds->ctx, ds->rowidx);
+    skm_big_free(ds->ctx, ds->val);
+    skm_big_free(ds->ctx, ds->sell);
     cudaFree(ds->slice_ptr);
     cudaFree(ds->kpp_mind);
     cudaFree(ds->kpp_cum);
-    cudaFree(ds->csr);
+    skm_big_free(ds->ctx, ds->csr);
+    SKM_TRACE_POINT("destroy: big frees", tdd);
     cudaFree(ds->rowptr);
     cudaFree(ds->unit_row);
     cudaFree(ds->unit_start);
     cudaFree(ds->unit_counter);
     skm_tsb_free(ds);
+    SKM_TRACE_POINT("destroy: small frees", tdd);
     free(ds->h_rowptr);
     delete ds;
 }
-
-#include <chrono>
-static bool skm_trace_on() { static const bool on = getenv("SKM_TRACE") != nullptr; return on; }
-static double skm_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-#define SKM_TRACE_POINT(label, t0)                                                             \
-    do { if (skm_trace_on()) { cudaDeviceSynchronize(); const double t1__ = skm_now();         \
-         fprintf(stderr, "[skm trace] %-28s %8.2f ms\n", label, 1e3 * (t1__ - (t0))); (t0) = t1__; } } while (0)
 
 // takes ownership of colptr/rowidx/val (device, final types)
 static int dataset_finish(skm_dataset *ds)
@@ -239,9 +315,134 @@ static int dataset_finish(skm_dataset *ds)
     return SKM_OK;
 }
 
+// ---- pipelined creation from host arrays ----
+// The upload of a large matrix is PCIe-bound (88 ms for config 2) and used to be followed by ~85 ms of image building
+// plus, at the first assignment, ~55 ms of entry-order scheduling -- with the GPU idle during the upload.  Here the
+// columns cross PCIe in chunks on a copy stream while the previous chunk is converted, validated, counted for the
+// row-major image and (when the caller says how many centres it will use) laid out in the entry order of that kernel
+// family.  Only the offsets scan and the scatter of the row-major image are left when the last chunk has landed.
+static int64_t host_jc(const void *jc, int jc_type, int64_t j)
+{
+    return jc_type == SKM_I32 ? (int64_t)((const int32_t *)jc)[j] : ((const int64_t *)jc)[j];
+}
+
+static int dataset_fill_pipelined(skm_dataset *ds, const void *jc, int jc_type, const void *ir, int ir_type,
+                                  const void *val, int val_type, int64_t K_hint)
+{
+    skm_ctx *ctx = ds->ctx;
+    const int64_t p = ds->p, n = ds->n, nnz = ds->nnz;
+    double t0 = skm_now();
+    // 1. column pointers, validated before anything walks them
+    {
+        DevBuf sj;
+        if (jc_type != SKM_I64) {
+            SKM_TRY(sj.alloc(type_size(jc_type) * (n + 1)));
+            SKM_TRY(h2d(ctx, sj.ptr, jc, type_size(jc_type) * (n + 1)));
+            SKM_TRY(skm_launch_convert_index(ctx, sj.ptr, jc_type, n + 1, ds->colptr, 1));
+        } else SKM_TRY(h2d(ctx, ds->colptr, jc, sizeof(int64_t) * (n + 1)));
+        SKM_CUDA(cudaMemsetAsync(ctx->d_flag, 0, 4 * sizeof(int), ctx->stream));
+        SKM_TRY(skm_launch_validate_cols_async(ctx, n, nnz, ds->colptr, ctx->d_flag));
+        SKM_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        SKM_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_flag[0] & 1) { skm_set_error("invalid CSC column pointers (must start at 0, be non-decreasing, end at nnz)"); return SKM_ERR_INVALID; }
+        ds->max_col_nnz = ctx->h_flag[1];
+    }
+    ds->device_bytes = (int64_t)sizeof(int64_t) * (n + 1) + (int64_t)sizeof(int32_t) * nnz + (int64_t)sizeof(float) * nnz;
+    // 2. skeletons of the two images (sizes depend on the column pointers only)
+    SKM_TRY(skm_build_sell(ds));
+    int layout = -1;
+    if (K_hint > 0 && ds->sell && ds->sell_wmax > 0 && ds->sell_wmax <= 254) {
+        FastPlan pl;
+        if (skm_fast_plan(ctx, p, K_hint, &pl, ds->max_col_nnz) && (pl.layout == 1 || pl.layout == 2)) layout = pl.layout;
+    }
+    SKM_TRACE_POINT("pipelined: colptr + skeletons", t0);
+    // 3. chunks of whole 512-column tiles, about 24 M entries each
+    const int64_t avg = nnz / n > 0 ? nnz / n : 1;
+    const char *ce = getenv("SKM_PIPELINE_CHUNK");                  // entries per chunk (tests shrink it)
+    const int64_t target = (ce && atoll(ce) > 0) ? atoll(ce) : 24000000;
+    int64_t cols = (target / avg + 511) / 512 * 512;
+    if (cols < 512) cols = 512;
+    const int64_t nchunks = (n + cols - 1) / cols;
+    int64_t max_e = 0;
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int64_t j0 = c * cols, j1 = std::min(n, j0 + cols);
+        max_e = std::max(max_e, host_jc(jc, jc_type, j1) - host_jc(jc, jc_type, j0));
+    }
+    SkmCsrBuild cb;
+    SKM_TRY(skm_csr_begin(ds, &cb, cols, nchunks));
+    const bool stage_i = ir_type != SKM_I32, stage_v = val_type != SKM_F32;
+    cudaStream_t cs = nullptr;
+    cudaEvent_t up[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+    DevBuf si[2], sv[2], ovf;
+    int rc = SKM_OK;
+    auto cleanup = [&]() {
+        if (cs) { cudaStreamSynchronize(cs); cudaStreamDestroy(cs); }
+        cudaStreamSynchronize(ctx->stream);
+        for (int i = 0; i < 2; ++i) { if (up[i]) cudaEventDestroy(up[i]); if (done[i]) cudaEventDestroy(done[i]); }
+    };
+    do {
+        if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { skm_set_error("cudaStreamCreate failed"); rc = SKM_ERR_CUDA; break; }
+        for (int i = 0; i < 2 && rc == SKM_OK; ++i) {
+            if (cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess) { skm_set_error("cudaEventCreate failed"); rc = SKM_ERR_CUDA; }
+            if (rc == SKM_OK && stage_i) rc = si[i].alloc(type_size(ir_type) * (size_t)max_e);
+            if (rc == SKM_OK && stage_v) rc = sv[i].alloc(type_size(val_type) * (size_t)max_e);
+        }
+        if (rc != SKM_OK) break;
+        if ((rc = ovf.alloc(sizeof(unsigned long long)))) break;
+        if (cudaMemsetAsync(ovf.ptr, 0, sizeof(unsigned long long), ctx->stream) != cudaSuccess) { rc = SKM_ERR_CUDA; break; }
+        // the copy stream may only start once the stream-ordered allocations and the memsets above have happened
+        if (cudaEventRecord(done[0], ctx->stream) != cudaSuccess || cudaStreamWaitEvent(cs, done[0], 0) != cudaSuccess) { rc = SKM_ERR_CUDA; break; }
+        for (int64_t c = 0; c < nchunks && rc == SKM_OK; ++c) {
+            const int slot = (int)(c & 1);
+            const int64_t j0 = c * cols, j1 = std::min(n, j0 + cols);
+            const int64_t e0 = host_jc(jc, jc_type, j0), e1 = host_jc(jc, jc_type, j1), ne = e1 - e0;
+            if (ne < 0 || e0 < 0 || e1 > nnz) { skm_set_error("invalid CSC column pointers"); rc = SKM_ERR_INVALID; break; }
+            cudaError_t e = cudaSuccess;
+            if (c >= 2) e = cudaStreamWaitEvent(cs, done[slot], 0);              // the staging slot has been converted
+            if (e == cudaSuccess && ne > 0) {
+                void *di = stage_i ? si[slot].ptr : (void *)(ds->rowidx + e0);
+                void *dv = stage_v ? sv[slot].ptr : (void *)((float *)ds->val + e0);
+                e = cudaMemcpyAsync(di, (const char *)ir + (size_t)e0 * type_size(ir_type), (size_t)ne * type_size(ir_type), cudaMemcpyHostToDevice, cs);
+                if (e == cudaSuccess)
+                    e = cudaMemcpyAsync(dv, (const char *)val + (size_t)e0 * type_size(val_type), (size_t)ne * type_size(val_type), cudaMemcpyHostToDevice, cs);
+            }
+            if (e == cudaSuccess) e = cudaEventRecord(up[slot], cs);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, up[slot], 0);
+            if (e != cudaSuccess) { skm_set_error("pipelined upload failed: %s", cudaGetErrorString(e)); rc = SKM_ERR_CUDA; break; }
+            if (ne > 0) {
+                if (stage_i && (rc = skm_launch_convert_index(ctx, si[slot].ptr, ir_type, ne, ds->rowidx + e0, 0))) break;
+                if (stage_v && (rc = skm_launch_convert_value(ctx, sv[slot].ptr, val_type, ne, (float *)ds->val + e0, SKM_F32))) break;
+            }
+            if (cudaEventRecord(done[slot], ctx->stream) != cudaSuccess) { rc = SKM_ERR_CUDA; break; }
+            if ((rc = skm_launch_validate_rows_async(ctx, p, ne, ds->rowidx + e0, ctx->d_flag))) break;
+            if ((rc = skm_csr_chunk(ds, &cb, c, j0, j1, e0, e1))) break;
+            if (layout > 0 && (rc = skm_sell_layout_range(ds, layout, j0 / SKM_SLICE, (j1 - j0 + SKM_SLICE - 1) / SKM_SLICE, ovf.as<unsigned long long>()))) break;
+        }
+        if (rc != SKM_OK) break;
+        if (cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) { skm_set_error("pipelined upload failed: %s", cudaGetErrorString(cudaGetLastError())); rc = SKM_ERR_CUDA; break; }
+        if (ctx->h_flag[0] & 2) { skm_set_error("invalid CSC row index (must lie in [0,p))"); rc = SKM_ERR_INVALID; break; }
+        SKM_TRACE_POINT("pipelined: upload + per-chunk work", t0);
+        if (layout > 0) { ds->sell_mode = layout; ds->sell_plain = false; }
+    } while (0);
+    cleanup();
+    if (rc != SKM_OK) { skm_csr_abort(&cb); return rc; }
+    rc = skm_csr_finish(ds, &cb);
+    SKM_TRACE_POINT("pipelined: csr finish", t0);
+    return rc;
+}
+
 extern "C" int skm_dataset_create_csc(skm_ctx *ctx, int64_t p, int64_t n, const void *jc, int jc_type,
                                       const void *ir, int ir_type, const void *val, int val_type,
                                       int store_dtype, int on_device, skm_dataset **out)
+{
+    return skm_dataset_create_csc_hint(ctx, p, n, jc, jc_type, ir, ir_type, val, val_type, store_dtype, on_device, 0, out);
+}
+
+extern "C" int skm_dataset_create_csc_hint(skm_ctx *ctx, int64_t p, int64_t n, const void *jc, int jc_type,
+                                           const void *ir, int ir_type, const void *val, int val_type,
+                                           int store_dtype, int on_device, int64_t K_hint, skm_dataset **out)
 {
     SKM_TRY(enter(ctx));
     SKM_REQUIRE(out, "out is NULL");
@@ -278,10 +479,14 @@ extern "C" int skm_dataset_create_csc(skm_ctx *ctx, int64_t p, int64_t n, const 
     int rc = SKM_OK;
     double tt0 = skm_now();
     do {
-        if ((rc = dev_alloc((void **)&ds->colptr, sizeof(int64_t) * (n + 1), "colptr"))) break;
-        if ((rc = dev_alloc((void **)&ds->rowidx, sizeof(int32_t) * nnz, "rowidx"))) break;
-        if ((rc = dev_alloc(&ds->val, type_size(store_dtype) * nnz, "val"))) break;
+        if ((rc = skm_big_alloc(ds->ctx, (void **)&ds->colptr, sizeof(int64_t) * (n + 1), "colptr"))) break;
+        if ((rc = skm_big_alloc(ds->ctx, (void **)&ds->rowidx, sizeof(int32_t) * nnz, "rowidx"))) break;
+        if ((rc = skm_big_alloc(ds->ctx, &ds->val, type_size(store_dtype) * nnz, "val"))) break;
         SKM_TRACE_POINT("alloc csc", tt0);
+        if (!on_device && store_dtype == SKM_F32 && n > 0 && nnz >= (1 << 22) && !getenv("SKM_NO_PIPELINE")) {
+            rc = dataset_fill_pipelined(ds, jc, jc_type, ir, ir_type, val, val_type, K_hint);
+            break;
+        }
         // stage raw arrays (host -> device) unless they already live on the device
         DevBuf sj, si, sv;
         const void *dj = jc, *di = ir, *dv = val;
@@ -342,9 +547,11 @@ extern "C" int skm_dataset_alloc_csc(skm_ctx *ctx, int64_t p, int64_t n, int64_t
     ds->uncommitted = true;
     int rc = SKM_OK;
     do {
-        if ((rc = dev_alloc((void **)&ds->colptr, sizeof(int64_t) * (n + 1), "colptr"))) break;
-        if ((rc = dev_alloc((void **)&ds->rowidx, sizeof(int32_t) * nnz, "rowidx"))) break;
-        if ((rc = dev_alloc(&ds->val, sizeof(float) * nnz, "val"))) break;
+        if ((rc = skm_big_alloc(ds->ctx, (void **)&ds->colptr, sizeof(int64_t) * (n + 1), "colptr"))) break;
+        if ((rc = skm_big_alloc(ds->ctx, (void **)&ds->rowidx, sizeof(int32_t) * nnz, "rowidx"))) break;
+        if ((rc = skm_big_alloc(ds->ctx, &ds->val, sizeof(float) * nnz, "val"))) break;
+        // the caller fills the arrays on streams of its own: the (stream-ordered) allocations must have happened
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { skm_set_error("allocation failed: %s", cudaGetErrorString(cudaGetLastError())); rc = SKM_ERR_CUDA; }
     } while (0);
     if (rc != SKM_OK) { skm_dataset_destroy(ds); return rc; }
     *out = ds;
@@ -496,13 +703,13 @@ extern "C" void skm_lloyd_destroy(skm_lloyd *L)
     cudaSetDevice(L->ctx->device);
     cudaStreamSynchronize(L->ctx->stream);
     cudaFree(L->centers); cudaFree(L->centers_old); cudaFree(L->cscaled_t); cudaFree(L->table);
-    cudaFree(L->assign_c);
-    cudaFree(L->cmax); cudaFree(L->assign); cudaFree(L->dist_f32); cudaFree(L->dist_f64);
-    cudaFree(L->best2); cudaFree(L->flagged); cudaFree(L->nflag); cudaFree(L->partials);
+    skm_big_free(L->ctx, L->assign_c);
+    cudaFree(L->cmax); skm_big_free(L->ctx, L->assign); skm_big_free(L->ctx, L->dist_f32); skm_big_free(L->ctx, L->dist_f64);
+    skm_big_free(L->ctx, L->best2); skm_big_free(L->ctx, L->flagged); cudaFree(L->nflag); cudaFree(L->partials);
     cudaFree(L->stats);
-    cudaFree(L->acc_local); cudaFree(L->assign_prev); cudaFree(L->changed); cudaFree(L->nchanged);
-    cudaFree(L->lb); cudaFree(L->centers_prev); cudaFree(L->table_t); cudaFree(L->shift); cudaFree(L->nchanged_pred);
-    cudaFree(L->tc_bimg); cudaFree(L->tc_scale); cudaFree(L->tc_cand); cudaFree(L->tc_lb4); cudaFree(L->tc_zshift); cudaFree(L->flagged2);
+    cudaFree(L->acc_local); skm_big_free(L->ctx, L->assign_prev); skm_big_free(L->ctx, L->changed); cudaFree(L->nchanged);
+    skm_big_free(L->ctx, L->lb); cudaFree(L->centers_prev); cudaFree(L->table_t); cudaFree(L->shift); cudaFree(L->nchanged_pred);
+    cudaFree(L->tc_bimg); cudaFree(L->tc_scale); skm_big_free(L->ctx, L->tc_cand); skm_big_free(L->ctx, L->tc_lb4); cudaFree(L->tc_zshift); skm_big_free(L->ctx, L->flagged2);
     if (L->h_stats) cudaFreeHost(L->h_stats);
     if (L->h_counts) cudaFreeHost(L->h_counts);
     delete L;
@@ -534,23 +741,23 @@ static int skm_lloyd_create_ex(skm_dataset *ds, int64_t K, int want_f64_dist, sk
         if ((rc = dev_alloc((void **)&L->centers, sizeof(double) * p * K, "centers"))) break;
         if ((rc = dev_alloc((void **)&L->centers_old, sizeof(double) * p * K, "centers_old"))) break;
         if ((rc = dev_alloc((void **)&L->cscaled_t, sizeof(double) * (p + 1) * K, "cscaled"))) break;
-        if ((rc = dev_alloc((void **)&L->assign, sizeof(int32_t) * n, "assign"))) break;
-        if ((rc = dev_alloc(&L->assign_c, sizeof(int32_t) * n, "assign_c"))) break;
+        if ((rc = skm_big_alloc(L->ctx, (void **)&L->assign, sizeof(int32_t) * n, "assign"))) break;
+        if ((rc = skm_big_alloc(L->ctx, &L->assign_c, sizeof(int32_t) * n, "assign_c"))) break;
         if ((rc = dev_alloc((void **)&L->partials, sizeof(double) * (2 * p * K + K + 1), "partials"))) break;
         if ((rc = dev_alloc((void **)&L->stats, sizeof(double) * 8, "stats"))) break;
         if ((rc = dev_alloc((void **)&L->nflag, sizeof(int) * 4, "nflag"))) break;
         if ((rc = dev_alloc((void **)&L->cmax, sizeof(float) * 4, "cmax"))) break;
         if (ds->store_dtype == SKM_F32) {
-            if ((rc = dev_alloc((void **)&L->dist_f32, sizeof(float) * n, "dist"))) break;
-            if ((rc = dev_alloc((void **)&L->flagged, sizeof(int32_t) * n, "flagged"))) break;
+            if ((rc = skm_big_alloc(L->ctx, (void **)&L->dist_f32, sizeof(float) * n, "dist"))) break;
+            if ((rc = skm_big_alloc(L->ctx, (void **)&L->flagged, sizeof(int32_t) * n, "flagged"))) break;
             FastPlan pl;
             if (skm_fast_plan(ds->ctx, p, K, &pl, ds->max_col_nnz)) {
                 if ((rc = dev_alloc((void **)&L->table, sizeof(float) * skm_fast_table_floats(p, pl), "table"))) break;
-                if (pl.nchunks > 1 && (rc = dev_alloc((void **)&L->best2, sizeof(float) * 2 * n, "best2"))) break;
+                if (pl.nchunks > 1 && (rc = skm_big_alloc(L->ctx, (void **)&L->best2, sizeof(float) * 2 * n, "best2"))) break;
             }
         }
         if (ds->store_dtype == SKM_F64 || want_f64_dist) {
-            if ((rc = dev_alloc((void **)&L->dist_f64, sizeof(double) * n, "dist64"))) break;
+            if ((rc = skm_big_alloc(L->ctx, (void **)&L->dist_f64, sizeof(double) * n, "dist64"))) break;
         }
         if (cudaMallocHost((void **)&L->h_stats, sizeof(double) * 8) != cudaSuccess ||
             cudaMallocHost((void **)&L->h_counts, sizeof(int64_t) * (K + 2)) != cudaSuccess) {
@@ -611,7 +818,7 @@ extern "C" int skm_lloyd_set_assign_mode(skm_lloyd *L, int mode)
     }
     if (mode == 1 && !L->lb) {
         const int64_t p = L->ds->p, n = L->ds->n, K = L->K;
-        SKM_TRY(dev_alloc((void **)&L->lb, sizeof(float) * n, "lb"));
+        SKM_TRY(skm_big_alloc(L->ctx, (void **)&L->lb, sizeof(float) * n, "lb"));
         SKM_TRY(dev_alloc((void **)&L->centers_prev, sizeof(double) * p * K, "centers_prev"));
         SKM_TRY(dev_alloc((void **)&L->table_t, sizeof(float) * K * (p + 1), "table_t"));
         SKM_TRY(dev_alloc((void **)&L->shift, sizeof(float) * (K + 4), "shift"));
@@ -641,13 +848,13 @@ static int tc_prepare(skm_lloyd *L)
 {
     skm_dataset *ds = L->ds;
     const int64_t p = ds->p, n = ds->n, K = L->K;
-    if (!L->lb) SKM_TRY(dev_alloc((void **)&L->lb, sizeof(float) * n, "lb"));
+    if (!L->lb) SKM_TRY(skm_big_alloc(L->ctx, (void **)&L->lb, sizeof(float) * n, "lb"));
     if (!L->table_t) SKM_TRY(dev_alloc((void **)&L->table_t, sizeof(float) * K * (p + 1), "table_t"));
     if (!L->tc_bimg) SKM_TRY(dev_alloc(&L->tc_bimg, skm_tcs_bimg_bytes(p, K), "centre image"));
     if (!L->tc_scale) SKM_TRY(dev_alloc((void **)&L->tc_scale, sizeof(float) * 4, "tc scale"));
-    if (!L->tc_cand) SKM_TRY(dev_alloc((void **)&L->tc_cand, sizeof(uint32_t) * n, "tc candidates"));
-    if (!L->tc_lb4) SKM_TRY(dev_alloc((void **)&L->tc_lb4, sizeof(float) * n, "tc bound"));
-    if (!L->flagged2) SKM_TRY(dev_alloc((void **)&L->flagged2, sizeof(int32_t) * n, "flagged2"));
+    if (!L->tc_cand) SKM_TRY(skm_big_alloc(L->ctx, (void **)&L->tc_cand, sizeof(uint32_t) * n, "tc candidates"));
+    if (!L->tc_lb4) SKM_TRY(skm_big_alloc(L->ctx, (void **)&L->tc_lb4, sizeof(float) * n, "tc bound"));
+    if (!L->flagged2) SKM_TRY(skm_big_alloc(L->ctx, (void **)&L->flagged2, sizeof(int32_t) * n, "flagged2"));
     if (!L->tc_zshift) {
         SKM_TRY(dev_alloc((void **)&L->tc_zshift, sizeof(float) * (K + 4), "zero shift"));
         SKM_CUDA(cudaMemsetAsync(L->tc_zshift, 0, sizeof(float) * (K + 4), ds->ctx->stream));
@@ -846,8 +1053,8 @@ extern "C" int skm_lloyd_set_update_mode(skm_lloyd *L, int mode)
     if (mode == 1 && !L->acc_local) {
         const int64_t p = L->ds->p, n = L->ds->n, K = L->K;
         SKM_TRY(dev_alloc((void **)&L->acc_local, sizeof(double) * (2 * p * K + K + 1), "acc_local"));
-        SKM_TRY(dev_alloc((void **)&L->assign_prev, sizeof(int32_t) * n, "assign_prev"));
-        SKM_TRY(dev_alloc((void **)&L->changed, sizeof(int32_t) * n, "changed"));
+        SKM_TRY(skm_big_alloc(L->ctx, (void **)&L->assign_prev, sizeof(int32_t) * n, "assign_prev"));
+        SKM_TRY(skm_big_alloc(L->ctx, (void **)&L->changed, sizeof(int32_t) * n, "changed"));
         SKM_TRY(dev_alloc((void **)&L->nchanged, sizeof(int) * 4, "nchanged"));
     }
     L->update_mode = mode;
@@ -976,19 +1183,23 @@ extern "C" int skm_lloyd_get_assignments(skm_lloyd *L, int32_t *assign_out, doub
     SKM_TRY(enter(ctx));
     if (!L->assigned) { skm_set_error("no assignments yet"); return SKM_ERR_STATE; }
     const int64_t n = L->ds->n;
-    if (assign_out) {
-        SKM_TRY(d2h_sync(ctx, assign_out, L->assign, sizeof(int32_t) * n));
-        for (int64_t j = 0; j < n; ++j) assign_out[j] += 1;            // MATLAB is 1-based
-    }
-    if (dist_out) {
-        if (L->dist_is_f64) SKM_TRY(d2h_sync(ctx, dist_out, L->dist_f64, sizeof(double) * n));
-        else {
-            std::vector<float> tmp(n);
-            SKM_TRY(d2h_sync(ctx, tmp.data(), L->dist_f32, sizeof(float) * n));
-            for (int64_t j = 0; j < n; ++j) dist_out[j] = (double)tmp[j];
-        }
-    }
-    return SKM_OK;
+    if (n == 0) return SKM_OK;
+    // 1-based indices (MATLAB) and doubles are produced on the device: a host loop over 1e7 columns cost 50 ms
+    void *sa = nullptr, *sd = nullptr;
+    int rc = SKM_OK;
+    do {
+        if (assign_out && (rc = skm_big_alloc(ctx, &sa, sizeof(int32_t) * n, "assignment export"))) break;
+        if (dist_out && !L->dist_is_f64 && (rc = skm_big_alloc(ctx, &sd, sizeof(double) * n, "distance export"))) break;
+        if ((rc = skm_launch_export(ctx, n, assign_out ? L->assign : nullptr, (int32_t *)sa,
+                                    (dist_out && !L->dist_is_f64) ? L->dist_f32 : nullptr, (double *)sd))) break;
+        if (assign_out && (rc = skm_d2h_pageable(ctx, assign_out, sa, sizeof(int32_t) * n))) break;
+        if (dist_out && (rc = skm_d2h_pageable(ctx, dist_out, L->dist_is_f64 ? (const void *)L->dist_f64 : sd, sizeof(double) * n))) break;
+    } while (0);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    skm_big_free(ctx, sa);
+    skm_big_free(ctx, sd);
+    if (rc == SKM_OK && e != cudaSuccess) { skm_set_error("read-back failed: %s", cudaGetErrorString(e)); rc = SKM_ERR_CUDA; }
+    return rc;
 }
 
 extern "C" int skm_lloyd_argmax_distance(skm_lloyd *L, double *maxdist, int64_t *j)
@@ -1309,9 +1520,9 @@ extern "C" int skm_fwht_sample_f32(skm_ctx *ctx, int64_t p2, int64_t n, int64_t 
     ds->store_dtype = SKM_F32;
     int rc = SKM_OK;
     do {
-        if ((rc = dev_alloc((void **)&ds->colptr, sizeof(int64_t) * (n + 1), "colptr"))) break;
-        if ((rc = dev_alloc((void **)&ds->rowidx, sizeof(int32_t) * ds->nnz, "rowidx"))) break;
-        if ((rc = dev_alloc(&ds->val, sizeof(float) * ds->nnz, "val"))) break;
+        if ((rc = skm_big_alloc(ds->ctx, (void **)&ds->colptr, sizeof(int64_t) * (n + 1), "colptr"))) break;
+        if ((rc = skm_big_alloc(ds->ctx, (void **)&ds->rowidx, sizeof(int32_t) * ds->nnz, "rowidx"))) break;
+        if ((rc = skm_big_alloc(ds->ctx, &ds->val, sizeof(float) * ds->nnz, "val"))) break;
         if (n == 0) { if ((rc = (cudaMemsetAsync(ds->colptr, 0, sizeof(int64_t), ctx->stream) == cudaSuccess) ? SKM_OK : SKM_ERR_CUDA)) break; }
         if ((rc = skm_launch_fwht_sample_f32(ctx, p2, n, m, x_dev, signs_dev, rows_dev, seed, col0, ds->colptr, ds->rowidx,
                                              (float *)ds->val))) break;
@@ -1365,9 +1576,9 @@ extern "C" int skm_dataset_from_dense_host(skm_ctx *ctx, int64_t p, int64_t p2, 
     ds->ctx = ctx; ds->p = p2; ds->n = n; ds->nnz = n * m; ds->store_dtype = SKM_F32;
     int rc = SKM_OK;
     do {
-        if ((rc = dev_alloc((void **)&ds->colptr, sizeof(int64_t) * (n + 1), "colptr"))) break;
-        if ((rc = dev_alloc((void **)&ds->rowidx, sizeof(int32_t) * ds->nnz, "rowidx"))) break;
-        if ((rc = dev_alloc(&ds->val, sizeof(float) * ds->nnz, "val"))) break;
+        if ((rc = skm_big_alloc(ds->ctx, (void **)&ds->colptr, sizeof(int64_t) * (n + 1), "colptr"))) break;
+        if ((rc = skm_big_alloc(ds->ctx, (void **)&ds->rowidx, sizeof(int32_t) * ds->nnz, "rowidx"))) break;
+        if ((rc = skm_big_alloc(ds->ctx, &ds->val, sizeof(float) * ds->nnz, "val"))) break;
         DevBuf raw[2], dense, dsign, scratch_colptr;
         std::vector<float> s32(p2);
         for (int64_t i = 0; i < p2; ++i) s32[i] = (float)signs[i];

@@ -9,6 +9,12 @@
 #define SKM_SLICE 32          // columns per SELL slice == warp width
 
 void skm_set_error(const char *fmt, ...);
+struct skm_ctx;
+// Big device arrays (the images of a dataset): cudaMalloc / cudaFree of gigabytes cost ~5 ms per GB and synchronise the
+// device; the stream-ordered pool keeps freed blocks for the next dataset (release threshold SKM_POOL_RETAIN_GB, default
+// 48) and frees without a device-wide stall.  Falls back to cudaMalloc when pools are unavailable or SKM_NO_POOL is set.
+int  skm_big_alloc(skm_ctx *ctx, void **ptr, size_t bytes, const char *what);
+void skm_big_free(skm_ctx *ctx, void *ptr);
 
 #define SKM_CUDA(call)                                                              \
     do {                                                                            \
@@ -66,7 +72,13 @@ struct skm_ctx {
     void       (*stream_cache_free)(void *);
     int64_t      tc_chunks;                 // chunks the tensor-core filter of the second pass ran on (and kept)
     int64_t      tc_chunks_dropped;         // chunks after which it was switched off (too many uncertain points)
+    bool         use_pool;                  // big arrays come from the device's stream-ordered memory pool
+    void        *bounce[2];                 // pinned staging for read-backs into pageable memory (lazily allocated)
+    cudaEvent_t  bounce_ev[2];
 };
+// device -> pageable host memory through two pinned staging buffers (a direct cudaMemcpy into fresh pageable memory
+// runs at ~4 GB/s); synchronises the stream
+int skm_d2h_pageable(skm_ctx *ctx, void *dst, const void *src_dev, size_t bytes);
 
 // RAII: records a start event now and a stop event at scope exit when timing is enabled
 struct SkmTimed {
@@ -226,6 +238,8 @@ int skm_build_csr(skm_dataset *ds);      // csr.cu
 // asynchronous pieces used by the streamed path (stream.cu); no host synchronisation inside
 int skm_launch_validate_async(skm_ctx *ctx, int64_t p, int64_t n, int64_t nnz, const int64_t *colptr,
                               const int32_t *rowidx, int *flags_dev /* [0]=error bits, [1]=max col nnz */);
+int skm_launch_validate_cols_async(skm_ctx *ctx, int64_t n, int64_t nnz, const int64_t *colptr, int *flags_dev);
+int skm_launch_validate_rows_async(skm_ctx *ctx, int64_t p, int64_t count, const int32_t *rowidx, int *flags_dev);
 int skm_launch_rebase_colptr(skm_ctx *ctx, const void *src, int src_type, int64_t count, int64_t base, int64_t *dst);
 int skm_build_sell_async(skm_ctx *ctx, skm_dataset *view, int32_t *width2_scratch, int64_t *elems_scratch,
                          void *cub_tmp, size_t cub_tmp_bytes);
@@ -299,6 +313,8 @@ int skm_launch_diff_assign(skm_ctx *ctx, int64_t n, int64_t K, const int32_t *as
                            const float *dist32, const double *dist64, int32_t *changed, int *nchanged, double *sumsq);
 int skm_launch_move_changed(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const int32_t *assign, int32_t *prev,
                             const int32_t *changed, const int *nchanged, int64_t nchanged_host, double *acc);
+// a_out[j] = a[j] + 1 (MATLAB indices), d_out[j] = (double)d[j]; either pair may be NULL
+int skm_launch_export(skm_ctx *ctx, int64_t n, const int32_t *a, int32_t *a_out, const float *d, double *d_out);
 int skm_launch_argmax(skm_ctx *ctx, int64_t n, const float *dist32, const double *dist64,
                       double *out_val, int64_t *out_idx);
 
@@ -316,6 +332,13 @@ int    skm_launch_tcs_resolve(skm_ctx *ctx, const skm_dataset *ds, int64_t K, co
                               const int32_t *flagged_in, const int *nflag_in, int64_t nflag_host, const uint32_t *cand,
                               const float *lb4, int32_t *assign, float *dist, float *lb, int32_t *flagged_out, int *nflag_out);
 int    skm_sell_ensure_any(skm_dataset *ds);
+int    skm_sell_layout_range(skm_dataset *ds, int mode, int64_t slice0, int64_t nsl, unsigned long long *ovf_dev);
+// csr.cu in three steps, so the row-major image can follow the upload chunk by chunk (chunks of whole 512-column tiles)
+struct SkmCsrBuild { void *counts, *offsets, *scan_tmp; size_t scan_bytes; int64_t max_tiles, nchunks; bool active; };
+int    skm_csr_begin(skm_dataset *ds, SkmCsrBuild *b, int64_t max_chunk_cols, int64_t nchunks);
+int    skm_csr_chunk(skm_dataset *ds, SkmCsrBuild *b, int64_t c, int64_t j0, int64_t j1, int64_t e0, int64_t e1);
+int    skm_csr_finish(skm_dataset *ds, SkmCsrBuild *b);
+void   skm_csr_abort(SkmCsrBuild *b);
 
 // tcgemm.cu: tensor-core (tcgen05, tf32) filter + exact evaluation of the candidates for the dense second pass
 bool   skm_tc_dense_usable(int64_t p, int64_t K);

@@ -218,7 +218,7 @@ struct SchedOut {
 };
 
 template <int NL>
-__global__ void k_sched_dual(int64_t n, int64_t nslices, int wmax, const int64_t *__restrict__ colptr,
+__global__ void k_sched_dual(int64_t n, int64_t slice0, int64_t nslices, int wmax, const int64_t *__restrict__ colptr,
                              const int32_t *__restrict__ rowidx, const int64_t *__restrict__ slice_ptr,
                              int4 *__restrict__ sell, unsigned long long *__restrict__ overflow_total)
 {
@@ -232,7 +232,7 @@ __global__ void k_sched_dual(int64_t n, int64_t nslices, int wmax, const int64_t
 
     const int64_t prob = (int64_t)blockIdx.x * nt + tid;  // half- / quarter-warp index
     if (prob >= PARTS * nslices) return;
-    const int64_t slice = prob / PARTS;
+    const int64_t slice = slice0 + prob / PARTS;           // slices [slice0, slice0 + nslices)
     const int half = (int)(prob % PARTS);
     const int64_t base = slice_ptr[slice];
     const int W = (int)((slice_ptr[slice + 1] - base) >> 5) * 2;
@@ -252,15 +252,15 @@ __global__ void k_sched_dual(int64_t n, int64_t nslices, int wmax, const int64_t
 }
 
 template <typename VT>
-__global__ void k_fill_sell_sched(int64_t p, int64_t n, int64_t nslices, int wmax, int boff, int nl,
+__global__ void k_fill_sell_sched(int64_t p, int64_t n, int64_t slice0, int64_t nslices, int wmax, int boff, int nl,
                                   const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
                                   const VT *__restrict__ val, const int64_t *__restrict__ slice_ptr,
                                   int4 *__restrict__ sell)
 {
     extern __shared__ unsigned short s_all[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
-    const int64_t warp = (int64_t)blockIdx.x * nwb + wib;
-    if (warp >= nslices) return;
+    if ((int64_t)blockIdx.x * nwb + wib >= nslices) return;
+    const int64_t warp = slice0 + (int64_t)blockIdx.x * nwb + wib;      // slice index
     // per warp: ord[wmax][32] (u16), start[16][32] (u16), code[wmax][32] (u8)
     unsigned short *ord = s_all + (size_t)wib * (wmax * 32 + 16 * 32 + wmax * 16);
     unsigned short *st = ord + (size_t)wmax * 32;
@@ -399,6 +399,28 @@ int skm_launch_validate_async(skm_ctx *ctx, int64_t p, int64_t n, int64_t nnz, c
         k_validate_rows<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p, nnz, rowidx, flags_dev);
         SKM_CHECK_LAUNCH(ctx);
     }
+    return SKM_OK;
+}
+
+// the two halves of the validation on their own (pipelined dataset creation): flags_dev as above
+int skm_launch_validate_cols_async(skm_ctx *ctx, int64_t n, int64_t nnz, const int64_t *colptr, int *flags_dev)
+{
+    if (n <= 0) return SKM_OK;
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    k_validate_cols<<<(unsigned)blocks, 256, 0, ctx->stream>>>(n, nnz, colptr, flags_dev);
+    SKM_CHECK_LAUNCH(ctx);
+    return SKM_OK;
+}
+int skm_launch_validate_rows_async(skm_ctx *ctx, int64_t p, int64_t count, const int32_t *rowidx, int *flags_dev)
+{
+    if (count <= 0) return SKM_OK;
+    int64_t blocks = (count + 255) / 256;
+    const int64_t cap = (int64_t)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    k_validate_rows<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p, count, rowidx, flags_dev);
+    SKM_CHECK_LAUNCH(ctx);
     return SKM_OK;
 }
 
@@ -545,8 +567,7 @@ int skm_build_sell(skm_dataset *ds)
     SKM_CUDA(cudaMemcpyAsync(ds->slice_ptr, hp.data(), sizeof(int64_t) * (nslices + 1),
                              cudaMemcpyHostToDevice, ctx->stream));
     size_t sell_bytes = sizeof(int4) * (size_t)(ds->sell_elems > 0 ? ds->sell_elems : 1);
-    e = cudaMalloc(&d, sell_bytes);
-    if (e != cudaSuccess) { skm_set_error("cudaMalloc(sell, %zu bytes) failed: %s", sell_bytes, cudaGetErrorString(e)); return SKM_ERR_NOMEM; }
+    SKM_TRY(skm_big_alloc(ctx, &d, sell_bytes, "sell"));
     ds->sell = (int4 *)d;
     ds->device_bytes += (int64_t)sell_bytes + (int64_t)sizeof(int64_t) * (nslices + 1);
     int wmax = 0;
@@ -555,6 +576,45 @@ int skm_build_sell(skm_dataset *ds)
     ds->sell_mode = -1;                 // filled lazily, in the entry order of the first kernel family that reads it
     ds->sell_plain = false;
     SKM_CUDA(cudaStreamSynchronize(ctx->stream));   // hp goes out of scope
+    return SKM_OK;
+}
+
+// Dual-table entry order (layout 1 or 2) of slices [slice0, slice0 + nsl): scheduler + fill, asynchronous on the context
+// stream.  The CSC entries of those slices' columns must be on the device; used slice range by slice range while an
+// upload is still in flight (api.cu, pipelined dataset creation) and for the whole image by skm_sell_ensure_layout.
+int skm_sell_layout_range(skm_dataset *ds, int mode, int64_t slice0, int64_t nsl, unsigned long long *ovf_dev)
+{
+    skm_ctx *ctx = ds->ctx;
+    if (nsl <= 0) return SKM_OK;
+    const int wmax = ds->sell_wmax;
+    if (wmax <= 0 || wmax > 254) { skm_set_error("dual-table layout needs columns of at most 254 entries"); return SKM_ERR_UNSUPPORTED; }
+    const int nl = mode == 1 ? 16 : 8;
+    // scheduler: one thread per half-/quarter-warp, as many as the scratch allows (interleaved shared memory)
+    const size_t per = (size_t)skm_bvn_bytes(nl);
+    int nt = (int)(((size_t)ctx->smem_optin - 1024) / per);
+    nt = nt >= 256 ? 256 : (nt & ~31);
+    if (nt < 32) { skm_set_error("dual-table scheduler does not fit in shared memory"); return SKM_ERR_UNSUPPORTED; }
+    const size_t smem = per * nt;
+    const int64_t probs = (32 / nl) * nsl;
+    if (nl == 16) {
+        SKM_CUDA(cudaFuncSetAttribute(k_sched_dual<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_sched_dual<16><<<(unsigned)((probs + nt - 1) / nt), nt, smem, ctx->stream>>>(
+            ds->n, slice0, nsl, wmax, ds->colptr, ds->rowidx, ds->slice_ptr, ds->sell, ovf_dev);
+    } else {
+        SKM_CUDA(cudaFuncSetAttribute(k_sched_dual<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_sched_dual<8><<<(unsigned)((probs + nt - 1) / nt), nt, smem, ctx->stream>>>(
+            ds->n, slice0, nsl, wmax, ds->colptr, ds->rowidx, ds->slice_ptr, ds->sell, ovf_dev);
+    }
+    SKM_CHECK_LAUNCH(ctx);
+    int warps = 8;
+    const size_t per_warp = (size_t)wmax * 64 + 16 * 64 + (size_t)wmax * 32;
+    while (warps > 1 && (size_t)warps * per_warp > (size_t)ctx->smem_optin - 1024) warps >>= 1;
+    const size_t smem2 = (size_t)warps * per_warp;
+    SKM_CUDA(cudaFuncSetAttribute(k_fill_sell_sched<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    k_fill_sell_sched<float><<<(unsigned)((nsl + warps - 1) / warps), warps * 32, smem2, ctx->stream>>>(
+        ds->p, ds->n, slice0, nsl, wmax, (int)skm_dual_boff(ds->p), nl, ds->colptr, ds->rowidx, (const float *)ds->val,
+        ds->slice_ptr, ds->sell);
+    SKM_CHECK_LAUNCH(ctx);
     return SKM_OK;
 }
 
@@ -576,37 +636,10 @@ int skm_sell_ensure_layout(skm_dataset *ds, int mode)
         return SKM_OK;
     }
     if (mode == 1 || mode == 2) {
-        if (wmax <= 0 || wmax > 254) { skm_set_error("dual-table layout needs columns of at most 254 entries"); return SKM_ERR_UNSUPPORTED; }
-        const int nl = mode == 1 ? 16 : 8;
-        // scheduler: one thread per half-/quarter-warp, as many as the scratch allows (interleaved shared memory)
-        const size_t per = (size_t)skm_bvn_bytes(nl);
-        int nt = (int)(((size_t)ctx->smem_optin - 1024) / per);
-        nt = nt >= 256 ? 256 : (nt & ~31);
-        if (nt < 32) { skm_set_error("dual-table scheduler does not fit in shared memory"); return SKM_ERR_UNSUPPORTED; }
-        const size_t smem = per * nt;
         DevBuf ovf;
         SKM_TRY(ovf.alloc(sizeof(unsigned long long)));
         SKM_CUDA(cudaMemsetAsync(ovf.ptr, 0, sizeof(unsigned long long), ctx->stream));
-        const int64_t probs = (32 / nl) * nslices;
-        if (nl == 16) {
-            SKM_CUDA(cudaFuncSetAttribute(k_sched_dual<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_sched_dual<16><<<(unsigned)((probs + nt - 1) / nt), nt, smem, ctx->stream>>>(
-                n, nslices, wmax, ds->colptr, ds->rowidx, ds->slice_ptr, ds->sell, ovf.as<unsigned long long>());
-        } else {
-            SKM_CUDA(cudaFuncSetAttribute(k_sched_dual<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_sched_dual<8><<<(unsigned)((probs + nt - 1) / nt), nt, smem, ctx->stream>>>(
-                n, nslices, wmax, ds->colptr, ds->rowidx, ds->slice_ptr, ds->sell, ovf.as<unsigned long long>());
-        }
-        SKM_CHECK_LAUNCH(ctx);
-        int warps = 8;
-        const size_t per_warp = (size_t)wmax * 64 + 16 * 64 + (size_t)wmax * 32;
-        while (warps > 1 && (size_t)warps * per_warp > (size_t)ctx->smem_optin - 1024) warps >>= 1;
-        const size_t smem2 = (size_t)warps * per_warp;
-        SKM_CUDA(cudaFuncSetAttribute(k_fill_sell_sched<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        k_fill_sell_sched<float><<<(unsigned)((nslices + warps - 1) / warps), warps * 32, smem2, ctx->stream>>>(
-            ds->p, n, nslices, wmax, (int)skm_dual_boff(ds->p), nl, ds->colptr, ds->rowidx, (const float *)ds->val,
-            ds->slice_ptr, ds->sell);
-        SKM_CHECK_LAUNCH(ctx);
+        SKM_TRY(skm_sell_layout_range(ds, mode, 0, nslices, ovf.as<unsigned long long>()));
         SKM_CUDA(cudaStreamSynchronize(ctx->stream));          // ovf dies here
         ds->sell_mode = mode; ds->sell_plain = false;
         return SKM_OK;

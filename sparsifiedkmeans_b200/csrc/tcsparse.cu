@@ -669,7 +669,7 @@ size_t skm_tcs_bimg_bytes(int64_t p, int64_t K)
 
 void skm_tsb_free(skm_dataset *ds)
 {
-    cudaFree(ds->tsb); ds->tsb = nullptr;
+    skm_big_free(ds->ctx, ds->tsb); ds->tsb = nullptr;
     cudaFree(ds->tsb_ptr); ds->tsb_ptr = nullptr;
     cudaFree(ds->colnorm2); ds->colnorm2 = nullptr;
     cudaFree(ds->xmax_bits); ds->xmax_bits = nullptr;
@@ -685,8 +685,8 @@ int skm_tsb_build(skm_dataset *ds)
     const int64_t nblk = ntiles * S;
     auto fail = [&](int rc) { skm_tsb_free(ds); return rc; };
     cudaError_t e;
-    if ((e = cudaMalloc((void **)&ds->tsb, sizeof(uint2) * (size_t)std::max<int64_t>(ds->nnz, 1))) != cudaSuccess ||
-        (e = cudaMalloc((void **)&ds->tsb_ptr, sizeof(int64_t) * (size_t)(nblk + 1))) != cudaSuccess ||
+    if (skm_big_alloc(ctx, (void **)&ds->tsb, sizeof(uint2) * (size_t)std::max<int64_t>(ds->nnz, 1), "tile/stripe image") != SKM_OK) return fail(SKM_ERR_NOMEM);
+    if ((e = cudaMalloc((void **)&ds->tsb_ptr, sizeof(int64_t) * (size_t)(nblk + 1))) != cudaSuccess ||
         (e = cudaMalloc((void **)&ds->colnorm2, sizeof(float) * (size_t)ds->n)) != cudaSuccess ||
         (e = cudaMalloc((void **)&ds->xmax_bits, sizeof(int) * 4)) != cudaSuccess) {
         cudaGetLastError();

@@ -566,6 +566,27 @@ int skm_launch_finalize_peers(skm_ctx *ctx, int64_t p, int64_t K, int ndev, cons
     return SKM_OK;
 }
 
+namespace {
+__global__ void k_export(int64_t n, const int32_t *__restrict__ a, int32_t *__restrict__ a_out, const float *__restrict__ d,
+                         double *__restrict__ d_out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        if (a_out) a_out[j] = a[j] + 1;
+        if (d_out) d_out[j] = (double)d[j];
+    }
+}
+}  // namespace
+
+int skm_launch_export(skm_ctx *ctx, int64_t n, const int32_t *a, int32_t *a_out, const float *d, double *d_out)
+{
+    if (n <= 0 || (!a_out && !d_out)) return SKM_OK;
+    const int64_t blocks = std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
+    k_export<<<(unsigned)blocks, 256, 0, ctx->stream>>>(n, a_out ? a : nullptr, a_out, d_out ? d : nullptr, d_out);
+    SKM_CHECK_LAUNCH(ctx);
+    return SKM_OK;
+}
+
 int skm_launch_argmax(skm_ctx *ctx, int64_t n, const float *dist32, const double *dist64,
                       double *out_val, int64_t *out_idx)
 {

@@ -133,8 +133,9 @@ class Dataset:
 
     # -- construction -----------------------------------------------------
     @classmethod
-    def from_csc(cls, p: int, n: int, jc, ir, val, store: str = "f32", ctx: Context | None = None):
-        """Upload host CSC arrays (any of int32/int64/uint64 indices, float32/float64 values)."""
+    def from_csc(cls, p: int, n: int, jc, ir, val, store: str = "f32", ctx: Context | None = None, K_hint: int = 0):
+        """Upload host CSC arrays (any of int32/int64/uint64 indices, float32/float64 values).  K_hint: the number of
+        centres the caller will use; large uploads then build that kernel family's entry order while they are in flight."""
         ctx = ctx or default_context()
         jc = np.ascontiguousarray(jc)
         ir = np.ascontiguousarray(ir)
@@ -148,18 +149,18 @@ class Dataset:
         if jc.shape[0] != n + 1:
             raise ValueError("jc must have n+1 entries")
         h = C.c_void_p()
-        check(ctx._lib.skm_dataset_create_csc(
+        check(ctx._lib.skm_dataset_create_csc_hint(
             ctx.handle, p, n, _ptr(jc), _NP_INDEX[jc.dtype], _ptr(ir), _NP_ROWS[ir.dtype],
-            _ptr(val), _NP_VALUE[val.dtype], SKM_F32 if store == "f32" else SKM_F64, 0, C.byref(h)))
+            _ptr(val), _NP_VALUE[val.dtype], SKM_F32 if store == "f32" else SKM_F64, 0, int(K_hint), C.byref(h)))
         return cls(ctx, h)
 
     @classmethod
-    def from_scipy(cls, X, store: str = "f32", ctx: Context | None = None):
+    def from_scipy(cls, X, store: str = "f32", ctx: Context | None = None, K_hint: int = 0):
         """X: scipy.sparse matrix of shape (p, n), points as columns."""
         import scipy.sparse as sp
         X = sp.csc_matrix(X)
         X.sort_indices()
-        return cls.from_csc(X.shape[0], X.shape[1], X.indptr, X.indices, X.data, store, ctx)
+        return cls.from_csc(X.shape[0], X.shape[1], X.indptr, X.indices, X.data, store, ctx, K_hint)
 
     @classmethod
     def from_device_csc(cls, p: int, n: int, jc_ptr: int, jc_type: int, ir_ptr: int, ir_type: int,

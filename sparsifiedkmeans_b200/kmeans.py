@@ -316,7 +316,7 @@ def kmeans_sparsified(X=None, K=None, **opts):
         del Xm
         OUTPUT["TimeToSample"] = time.perf_counter() - t1
         ds = (MultiDataset.from_scipy(Xs, store=o["Store"], mctx=mctx) if mctx is not None
-              else Dataset.from_scipy(Xs, store=o["Store"], ctx=ctx))
+              else Dataset.from_scipy(Xs, store=o["Store"], ctx=ctx, K_hint=K))
     OUTPUT["Pipeline"] = pipeline
     OUTPUT["Devices"] = OUTPUT_devices
     make_lloyd = (lambda Kx, inc, bnd: MultiLloyd(ds, Kx, incremental=inc, bounded=bnd)) if mctx is not None else \
