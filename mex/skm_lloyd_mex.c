@@ -141,8 +141,9 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         if (h == MAX_H) mexErrMsgIdAndTxt("skm_b200:tooManyHandles", "too many live datasets");
         const int64_t p = (int64_t)mxGetM(prhs[1]), n = (int64_t)mxGetN(prhs[1]);
         g_h[h].K = (int64_t)mxGetScalar(prhs[2]);
-        skm_mex_check(skm_dataset_create_csc(ctx, p, n, mxGetJc(prhs[1]), SKM_I64, mxGetIr(prhs[1]), SKM_I64,
-                                             mxGetPr(prhs[1]), SKM_F64, SKM_F32, 0, &g_h[h].ds), NULL);
+        /* K as a hint: a large X is uploaded in chunks and the entry order for K centres is built under the upload */
+        skm_mex_check(skm_dataset_create_csc_hint(ctx, p, n, mxGetJc(prhs[1]), SKM_I64, mxGetIr(prhs[1]), SKM_I64,
+                                                  mxGetPr(prhs[1]), SKM_F64, SKM_F32, 0, g_h[h].K, &g_h[h].ds), NULL);
         int rc = skm_lloyd_create(g_h[h].ds, g_h[h].K, &g_h[h].L);
         if (rc != SKM_OK) { skm_dataset_destroy(g_h[h].ds); g_h[h].ds = NULL; skm_mex_check(rc, NULL); }
         plhs[0] = mxCreateDoubleScalar((double)h);

@@ -285,6 +285,8 @@ extern "C" void skm_dataset_destroy(skm_dataset *ds)
     cudaFree(ds->slice_ptr);
     cudaFree(ds->kpp_mind);
     cudaFree(ds->kpp_cum);
+    skm_big_free(ds->ctx, ds->kpp_flag);
+    cudaFree(ds->kpp_c);
     skm_big_free(ds->ctx, ds->csr);
     SKM_TRACE_POINT("destroy: big frees", tdd);
     cudaFree(ds->rowptr);
@@ -1658,13 +1660,27 @@ static int kpp_update_common(skm_dataset *ds, const double *center, int has_gamm
     }
     std::vector<double> c(center, center + p);
     if (has_gamma) for (int64_t i = 0; i < p; ++i) c[i] = center[i] / gamma;    // full(centers)/gamma, IEEE division
-    DevBuf dc;
-    SKM_TRY(dc.alloc(sizeof(double) * std::max<int64_t>(p, 1)));
-    SKM_TRY(h2d(ctx, dc.ptr, c.data(), sizeof(double) * p));
-    SKM_TRY(skm_launch_kpp_update(ctx, ds, dc.as<double>(), first, ds->kpp_mind, masked));
+    // scratch kept with the dataset: a cudaMalloc / cudaFree pair per round costs more than the round's kernels at 8 GPUs
+    if (!ds->kpp_c) SKM_TRY(dev_alloc((void **)&ds->kpp_c, sizeof(double) * (p + 1) + sizeof(float) * (p + 4), "kpp centre"));
+    double *dcp = ds->kpp_c;
+    float *c32p = reinterpret_cast<float *>(ds->kpp_c + p + 1);
+    SKM_CUDA(cudaStreamSynchronize(ctx->stream));                     // `c` of the previous call is no longer being copied
+    SKM_TRY(h2d(ctx, dcp, c.data(), sizeof(double) * p));
+    ds->kpp_last_exact = -1;
+    if (!first && !masked && skm_kpp_filter_usable(ctx, ds)) {
+        // rounds after the first: an fp32 pass proves for most columns that the new centre is farther than their
+        // current minimum; only the rest is evaluated in fp64 (values stay bit-identical to the reference's)
+        if (!ds->kpp_flag) SKM_TRY(skm_big_alloc(ctx, (void **)&ds->kpp_flag, sizeof(int32_t) * (n + 4), "kpp filter list"));
+        SKM_TRY(skm_sell_ensure_any(ds));
+        int *nflag = reinterpret_cast<int *>(ds->kpp_flag + n);
+        SKM_TRY(skm_launch_kpp_update_filtered(ctx, ds, dcp, ds->kpp_mind, c32p, ds->kpp_flag, nflag));
+        SKM_CUDA(cudaMemcpyAsync(ctx->h_flag + 11, nflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        ds->kpp_last_exact = -2;                                      // in h_flag[11] once the block sums have been read
+    } else SKM_TRY(skm_launch_kpp_update(ctx, ds, dcp, first, ds->kpp_mind, masked));
     SKM_TRY(skm_launch_scan_sq(ctx, n, ds->kpp_mind, ds->kpp_cum));
     std::vector<double> bs(nb);
     SKM_TRY(d2h_sync(ctx, bs.data(), ds->kpp_cum, sizeof(double) * nb));
+    if (ds->kpp_last_exact == -2) ds->kpp_last_exact = ctx->h_flag[11];
     double tot = 0.0;
     for (int64_t b = 0; b < nb; ++b) tot += bs[b];
     if (sum_d2) *sum_d2 = tot;

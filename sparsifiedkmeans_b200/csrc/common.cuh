@@ -150,6 +150,9 @@ struct skm_dataset {
     // k-means++ running minimum distance (allocated on first use)
     double  *kpp_mind;                  // [n]
     double  *kpp_cum;                   // [n] inclusive scan of mind^2
+    int32_t *kpp_flag;                  // [n] columns the fp32 filter of a k-means++ round could not skip; then the counter
+    double  *kpp_c;                     // [p] scaled centre of the current round, then float[p + 2] (its fp32 copy, max |c|)
+    int64_t  kpp_last_exact;            // columns the last round evaluated exactly (-1: all of them)
     // tile/stripe block image for the tensor-core filter (tcsparse.cu), built on first use
     uint2   *tsb;                       // [nnz] (key, value bits), blocks of (128 columns x 64 rows)
     int64_t *tsb_ptr;                   // [ntiles * stripes + 1]
@@ -367,3 +370,6 @@ int skm_launch_sample_rows(skm_ctx *ctx, int64_t p2, int64_t n, int64_t m, uint6
 int skm_launch_kpp_update(skm_ctx *ctx, const skm_dataset *ds, const double *c_scaled /* dev [p] */,
                           int first, double *mind, int masked = 0);
 int skm_launch_scan_sq(skm_ctx *ctx, int64_t n, const double *mind, double *cum);
+bool skm_kpp_filter_usable(const skm_ctx *ctx, const skm_dataset *ds);
+int skm_launch_kpp_update_filtered(skm_ctx *ctx, const skm_dataset *ds, const double *c_scaled, double *mind,
+                                   float *c32, int32_t *flagged, int *nflag);

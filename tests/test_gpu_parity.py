@@ -335,3 +335,31 @@ def test_upload_accepts_uint16_rows(ctx):
     wa, _, _ = host_ref.find_cluster_assignments(X, c, gamma)
     assert np.array_equal(a, wa)
     ds.close()
+
+
+@pytest.mark.parametrize("kind", ["mixture", "unstructured"])
+def test_kpp_filtered_rounds_match_reference(ctx, kind):
+    """Rounds after the first run an fp32 filter in front of the exact pass (n >= 65536): the running minimum stays
+    bit-identical to the reference's recomputation, with and without the filter."""
+    import os
+    from sparsifiedkmeans_b200 import Dataset
+    X, _, gamma = make_sparsified(p=128, n=70000, m=12, K=6, seed=31, kind=kind, ragged=True)
+    ds = Dataset.from_scipy(X, store="f32", ctx=ctx)
+    chosen = [11, 40000, 123, 69999, 5, 31000]
+    for i, j in enumerate(chosen):
+        tot = ds.kpp_update(np.asarray(X[:, j].todense()).ravel(), gamma, first=(i == 0))
+        cen = np.asarray(X[:, chosen[: i + 1]].todense())
+        _, wd, _ = host_ref.find_cluster_assignments(X, cen, gamma, centers_sparse=False)
+        assert np.array_equal(ds.kpp_mindist(), wd), f"round {i}"
+        np.testing.assert_allclose(tot, np.sum(wd ** 2), rtol=1e-12)
+    got = ds.kpp_mindist().copy()
+    ds.close()
+    os.environ["SKM_NO_KPP_FILTER"] = "1"
+    try:
+        ds = Dataset.from_scipy(X, store="f32", ctx=ctx)
+        for i, j in enumerate(chosen):
+            ds.kpp_update(np.asarray(X[:, j].todense()).ravel(), gamma, first=(i == 0))
+        assert np.array_equal(ds.kpp_mindist(), got)
+        ds.close()
+    finally:
+        del os.environ["SKM_NO_KPP_FILTER"]
