@@ -233,6 +233,81 @@ __global__ void __launch_bounds__(32 * W) k_fwht_cta(int64_t n, float *__restric
     }
 }
 
+// Variant without warp shuffles (an experiment, kept behind SKM_FWHT_X=1; NEGATIVE result, profiles/r2_fwht.md).  The five
+// lane-bit stages of k_fwht_cta cost 160 SHFL + 160 FMA per thread and column; shuffles and shared-memory accesses share
+// the same issue port, and the hypothesis was that this port, not HBM, bounds k_fwht_cta (ncu: l1tex 63 %, issue 55 %,
+// DRAM 4.1 of 6.5 TB/s).  Here the warp's 32 x 32 block is TRANSPOSED through shared memory
+// instead (padded stride 33: conflict-free both ways), so the lane bits become register-slot bits and all ten low stages
+// run as plain register butterflies: 128 shared-memory instructions per thread and column instead of 224 port slots, and
+// 160 fewer FMAs.  The padded transpose layout is exactly the padded natural layout the warp-bit exchange reads, so the
+// values are written back in place and one __syncthreads separates the two uses.
+template <int W>
+__global__ void __launch_bounds__(32 * W) k_fwht_cta_x(int64_t n, float *__restrict__ x, const float *__restrict__ signs, float divide_by)
+{
+    extern __shared__ __align__(16) unsigned char fc_raw[];
+    float *s = reinterpret_cast<float *>(fc_raw);          // W x 1056 floats: one pad word per 32
+    constexpr int T = 32 * W, P2 = 1024 * W, G = 32 / W;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float *sw = s + w * 1056;
+    for (int64_t col = blockIdx.x; col < n; col += gridDim.x) {
+        float *g = x + col * P2;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int idx = (w << 10) | (j << 5) | lane;
+            float t = __ldcs(g + idx);
+            if (signs) t *= __ldg(signs + idx);
+            v[j] = t;
+        }
+#pragma unroll
+        for (int h = 1; h < 32; h <<= 1) {                  // index bits 5..9
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (!(j & h)) { const float a = v[j], b = v[j + h]; v[j] = a + b; v[j + h] = a - b; }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sw[j * 33 + lane] = v[j];
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = sw[lane * 33 + j];          // (slot j, lane l) <- (slot l, lane j)
+#pragma unroll
+        for (int h = 1; h < 32; h <<= 1) {                  // index bits 0..4
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (!(j & h)) { const float a = v[j], b = v[j + h]; v[j] = a + b; v[j + h] = a - b; }
+        }
+        // element (w << 10) | (lane << 5) | j lives at padded address idx + (idx >> 5) = w * 1056 + lane * 33 + j
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sw[lane * 33 + j] = v[j];
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+#pragma unroll
+            for (int jw = 0; jw < W; ++jw) {
+                const int nidx = (jw << 10) | (i * T + threadIdx.x);
+                v[i * W + jw] = s[nidx + (nidx >> 5)];
+            }
+        }
+#pragma unroll
+        for (int h = 1; h < W; h <<= 1) {                   // index bits 10..
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                if (!((q % W) & h)) { const float a = v[q], b = v[q + h]; v[q] = a + b; v[q + h] = a - b; }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+#pragma unroll
+            for (int jw = 0; jw < W; ++jw) {
+                float t = v[i * W + jw];
+                if (divide_by != 0.f) t = __fdiv_rn(t, divide_by);
+                __stcs(g + ((jw << 10) | (i * T + threadIdx.x)), t);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // Same transform with the NEXT column prefetched by the TMA while the current one is finished: a column of
 // p2 >= 8192 fills the CTA's shared memory, so only one is resident per SM and, without this, nothing is in flight
 // between the last load of a column and the first load of the next (ncu: profiles/r2_fwht.md).  The column buffer
@@ -331,9 +406,11 @@ int launch_fwht_warp(skm_ctx *ctx, int64_t n, float *x, const float *signs, floa
 template <int W>
 int launch_fwht_cta(skm_ctx *ctx, int64_t n, float *x, const float *signs, float divide_by)
 {
-    const size_t smem = (size_t)1024 * W * sizeof(float);
     static const bool no_tma = getenv("SKM_FWHT_NO_TMA") != nullptr;
-    auto kern = (W >= 8 && !no_tma) ? k_fwht_cta_tma<W> : k_fwht_cta<W>;
+    static const char *xe = getenv("SKM_FWHT_X");           // 1: shuffle-free variant for every size, 0: never
+    const bool use_x = xe ? atoi(xe) != 0 : false;          // measured 3-14 % SLOWER than the shuffle kernels at every size: opt-in only
+    const size_t smem = use_x ? (size_t)1056 * W * sizeof(float) : (size_t)1024 * W * sizeof(float);
+    auto kern = use_x ? k_fwht_cta_x<W> : ((W >= 8 && !no_tma) ? k_fwht_cta_tma<W> : k_fwht_cta<W>);
     SKM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     SKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * W, smem));
