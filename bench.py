@@ -347,6 +347,21 @@ class Rig:
                              "(use --impl reference for the CPU arm)")
         torch.cuda.set_device(self.local)
         self.dev = torch.device(f"cuda:{self.local}")
+        # Host side of the end-to-end leg: run this rank, and allocate its pinned buffers, on the CPUs next to its GPU
+        # (NVML's ideal affinity).  Without it the 8 ranks of one box share one NUMA node's memory and root complex and
+        # the per-rank H2D rate drops from 54 to 22 GB/s.  Restored before the CPU baseline is timed.
+        self.affinity_all = None
+        self.affinity = None
+        try:
+            import pynvml
+            self.affinity_all = os.sched_getaffinity(0)
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.local]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else self.local
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(idx))
+            self.affinity = sorted(os.sched_getaffinity(0))
+        except Exception:
+            pass
         if self.world > 1:
             # keep stdout to the one JSON line: whatever NCCL logs (its version banner at WARN/VERSION/INFO) goes to stderr
             os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -355,6 +370,14 @@ class Rig:
         self.ext = torch.cuda.ExternalStream(self.ctx.stream, device=self.dev)
         self.ev0 = torch.cuda.Event(enable_timing=True)
         self.ev1 = torch.cuda.Event(enable_timing=True)
+
+    def unbind(self):
+        """back to every core (the CPU baseline uses all host threads)"""
+        if self.affinity_all:
+            try:
+                os.sched_setaffinity(0, self.affinity_all)
+            except Exception:
+                pass
 
     def fence(self):
         if self.world > 1:
@@ -690,6 +713,8 @@ def run_ours(args):
             e2e["int32_rows_variant"] = {k: e2e_i32[k] for k in ("value", "ms_per_step", "h2d_bytes_per_step")}
         else:
             e2e = e2e_i32
+        if rig.affinity is not None:
+            e2e["host_cpus_bound_to_gpu"] = len(rig.affinity)
 
     legs = {}
     # Whole-job variant (reported beside the per-step number above, never instead of it): what one
@@ -805,6 +830,7 @@ def run_ours(args):
     if rank == 0:
         cpu = None
         if not args.no_cpu:
+            rig.unbind()
             r, sample, kind, cores = cpu_rate(cfg, args.cpu_seconds, os.cpu_count() or 1)
             cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
         out = {
