@@ -555,6 +555,8 @@ def modes_at_fixed_point(rig, L, n, m, steps, gamma):
             return {"ms_per_step": ms_i, "value": rig.world * n / (ms_i * 1e-3), "unit": UNIT, "last_update": kind,
                     "columns_moved_last_step": nch, "columns_reevaluated_last_step": L.last_assign_flagged(),
                     "assign_ms": k1i, "assign_algorithmic_GBps": alg_bytes / (k1i * 1e-3) / 1e9 if k1i else None,
+                    "assign_frac_of_hbm_peak": (alg_bytes / (k1i * 1e-3) / 1e9 / _peaks()[0]) if k1i else None,
+                    "assign_kernel": "k_assign_bounded (one centre value per entry)" if bounded else L.kernel_name,
                     "objective": sti.objective}
         except Exception as e:                              # never let the extra legs break the contract line
             return {"error": repr(e)}
@@ -849,6 +851,8 @@ def run_ours(args):
             "rechecked_last_step": main["rechecked_last_step"], "objective": main["objective"],
         }
         out.update(legs)
+        if e2e and isinstance(e2e.get("whole_job_variant"), dict):
+            out["whole_job"] = e2e["whole_job_variant"]          # first-class copy: upload once + images + iterations + read-back
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
