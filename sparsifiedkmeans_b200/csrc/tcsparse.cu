@@ -57,8 +57,11 @@ constexpr int TS_DW = 1;                             // densifier warps per oper
 constexpr int TS_REGE = 16;                          // entries per lane held in registers per block (16 x 32 = 512 per block)
 // operand stages: the stage round trip (MMAs complete -> zeros back -> new pairs -> fence -> MMA issue) is ~1500 cycles
 // against 256 (N = 64) or 512 (N = 128) cycles of MMA per block, so as many stages as shared memory holds
-__host__ __device__ constexpr int ts_stages(int BN) { return BN <= 64 ? 6 : 4; }
-__host__ __device__ constexpr int ts_threads(int BN) { return 32 * (6 + ts_stages(BN) * TS_DW); }
+// HAMMER > 0 (micro-benchmark only, SKM_TC_HAMMER=1): that many extra warps stream LDS.128 from a 16 KB region for as
+// long as the filter runs, to measure whether the MMAs' operand fetch and the LSU share their shared-memory bandwidth
+__host__ __device__ constexpr int ts_stages(int BN, int HAMMER = 0) { return BN <= 64 ? (HAMMER ? 5 : 6) : 4; }
+__host__ __device__ constexpr int ts_threads(int BN, int HAMMER = 0) { return 32 * (6 + ts_stages(BN, HAMMER) * TS_DW + HAMMER); }
+constexpr int TS_HAMMER_BYTES = 16384;
 constexpr int TS_MAXS = 64;                          // stripes the builder keeps counters for (p <= 4096)
 
 // ---------------------------------------------------------------- PTX helpers (same idioms as tcgemm.cu)
@@ -312,16 +315,17 @@ struct TcsParams {
     uint32_t      *cand;           // second | third << 16
     float         *lb4;            // lower bound on the distance to every centre outside the best three
     float         *dbg_scores;     // optional [n][BN] raw scores (tests)
+    unsigned long long *hammer_out; // micro-benchmark counters (HAMMER instantiation only)
 };
 
-template <int BN>
-__global__ void __launch_bounds__(ts_threads(BN), 1) k_tcs_filter(const TcsParams P)
+template <int BN, int HAMMER>
+__global__ void __launch_bounds__(ts_threads(BN, HAMMER), 1) k_tcs_filter(const TcsParams P)
 {
     constexpr int T = 256 / BN;                       // tiles per super-tile: one set of accumulators = 256 TMEM columns
     constexpr int LOG_T = (T == 2) ? 1 : 2;
     constexpr int NB = 2;                             // stages of the centre image
-    constexpr int TS_STAGES = ts_stages(BN);
-    constexpr int TS_THREADS = ts_threads(BN);
+    constexpr int TS_STAGES = ts_stages(BN, HAMMER);
+    constexpr int TS_THREADS = ts_threads(BN, HAMMER);
     constexpr uint32_t B_BYTES = BN * 256;            // 2 k-blocks x BN rows x 128 bytes
     static_assert(BN == 64 || BN == 128, "BN");
     extern __shared__ __align__(1024) unsigned char ts_smem[];
@@ -346,6 +350,7 @@ __global__ void __launch_bounds__(ts_threads(BN), 1) k_tcs_filter(const TcsParam
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (HAMMER > 0 && threadIdx.x == 0) { tmem_slot[2] = 0; tmem_slot[3] = 0; }
     {   // operand stages start as zero tiles; the densifiers keep them zero outside the block in flight
         int4 *z = reinterpret_cast<int4 *>(smA);
         for (int i = threadIdx.x; i < TS_STAGES * TS_A_BYTES / 16; i += TS_THREADS) z[i] = make_int4(0, 0, 0, 0);
@@ -465,6 +470,31 @@ __global__ void __launch_bounds__(ts_threads(BN), 1) k_tcs_filter(const TcsParam
                 }
             }
         }
+    } else if (HAMMER > 0 && warp >= 6 + TS_STAGES * TS_DW) {
+        // ===== micro-benchmark: LSU shared-memory reads while the MMAs fetch their operands =====
+        volatile int *stop = reinterpret_cast<volatile int *>(tmem_slot + 2);
+        const int4 *hb = reinterpret_cast<const int4 *>(reinterpret_cast<unsigned char *>(tmem_slot) + 64);
+        int4 a0 = make_int4(0, 0, 0, 0), a1 = a0, a2 = a0, a3 = a0;
+        unsigned long long iters = 0;
+        const uint32_t hba = s32(hb) + lane * 16;
+        const long long t0 = clock64();
+        for (;;) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {                      // volatile asm: the loads stay in the loop
+                int4 v;
+                asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                             : "r"(hba + (uint32_t)((r & 31) * 512)));
+                a0.x ^= v.x; a1.y ^= v.y; a2.z ^= v.z; a3.w ^= v.w;
+            }
+            iters += 32;                                      // LDS.128 warp-instructions per trip
+            if ((iters & 255) == 0 && *stop) break;
+        }
+        const long long t1 = clock64();
+        if (lane == 0 && P.hammer_out) {
+            atomicAdd(P.hammer_out, iters);
+            atomicMax(P.hammer_out + 1, (unsigned long long)(t1 - t0));
+            if ((a0.x ^ a1.y ^ a2.z ^ a3.w) == 0x12345678) P.hammer_out[2] = 1;      // keep the loads alive
+        }
     } else {
         // ===== densifiers: TS_DW warps per operand stage; a stage takes every TS_STAGES-th block of the CTA's sequence
         // (super-tile, stripe, tile); warp h of the stage takes entries h*32 + lane, + 32 TS_DW, ... of the block.
@@ -538,6 +568,11 @@ __global__ void __launch_bounds__(ts_threads(BN), 1) k_tcs_filter(const TcsParam
             advance(pn);
             issue_ptr(pn, o0n, o1n);
         }
+    }
+    if (HAMMER > 0 && warp < 4) {
+        // the epilogue warps finish last: the last one to arrive stops the hammer warps
+        __syncwarp();
+        if (lane == 0 && atomicAdd(reinterpret_cast<int *>(tmem_slot + 3), 1) == 3) *reinterpret_cast<volatile int *>(tmem_slot + 2) = 1;
     }
     tc_fence_before();
     __syncthreads();
@@ -630,19 +665,49 @@ __global__ void __launch_bounds__(256) k_tcs_resolve(const ResolveParams P)
     }
 }
 
-template <int BN>
-int launch_filter(skm_ctx *ctx, const TcsParams &P)
+template <int BN, int HAMMER>
+int launch_filter_h(skm_ctx *ctx, const TcsParams &P)
 {
     constexpr int NB = 2;
-    const size_t smem = 1024 + (size_t)ts_stages(BN) * TS_A_BYTES + (size_t)NB * BN * 256 + 256;
-    SKM_CUDA(cudaFuncSetAttribute(k_tcs_filter<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = 1024 + (size_t)ts_stages(BN, HAMMER) * TS_A_BYTES + (size_t)NB * BN * 256 + 256 + (HAMMER ? TS_HAMMER_BYTES : 0);
+    SKM_CUDA(cudaFuncSetAttribute(k_tcs_filter<BN, HAMMER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     constexpr int T = 256 / BN;
     const int64_t nst = (P.ntiles + T - 1) / T;
     const int64_t blocks = std::min<int64_t>(ctx->sm_count, nst);
     if (blocks < 1) return SKM_OK;
-    k_tcs_filter<BN><<<(unsigned)blocks, ts_threads(BN), smem, ctx->stream>>>(P);
+    k_tcs_filter<BN, HAMMER><<<(unsigned)blocks, ts_threads(BN, HAMMER), smem, ctx->stream>>>(P);
     SKM_CHECK_LAUNCH(ctx);
     return SKM_OK;
+}
+
+template <int BN>
+int launch_filter(skm_ctx *ctx, const TcsParams &P)
+{
+    static const char *h = getenv("SKM_TC_HAMMER");
+    if (BN == 64 && h && atoi(h) > 0) {
+        // micro-benchmark: 8 extra warps read shared memory with LDS.128 for as long as the filter runs
+        TcsParams Q = P;
+        DevBuf cnt;
+        SKM_TRY(cnt.alloc(4 * sizeof(unsigned long long)));
+        SKM_CUDA(cudaMemsetAsync(cnt.ptr, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        Q.hammer_out = cnt.as<unsigned long long>();
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, ctx->stream);
+        const int rc = launch_filter_h<64, 8>(ctx, Q);
+        cudaEventRecord(e1, ctx->stream);
+        unsigned long long hc[4] = {0, 0, 0, 0};
+        cudaMemcpyAsync(hc, cnt.ptr, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        const double sms = (double)std::min<int64_t>(ctx->sm_count, (P.ntiles + 3) / 4);
+        fprintf(stderr, "[skm tc hammer] filter %.3f ms with 8 LDS.128 warps per SM: %.1f B/clk/SM of LSU shared-memory reads (%llu warp-loads, %llu cycles)\n",
+                ms, hc[1] ? (double)hc[0] * 512.0 / sms / (double)hc[1] : 0.0, hc[0], hc[1]);
+        return rc;
+    }
+    return launch_filter_h<BN, 0>(ctx, P);
 }
 
 }  // namespace
@@ -777,7 +842,7 @@ int skm_launch_tcs_filter(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const 
     P.abs_unit = (float)(m * 260.0 / 33554432.0);
     P.ga = (float)(1.01 * (m + 5.0) * u32);
     P.sqrt_m = (float)(sqrt(m) * (1.0 + 1e-6));
-    P.assign = assign; P.lb = lb; P.cand = cand; P.lb4 = lb4; P.dbg_scores = dbg_scores;
+    P.assign = assign; P.lb = lb; P.cand = cand; P.lb4 = lb4; P.dbg_scores = dbg_scores; P.hammer_out = nullptr;
     if (skm_tcs_bn(K) == 64) return launch_filter<64>(ctx, P);
     return launch_filter<128>(ctx, P);
 }
