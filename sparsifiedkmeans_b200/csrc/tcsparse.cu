@@ -544,6 +544,9 @@ __global__ void __launch_bounds__(ts_threads(BN, HAMMER), 1) k_tcs_filter(const 
                 for (int e = TS_REGE * 32 * TS_DW; e < c_prev; e += 32 * TS_DW)
                     *reinterpret_cast<uint32_t *>(A + (b_prev[e].x & 0x7fffu)) = 0u;
             }
+            // a zero of the old block and a pair of the new one may target the same position from different lanes:
+            // order them (compute-sanitizer racecheck flags the pair otherwise; profiles/r2_tcsparse.md)
+            __syncwarp();
 #pragma unroll
             for (int t = 0; t < TS_REGE; ++t)
                 if (t * (32 * TS_DW) < c_cur) *reinterpret_cast<uint32_t *>(A + off[t]) = pk[t];
