@@ -228,6 +228,16 @@ int   skm_lloyd_accumulate(skm_lloyd *L);
 int   skm_lloyd_set_assign_mode(skm_lloyd *L, int mode);
 /* Columns the last bounded skm_lloyd_assign had to re-evaluate (-1: that call evaluated every column). */
 int   skm_lloyd_last_assign(skm_lloyd *L, int64_t *n_flagged);
+/* Partial-distance pruning of the full assignment pass (plans that need several launches, K > 16).  -1 (default):
+ * automatic, 0: off, 1: always try.  A pass over the first ~15 % of every column's stored entries for all K centres
+ * gives a candidate winner and -- every term of the masked distance being non-negative -- a lower bound on the distance
+ * to every other centre; the candidate is then evaluated exactly on all entries and kept iff it stays below that bound
+ * (rounding guards on both sides).  Columns that cannot be kept are evaluated against every centre (fp64, reference
+ * order, when they are fewer than n/16; otherwise the ordinary full pass runs and the pruned pass sits out 1, 2, 4, ... 32
+ * calls).  Assignments and distances are the same as without it. */
+int   skm_lloyd_set_prune(skm_lloyd *L, int mode);
+/* Columns the last pruned pass could not keep (-1: the last pass was not pruned) and the entry pairs it read per column. */
+int   skm_lloyd_last_prune(skm_lloyd *L, int64_t *not_kept, int64_t *pairs);
 /* Which kernels the full assignment pass of skm_lloyd_assign runs.  -1 (default): automatic.  1: the tensor-core
  * plan (SKM_F32 datasets, 2 <= K <= 128, p <= 4096; never chosen automatically: it measured 4.9 ms against 5.35 ms
  * per pass at K = 64 and needs a fourth image of X): every column is

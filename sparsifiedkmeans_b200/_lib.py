@@ -88,6 +88,8 @@ SIGNATURES = {
     "skm_lloyd_accumulate": (_int, [_vp]),
     "skm_lloyd_set_assign_mode": (_int, [_vp, _int]),
     "skm_lloyd_last_assign": (_int, [_vp, C.POINTER(_i64)]),
+    "skm_lloyd_set_prune": (_int, [_vp, _int]),
+    "skm_lloyd_last_prune": (_int, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "skm_lloyd_set_tc_filter": (_int, [_vp, _int]),
     "skm_lloyd_last_tc": (_int, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "skm_debug_tc_scores": (_int, [_vp, _int, C.c_double, _vp, C.POINTER(_i64)]),

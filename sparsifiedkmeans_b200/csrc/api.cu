@@ -736,6 +736,8 @@ static int skm_lloyd_create_ex(skm_dataset *ds, int64_t K, int want_f64_dist, sk
     memset(L, 0, sizeof *L);
     L->ds = ds; L->ctx = ds->ctx; L->K = K;
     L->tc_filter = -1;
+    L->prune_mode = -1;
+    L->last_prune[0] = L->last_prune[1] = -1;
     L->last_tc[0] = L->last_tc[1] = L->last_tc[2] = -1;
     const int64_t p = ds->p, n = ds->n;
     int rc = SKM_OK;
@@ -818,18 +820,55 @@ extern "C" int skm_lloyd_set_assign_mode(skm_lloyd *L, int mode)
         skm_set_error("the bounded assignment needs an SKM_F32 dataset");
         return SKM_ERR_UNSUPPORTED;
     }
-    if (mode == 1 && !L->lb) {
+    if (mode == 1) {
+        // each buffer on its own: the pruned / tensor-core passes may already have allocated some of them
         const int64_t p = L->ds->p, n = L->ds->n, K = L->K;
-        SKM_TRY(skm_big_alloc(L->ctx, (void **)&L->lb, sizeof(float) * n, "lb"));
-        SKM_TRY(dev_alloc((void **)&L->centers_prev, sizeof(double) * p * K, "centers_prev"));
-        SKM_TRY(dev_alloc((void **)&L->table_t, sizeof(float) * K * (p + 1), "table_t"));
-        SKM_TRY(dev_alloc((void **)&L->shift, sizeof(float) * (K + 4), "shift"));
-        SKM_TRY(dev_alloc((void **)&L->nchanged_pred, 16, "predict counter"));
+        if (!L->lb) SKM_TRY(skm_big_alloc(L->ctx, (void **)&L->lb, sizeof(float) * n, "lb"));
+        if (!L->centers_prev) SKM_TRY(dev_alloc((void **)&L->centers_prev, sizeof(double) * p * K, "centers_prev"));
+        if (!L->table_t) SKM_TRY(dev_alloc((void **)&L->table_t, sizeof(float) * K * (p + 1), "table_t"));
+        if (!L->shift) SKM_TRY(dev_alloc((void **)&L->shift, sizeof(float) * (K + 4), "shift"));
+        if (!L->nchanged_pred) SKM_TRY(dev_alloc(&L->nchanged_pred, 16, "predict counter"));
     }
     L->assign_mode = mode;
     L->lb_valid = false;
     L->bounded_skip = 0;
     L->bounded_backoff = 0;
+    return SKM_OK;
+}
+
+// ---- partial-distance pruning of the full pass (plans with several launches, K > 16) ----
+// Every term of the masked distance is non-negative, so the sum over a PREFIX of a column's entries is a lower bound of
+// its distance to that centre.  A pass over the first ~15 % of every column's entries for all K centres (the same
+// kernels, `max_pairs`) yields a candidate winner and, from the second-smallest partial sum minus its rounding guard, a
+// lower bound on the distance to every other centre; `k_assign_bounded` then evaluates the candidate exactly on all
+// entries and keeps it iff it stays below that bound.  Columns it cannot keep are evaluated against every centre (fp64
+// when fewer than n/16; the ordinary full pass when many, after which the pruned pass sits out 1, 2, 4, ... 32 calls).  Exact: a kept
+// winner beats a rigorous lower bound of every other centre.  It pays when clusters are separated (mixture at K = 64:
+// 5.4 -> ~2 ms per pass) and costs one wasted attempt in 33 on data without structure.
+static bool prune_wanted(skm_lloyd *L)
+{
+    if (L->prune_mode == 0) return false;
+    if (L->prune_mode == 1) return true;
+    static const char *e = getenv("SKM_PRUNE");
+    if (e && *e && atoi(e) == 0) return false;
+    if (L->prune_skip > 0) { L->prune_skip -= 1; return false; }
+    return true;
+}
+
+extern "C" int skm_lloyd_set_prune(skm_lloyd *L, int mode)
+{
+    SKM_REQUIRE(L, "NULL argument");
+    SKM_REQUIRE(mode >= -1 && mode <= 1, "prune mode must be -1 (automatic), 0 (off) or 1 (always try)");
+    L->prune_mode = mode;
+    L->prune_skip = L->prune_backoff = 0;
+    return SKM_OK;
+}
+
+extern "C" int skm_lloyd_last_prune(skm_lloyd *L, int64_t *not_kept, int64_t *pairs)
+{
+    SKM_REQUIRE(L, "NULL argument");
+    if (not_kept) *not_kept = L->last_prune[0];
+    if (pairs) *pairs = L->last_prune[1];
     return SKM_OK;
 }
 
@@ -1020,7 +1059,55 @@ extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
             L->bounded_skip = L->bounded_backoff;
         }
     }
-    if (use_tc) {
+    L->last_prune[0] = L->last_prune[1] = -1;
+    bool pruned = false;
+    {
+        const int64_t w2max = ds->uniform_width ? ds->sell_width2 : ds->sell_wmax / 2;
+        if (fast && !use_tc && pl.nchunks > 1 && !pl.global_table && w2max >= 8 && ds->n > 0 && prune_wanted(L)) {
+            const int64_t p = ds->p, n = ds->n, K = L->K;
+            if (!L->lb) SKM_TRY(skm_big_alloc(ctx, (void **)&L->lb, sizeof(float) * n, "lb"));
+            if (!L->table_t) SKM_TRY(dev_alloc((void **)&L->table_t, sizeof(float) * K * (p + 1), "table_t"));
+            if (!L->tc_zshift) {
+                SKM_TRY(dev_alloc((void **)&L->tc_zshift, sizeof(float) * (K + 4), "zero shift"));
+                SKM_CUDA(cudaMemsetAsync(L->tc_zshift, 0, sizeof(float) * (K + 4), ctx->stream));
+            }
+            int pairs = (int)((w2max * 15 + 99) / 100);
+            if (pairs < 4) pairs = 4;          // 8 entries: fewer leave too many columns to the fallback (profiles/r2_prune.md)
+            {
+                static const char *pe = getenv("SKM_PRUNE_PAIRS");          // tuning knob
+                if (pe && atoi(pe) > 0) pairs = atoi(pe);
+            }
+            int64_t nfl = 0;
+            {
+                SkmTimed t(ctx, SKM_T_ASSIGN);
+                SKM_TRY(skm_launch_build_table(ctx, p, K, L->cscaled_t, pl, L->table, L->cmax));
+                SKM_TRY(skm_launch_assign_fast(ctx, ds, K, pl, L->table, L->cmax, L->assign, L->dist_f32, L->best2,
+                                               L->flagged, L->nflag, nullptr, L->lb, pairs));
+                SKM_TRY(skm_launch_build_table_t(ctx, p, K, L->cscaled_t, L->table_t, L->cmax));
+                SKM_TRY(skm_launch_assign_bounded(ctx, ds, K, L->table_t, L->cmax, L->tc_zshift, L->assign, L->lb, L->dist_f32,
+                                                  L->flagged, L->nflag));
+                SKM_CUDA(cudaMemcpyAsync(ctx->h_flag + 10, L->nflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                SKM_CUDA(cudaStreamSynchronize(ctx->stream));
+                nfl = ctx->h_flag[10];
+            }
+            L->last_prune[0] = nfl; L->last_prune[1] = pairs;
+            // the fp64 re-evaluation costs ~3.4 us per 1000 columns at K = 64: up to n/16 columns the pruned pass still wins
+            if (nfl <= n / 16) {
+                SkmTimed t(ctx, SKM_T_RECHECK);
+                SKM_TRY(skm_launch_exact_assign(ctx, ea, L->assign, nullptr, L->dist_f32, L->flagged, L->nflag, n, L->lb));
+                L->prune_backoff = 0;
+                pruned = true;
+            } else {
+                // no structure to exploit (or centres far from converged): the full pass below redoes every column
+                L->prune_backoff = L->prune_backoff ? (L->prune_backoff < 32 ? 2 * L->prune_backoff : 32) : 1;
+                L->prune_skip = L->prune_backoff;
+            }
+        }
+    }
+    if (pruned) {
+        L->dist_is_f64 = false;
+        if (want_bounds) L->lb_valid = true;
+    } else if (use_tc) {
         SKM_TRY(tc_assign(L, ea, nullptr));
         L->dist_is_f64 = false;
         if (want_bounds) L->lb_valid = true;
@@ -1228,6 +1315,9 @@ extern "C" const char *skm_lloyd_kernel_name(skm_lloyd *L)
     const skm_dataset *ds = L->ds;
     if (ds->store_dtype == SKM_F32 && L->table && skm_fast_plan(ds->ctx, ds->p, L->K, &pl, ds->max_col_nnz)) {
         if (tc_wanted(L) && ds->tsb) snprintf(name, sizeof name, "k_tcs_filter<%d> + k_assign_bounded", skm_tcs_bn(L->K));
+        else if (L->last_prune[0] >= 0 && L->last_prune[0] <= ds->n / 16)
+            snprintf(name, sizeof name, "k_assign_fast<%d>%s x%d on %lld of the entry pairs + k_assign_bounded", pl.kc,
+                     pl.dual8 ? " (dual table)" : "", pl.nchunks, (long long)L->last_prune[1]);
         else if (pl.mode64) snprintf(name, sizeof name, "k_assign_fast64<%d>", pl.kc);
         else snprintf(name, sizeof name, "k_assign_fast<%d>%s%s x%d", pl.kc, pl.global_table ? " (global table)" : "",
                       pl.dual8 ? " (dual table)" : "", pl.nchunks);

@@ -42,6 +42,7 @@ struct FastParams {
     int32_t       *flagged;
     int           *nflag;
     float         *lb;           // optional: lower bound on the distance to every centre but the winner (bounded.cu)
+    int            max_pairs;    // > 0: only the first max_pairs entry pairs of every column (partial-distance pass)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -192,6 +193,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assign_fast(const FastParams 
         int w2;
         if (P.uniform) { base = slice * (int64_t)P.width2 * 32; w2 = P.width2; }
         else { base = P.slice_ptr[slice]; w2 = (int)((P.slice_ptr[slice + 1] - base) >> 5); }
+        if (P.max_pairs > 0 && w2 > P.max_pairs) w2 = P.max_pairs;     // partial pass: a prefix of every column's entries
         const int4 *src = P.sell + base + lane;
 
         float acc[KC];
@@ -263,6 +265,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assign_fast64(const FastParam
         int w2;
         if (P.uniform) { base = slice * (int64_t)P.width2 * 32; w2 = P.width2; }
         else { base = P.slice_ptr[slice]; w2 = (int)((P.slice_ptr[slice + 1] - base) >> 5); }
+        if (P.max_pairs > 0 && w2 > P.max_pairs) w2 = P.max_pairs;     // partial pass: a prefix of every column's entries
         const int4 *src = P.sell + base + lane;
 
         float acc[KC];
@@ -501,7 +504,7 @@ int skm_launch_build_table(skm_ctx *ctx, int64_t p, int64_t K, const double *ct,
 
 int skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const FastPlan &pl,
                            const float *table, const float *cmax, int32_t *assign, float *dist,
-                           float *best2, int32_t *flagged, int *nflag, const int *m_dev, float *lb)
+                           float *best2, int32_t *flagged, int *nflag, const int *m_dev, float *lb, int max_pairs)
 {
     SKM_CUDA(cudaMemsetAsync(nflag, 0, sizeof(int), ctx->stream));
     if (ds->n == 0) return SKM_OK;
@@ -528,6 +531,7 @@ int skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const
     P.flagged = flagged;
     P.nflag = nflag;
     P.lb = lb;
+    P.max_pairs = max_pairs;
     for (int c = 0; c < pl.nchunks; ++c) {
         P.table = table + (size_t)c * pl.rows * pl.ks;
         P.k0 = c * pl.kc;

@@ -208,6 +208,10 @@ struct skm_lloyd {
     int64_t  last_predicted_keep;   // columns the a-priori test proved to keep their centre (-1: not run)
     int64_t  last_bounded_flagged;   // columns the bounds could not keep (-1: the pass evaluated everything)
     int      bounded_skip, bounded_backoff;   // passes to sit out after a bounded pass that kept too few columns
+    // partial-distance pruning of the full pass (multi-launch plans, K > 16): -1 = automatic, 0 = off, 1 = always try
+    int      prune_mode;
+    int      prune_skip, prune_backoff;   // full passes to run unpruned after a pruned pass that kept too few columns
+    int64_t  last_prune[2];               // columns the pruned pass could not keep (-1: not tried), entry pairs it read
     // tensor-core filter plan (tcsparse.cu): -1 = automatic, 0 = off, 1 = on
     int      tc_filter;
     void    *tc_bimg;        // swizzled fp16 centre image
@@ -294,7 +298,7 @@ int  skm_launch_build_table(skm_ctx *ctx, int64_t p, int64_t K, const double *ct
 int  skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const FastPlan &pl,
                             const float *table, const float *cmax, int32_t *assign, float *dist,
                             float *best2, int32_t *flagged, int *nflag, const int *m_dev = nullptr,
-                            float *lb = nullptr);
+                            float *lb = nullptr, int max_pairs = 0);
 
 // bounded.cu
 int skm_launch_center_shift(skm_ctx *ctx, int64_t p, int64_t K, const double *centers, double *centers_prev,

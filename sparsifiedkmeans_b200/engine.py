@@ -384,6 +384,17 @@ class Lloyd:
         check(self._lib.skm_lloyd_last_assign(self.handle, C.byref(v)))
         return int(v.value)
 
+    def set_prune(self, mode):
+        """None: automatic; True / False: always / never try the partial-distance pruning of the full assignment pass
+        (skm_lloyd_set_prune, plans with several launches: K > 16); assignments are the same either way."""
+        check(self._lib.skm_lloyd_set_prune(self.handle, -1 if mode is None else (1 if mode else 0)))
+
+    def last_prune(self) -> tuple[int, int]:
+        """(columns the last pruned pass could not keep, entry pairs it read per column); (-1, -1): not pruned."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        check(self._lib.skm_lloyd_last_prune(self.handle, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def set_tc_filter(self, mode):
         """None: automatic; True / False: force the tensor-core plan of the full assignment pass on / off
         (skm_lloyd_set_tc_filter); assignments are the same either way."""

@@ -1,0 +1,102 @@
+"""Partial-distance pruning of the full assignment pass (skm_lloyd_set_prune): a prefix pass over ~15 % of every column's
+entries + the exact evaluation of its winner + the fallback give the oracle's assignments on separated AND on structureless
+data; the automatic mode backs off when nothing can be pruned."""
+import numpy as np
+import pytest
+
+from oracle import host_ref
+from tests.util import make_sparsified
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("kind", ["mixture", "unstructured"])
+@pytest.mark.parametrize("K,p,m,ragged", [(64, 1024, 51, False), (33, 256, 26, True), (100, 512, 40, False), (17, 784, 78, True)])
+def test_pruned_pass_matches_reference(ctx, kind, K, p, m, ragged):
+    from sparsifiedkmeans_b200 import Dataset, Lloyd
+    X, c, gamma = make_sparsified(p=p, n=6000, m=m, K=K, seed=K * 3 + p, kind=kind, f32=True, ragged=ragged)
+    ds = Dataset.from_scipy(X, store="f32", ctx=ctx)
+    wa, wd, _ = host_ref.find_cluster_assignments(X, c, gamma)
+    L = Lloyd(ds, K)
+    L.set_prune(True)
+    L.set_centers(c)
+    L.assign(gamma)
+    a, d = L.assignments()
+    assert np.array_equal(a, wa), f"{np.count_nonzero(a != wa)} assignments differ"
+    np.testing.assert_allclose(d, wd, rtol=2e-5, atol=1e-30)
+    not_kept, pairs = L.last_prune()
+    assert pairs >= 2 and 0 <= not_kept <= X.shape[1]
+    if kind == "mixture" and not ragged:
+        assert not_kept <= X.shape[1] // 20, "separated clusters: the prefix pass bounds (nearly) every other centre away"
+    # the sums that follow are the same as without pruning
+    L.accumulate(); L.finalize(gamma)
+    L0 = Lloyd(ds, K)
+    L0.set_prune(False)
+    L0.set_centers(c)
+    L0.assign(gamma); L0.accumulate(); L0.finalize(gamma)
+    assert L0.last_prune() == (-1, -1)
+    a0, _ = L0.assignments()
+    assert np.array_equal(a0, a)
+    np.testing.assert_array_equal(L.get_centers(), L0.get_centers())
+    L.close(); L0.close(); ds.close()
+
+
+def test_prune_trajectory_and_backoff(ctx):
+    """Automatic mode from a poor start, with and without the stateful modes: identical assignments every iteration;
+    on structureless data the pruned pass is tried, fails, and sits out the following calls."""
+    from sparsifiedkmeans_b200 import Dataset, Lloyd
+    X, c, gamma = make_sparsified(p=512, n=20000, m=26, K=48, seed=11, kind="mixture", f32=True)
+    rng = np.random.default_rng(3)
+    start = c[:, rng.integers(0, 48, 48)] + 0.3 * rng.standard_normal(c.shape)
+    ds = Dataset.from_scipy(X, store="f32", ctx=ctx)
+    runs = []
+    for prune, modes in [(False, False), (None, False), (True, True)]:
+        L = Lloyd(ds, 48, incremental=modes, bounded=modes)
+        L.set_prune(prune)
+        L.set_centers(start)
+        hist = []
+        for _ in range(10):
+            L.step(gamma, gamma)
+            hist.append(L.assignments(want_dist=False)[0].copy())
+        runs.append((hist, L.get_centers()))
+        L.close()
+    for hist, cen in runs[1:]:
+        for it, (h0, h1) in enumerate(zip(runs[0][0], hist)):
+            assert np.array_equal(h0, h1), f"iteration {it}: {np.count_nonzero(h0 != h1)} differ"
+        np.testing.assert_allclose(cen, runs[0][1], rtol=1e-9, atol=1e-12)
+    ds.close()
+    Xu, cu, gu = make_sparsified(p=512, n=20000, m=26, K=48, seed=12, kind="unstructured", f32=True)
+    dsu = Dataset.from_scipy(Xu, store="f32", ctx=ctx)
+    L = Lloyd(dsu, 48)
+    L.set_centers(cu)
+    tried = []
+    for _ in range(6):
+        L.assign(gu)
+        tried.append(L.last_prune()[0] >= 0)
+    wa, _, _ = host_ref.find_cluster_assignments(Xu, cu, gu)
+    assert np.array_equal(L.assignments(want_dist=False)[0], wa)
+    assert tried[0] and not all(tried), tried             # tried once, then backed off
+    L.close(); dsu.close()
+
+
+def test_modes_enabled_after_a_pruned_pass(ctx):
+    """The pruned pass allocates some of the bounded mode's buffers; switching the modes on afterwards must still work
+    (regression: set_assign_mode used to skip its own allocations when the bound array already existed)."""
+    from sparsifiedkmeans_b200 import Dataset, Lloyd
+    X, c, gamma = make_sparsified(p=512, n=12000, m=26, K=40, seed=21, kind="mixture", f32=True)
+    ds = Dataset.from_scipy(X, store="f32", ctx=ctx)
+    L = Lloyd(ds, 40)
+    L.set_centers(c + 0.2 * np.random.default_rng(1).standard_normal(c.shape))
+    L.step(gamma, gamma)
+    assert L.last_prune()[0] >= 0
+    L.set_update_mode(True)
+    L.set_assign_mode(True)
+    L0 = Lloyd(ds, 40)
+    L0.set_prune(False)
+    L0.set_centers(L.get_centers())
+    for _ in range(6):
+        L.step(gamma, gamma)
+        L0.step(gamma, gamma)
+        assert np.array_equal(L.assignments(want_dist=False)[0], L0.assignments(want_dist=False)[0])
+    np.testing.assert_allclose(L.get_centers(), L0.get_centers(), rtol=1e-9, atol=1e-12)
+    L.close(); L0.close(); ds.close()
