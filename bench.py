@@ -432,7 +432,7 @@ def k1_roofline(rig, L, tim, n, m, steps):
         pass
     return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak if achieved else None,
-            "traffic": traffic, "traffic_note": "ncu dram bytes of one launch x launches per pass x points",
+            "traffic": traffic, "traffic_note": "ncu dram bytes per point, summed over the launches of one pass (profiles/ncu_traffic.json), x points",
             "kernel": name, "launches_per_pass": launches_per_pass, "ms_per_launch": k1_ms_avg,
             "ms_per_pass": k1_ms_avg, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
             "step_breakdown_ms": {k: v[0] / steps for k, v in tim.items() if v[1]}}

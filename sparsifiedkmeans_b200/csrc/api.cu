@@ -711,6 +711,7 @@ extern "C" void skm_lloyd_destroy(skm_lloyd *L)
     cudaFree(L->stats);
     cudaFree(L->acc_local); skm_big_free(L->ctx, L->assign_prev); skm_big_free(L->ctx, L->changed); cudaFree(L->nchanged);
     skm_big_free(L->ctx, L->lb); cudaFree(L->centers_prev); cudaFree(L->table_t); cudaFree(L->shift); cudaFree(L->nchanged_pred);
+    cudaFree(L->prune_table16); cudaFree(L->prune_scale);
     cudaFree(L->tc_bimg); cudaFree(L->tc_scale); skm_big_free(L->ctx, L->tc_cand); skm_big_free(L->ctx, L->tc_lb4); cudaFree(L->tc_zshift); skm_big_free(L->ctx, L->flagged2);
     if (L->h_stats) cudaFreeHost(L->h_stats);
     if (L->h_counts) cudaFreeHost(L->h_counts);
@@ -845,6 +846,13 @@ extern "C" int skm_lloyd_set_assign_mode(skm_lloyd *L, int mode)
 // when fewer than n/16; the ordinary full pass when many, after which the pruned pass sits out 1, 2, 4, ... 32 calls).  Exact: a kept
 // winner beats a rigorous lower bound of every other centre.  It pays when clusters are separated (mixture at K = 64:
 // 5.4 -> ~2 ms per pass) and costs one wasted attempt in 33 on data without structure.
+// prefix launches on the half-precision table unless it does not fit or SKM_PRUNE_F32 asks for the fp32 kernels
+static bool prune_half_table(const skm_ctx *ctx, int64_t p, int64_t K, Prefix16Plan *hp)
+{
+    const bool f32 = getenv("SKM_PRUNE_F32") != nullptr;          // read every call: the tests switch it
+    return !f32 && skm_prefix16_plan(ctx, p, K, hp);
+}
+
 static bool prune_wanted(skm_lloyd *L)
 {
     if (L->prune_mode == 0) return false;
@@ -1080,10 +1088,22 @@ extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
             int64_t nfl = 0;
             {
                 SkmTimed t(ctx, SKM_T_ASSIGN);
-                SKM_TRY(skm_launch_build_table(ctx, p, K, L->cscaled_t, pl, L->table, L->cmax));
-                SKM_TRY(skm_launch_assign_fast(ctx, ds, K, pl, L->table, L->cmax, L->assign, L->dist_f32, L->best2,
-                                               L->flagged, L->nflag, nullptr, L->lb, pairs));
-                SKM_TRY(skm_launch_build_table_t(ctx, p, K, L->cscaled_t, L->table_t, L->cmax));
+                Prefix16Plan hp;
+                if (prune_half_table(ctx, p, K, &hp)) {
+                    // one launch over a half-precision table (prefix16.cu); cmax comes from the fp32 row table
+                    if (!L->prune_table16) {
+                        SKM_TRY(dev_alloc(&L->prune_table16, skm_prefix16_table_bytes(p, hp), "half-precision prefix table"));
+                        SKM_TRY(dev_alloc((void **)&L->prune_scale, 4 * sizeof(float), "prefix scale"));
+                    }
+                    SKM_TRY(skm_launch_build_table_t(ctx, p, K, L->cscaled_t, L->table_t, L->cmax));
+                    SKM_TRY(skm_launch_build_table16(ctx, p, K, L->cscaled_t, hp, L->cmax, L->prune_table16, L->prune_scale));
+                    SKM_TRY(skm_launch_prefix16(ctx, ds, K, hp, L->prune_table16, L->prune_scale, L->assign, L->best2, L->lb, pairs));
+                } else {
+                    SKM_TRY(skm_launch_build_table(ctx, p, K, L->cscaled_t, pl, L->table, L->cmax));
+                    SKM_TRY(skm_launch_assign_fast(ctx, ds, K, pl, L->table, L->cmax, L->assign, L->dist_f32, L->best2,
+                                                   L->flagged, L->nflag, nullptr, L->lb, pairs));
+                    SKM_TRY(skm_launch_build_table_t(ctx, p, K, L->cscaled_t, L->table_t, L->cmax));
+                }
                 SKM_TRY(skm_launch_assign_bounded(ctx, ds, K, L->table_t, L->cmax, L->tc_zshift, L->assign, L->lb, L->dist_f32,
                                                   L->flagged, L->nflag));
                 SKM_CUDA(cudaMemcpyAsync(ctx->h_flag + 10, L->nflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1315,9 +1335,15 @@ extern "C" const char *skm_lloyd_kernel_name(skm_lloyd *L)
     const skm_dataset *ds = L->ds;
     if (ds->store_dtype == SKM_F32 && L->table && skm_fast_plan(ds->ctx, ds->p, L->K, &pl, ds->max_col_nnz)) {
         if (tc_wanted(L) && ds->tsb) snprintf(name, sizeof name, "k_tcs_filter<%d> + k_assign_bounded", skm_tcs_bn(L->K));
-        else if (L->last_prune[0] >= 0 && L->last_prune[0] <= ds->n / 16)
-            snprintf(name, sizeof name, "k_assign_fast<%d>%s x%d on %lld of the entry pairs + k_assign_bounded", pl.kc,
-                     pl.dual8 ? " (dual table)" : "", pl.nchunks, (long long)L->last_prune[1]);
+        else if (L->last_prune[0] >= 0 && L->last_prune[0] <= ds->n / 16) {
+            Prefix16Plan hp;
+            if (prune_half_table(ds->ctx, ds->p, L->K, &hp))
+                snprintf(name, sizeof name, "k_prefix16<%d> x%d on %lld of the entry pairs + k_assign_bounded", hp.kc, hp.nchunks,
+                         (long long)L->last_prune[1]);
+            else
+                snprintf(name, sizeof name, "k_assign_fast<%d>%s x%d on %lld of the entry pairs + k_assign_bounded", pl.kc,
+                         pl.dual8 ? " (dual table)" : "", pl.nchunks, (long long)L->last_prune[1]);
+        }
         else if (pl.mode64) snprintf(name, sizeof name, "k_assign_fast64<%d>", pl.kc);
         else snprintf(name, sizeof name, "k_assign_fast<%d>%s%s x%d", pl.kc, pl.global_table ? " (global table)" : "",
                       pl.dual8 ? " (dual table)" : "", pl.nchunks);

@@ -211,6 +211,8 @@ struct skm_lloyd {
     // partial-distance pruning of the full pass (multi-launch plans, K > 16): -1 = automatic, 0 = off, 1 = always try
     int      prune_mode;
     int      prune_skip, prune_backoff;   // full passes to run unpruned after a pruned pass that kept too few columns
+    void    *prune_table16;  // half-precision centre table of the one-launch prefix (prefix16.cu)
+    float   *prune_scale;    // [4] its scale, 1/scale and rounding bound
     int64_t  last_prune[2];               // columns the pruned pass could not keep (-1: not tried), entry pairs it read
     // tensor-core filter plan (tcsparse.cu): -1 = automatic, 0 = off, 1 = on
     int      tc_filter;
@@ -299,6 +301,20 @@ int  skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, cons
                             const float *table, const float *cmax, int32_t *assign, float *dist,
                             float *best2, int32_t *flagged, int *nflag, const int *m_dev = nullptr,
                             float *lb = nullptr, int max_pairs = 0);
+
+// prefix16.cu: the prefix launch of the pruned pass on a half-precision table (all K <= 64 centres in one launch)
+struct Prefix16Plan {
+    int kc;           // centres per launch: 32 or 64
+    int row_bytes;    // table row: kc halves + 16 bytes of padding
+    int nchunks;      // launches (K > 64: several)
+    size_t smem;
+};
+bool   skm_prefix16_plan(const skm_ctx *ctx, int64_t p, int64_t K, Prefix16Plan *pl);
+size_t skm_prefix16_table_bytes(int64_t p, const Prefix16Plan &pl);
+int    skm_launch_build_table16(skm_ctx *ctx, int64_t p, int64_t K, const double *ct, const Prefix16Plan &pl, const float *cmax,
+                                void *table, float *scale);
+int    skm_launch_prefix16(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const Prefix16Plan &pl, const void *table,
+                           const float *scale, int32_t *assign, float *best2, float *lb, int max_pairs);
 
 // bounded.cu
 int skm_launch_center_shift(skm_ctx *ctx, int64_t p, int64_t K, const double *centers, double *centers_prev,

@@ -10,10 +10,17 @@ from tests.util import make_sparsified
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("prefix", ["half", "f32"])
 @pytest.mark.parametrize("kind", ["mixture", "unstructured"])
-@pytest.mark.parametrize("K,p,m,ragged", [(64, 1024, 51, False), (33, 256, 26, True), (100, 512, 40, False), (17, 784, 78, True)])
-def test_pruned_pass_matches_reference(ctx, kind, K, p, m, ragged):
+@pytest.mark.parametrize("K,p,m,ragged", [(64, 1024, 51, False), (33, 256, 26, True), (100, 512, 40, False), (17, 784, 78, True),
+                                          (130, 300, 40, True)])
+def test_pruned_pass_matches_reference(ctx, monkeypatch, prefix, kind, K, p, m, ragged):
+    """Both prefix kernels: the one-launch half-precision table (prefix16.cu, default) and the fp32 K1 kernels."""
     from sparsifiedkmeans_b200 import Dataset, Lloyd
+    if prefix == "f32":
+        monkeypatch.setenv("SKM_PRUNE_F32", "1")
+    else:
+        monkeypatch.delenv("SKM_PRUNE_F32", raising=False)
     X, c, gamma = make_sparsified(p=p, n=6000, m=m, K=K, seed=K * 3 + p, kind=kind, f32=True, ragged=ragged)
     ds = Dataset.from_scipy(X, store="f32", ctx=ctx)
     wa, wd, _ = host_ref.find_cluster_assignments(X, c, gamma)
@@ -26,6 +33,7 @@ def test_pruned_pass_matches_reference(ctx, kind, K, p, m, ragged):
     np.testing.assert_allclose(d, wd, rtol=2e-5, atol=1e-30)
     not_kept, pairs = L.last_prune()
     assert pairs >= 2 and 0 <= not_kept <= X.shape[1]
+    assert ("k_prefix16" in L.kernel_name) == (prefix == "half" and not_kept <= X.shape[1] // 16), L.kernel_name
     if kind == "mixture" and not ragged:
         assert not_kept <= X.shape[1] // 20, "separated clusters: the prefix pass bounds (nearly) every other centre away"
     # the sums that follow are the same as without pruning
@@ -100,3 +108,49 @@ def test_modes_enabled_after_a_pruned_pass(ctx):
         assert np.array_equal(L.assignments(want_dist=False)[0], L0.assignments(want_dist=False)[0])
     np.testing.assert_allclose(L.get_centers(), L0.get_centers(), rtol=1e-9, atol=1e-12)
     L.close(); L0.close(); ds.close()
+
+
+@pytest.mark.parametrize("scale", [1e-30, 1e-12, 1e-6, 1.0, 3e4, 1e12, 1e25])
+def test_half_table_prefix_is_scale_free(ctx, monkeypatch, scale):
+    """The half-precision table stores s c' with s a power of two chosen from max |c'|: data and centres far outside the
+    fp16 range prune exactly like data of order one (same columns kept), and the assignments stay the oracle's."""
+    from sparsifiedkmeans_b200 import Dataset, Lloyd
+    monkeypatch.delenv("SKM_PRUNE_F32", raising=False)
+    X, c, gamma = make_sparsified(p=512, n=8000, m=40, K=48, seed=5, kind="mixture", f32=True)
+    X = X.copy()
+    X.data = (X.data.astype(np.float32) * np.float32(scale)).astype(X.data.dtype)
+    c = c * float(np.float32(scale))
+    ds = Dataset.from_scipy(X, store="f32", ctx=ctx)
+    wa, wd, _ = host_ref.find_cluster_assignments(X, c, gamma)
+    L = Lloyd(ds, 48)
+    L.set_prune(True)
+    L.set_centers(c)
+    L.assign(gamma)
+    a, d = L.assignments()
+    assert np.array_equal(a, wa)
+    np.testing.assert_allclose(d, wd, rtol=2e-5, atol=0)
+    if 1e-13 < scale < 1e13:                 # beyond that the fp32 SQUARES leave the fp32 range: everything goes to fp64
+        assert L.last_prune()[0] <= X.shape[1] // 20, L.last_prune()
+    L.close(); ds.close()
+
+
+def test_half_table_prefix_nan_and_huge_centres(ctx, monkeypatch):
+    """A NaN centre entry and a centre 1e30 away: nothing is kept on a wrong bound, the oracle's MATLAB-min semantics hold."""
+    from sparsifiedkmeans_b200 import Dataset, Lloyd
+    monkeypatch.delenv("SKM_PRUNE_F32", raising=False)
+    X, c, gamma = make_sparsified(p=256, n=4000, m=26, K=20, seed=9, kind="mixture", f32=True)
+    for variant in ("nan", "huge"):
+        c2 = c.copy()
+        if variant == "nan":
+            c2[7, 3] = np.nan
+        else:
+            c2[:, 5] = 1e30
+        ds = Dataset.from_scipy(X, store="f32", ctx=ctx)
+        wa, wd, _ = host_ref.find_cluster_assignments(X, c2, gamma)
+        L = Lloyd(ds, 20)
+        L.set_prune(True)
+        L.set_centers(c2)
+        L.assign(gamma)
+        a, d = L.assignments()
+        assert np.array_equal(a, wa), variant
+        L.close(); ds.close()
