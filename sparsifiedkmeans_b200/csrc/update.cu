@@ -5,6 +5,7 @@
 // The partials buffer is [S (p*K) | N (p*K) | counts (K) | sumsq (1)] in doubles, column-major
 // per cluster (S[k*p + r]); it is what the multi-GPU all-reduce sums.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -480,6 +481,10 @@ static int launch_csr_bw(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const A
     const size_t budget = (size_t)ctx->smem_optin - 2048;
     const size_t per_k = (size_t)12 * BW;
     int warps = 8;
+    {
+        static const char *e = getenv("SKM_K2_WARPS");              // tuning knob
+        if (e && atoi(e) > 0 && atoi(e) <= 32) warps = atoi(e);
+    }
     while (warps > 1 && (size_t)warps * per_k * (size_t)(K < 32 ? K : 32) > budget) warps >>= 1;
     int64_t kb = (int64_t)(budget / ((size_t)warps * per_k));
     if (kb > K) kb = K;
@@ -506,9 +511,20 @@ template <typename AT>
 static int accumulate_csr_bins(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const AT *assign_c, double *S, double *N)
 {
     // shrink the bin width until roughly 32 warps fit on an SM
+    {
+        static const char *e = getenv("SKM_K2_BW");                 // tuning knob: bin columns per cluster per warp
+        const int bw = e ? atoi(e) : 0;
+        if (bw == 32) return launch_csr_bw<AT, 32>(ctx, ds, K, assign_c, S, N);
+        if (bw == 16) return launch_csr_bw<AT, 16>(ctx, ds, K, assign_c, S, N);
+        if (bw == 8) return launch_csr_bw<AT, 8>(ctx, ds, K, assign_c, S, N);
+        if (bw == 4) return launch_csr_bw<AT, 4>(ctx, ds, K, assign_c, S, N);
+    }
     if (K <= 16) return launch_csr_bw<AT, 32>(ctx, ds, K, assign_c, S, N);
-    if (K <= 32) return launch_csr_bw<AT, 16>(ctx, ds, K, assign_c, S, N);
-    if (K <= 64) return launch_csr_bw<AT, 8>(ctx, ds, K, assign_c, S, N);
+    // The kernel sits on the shared-memory pipe (ncu at K = 64, BW = 8: l1tex 93 %, mio_throttle the top stall): every
+    // turn-taking phase is four shared-memory instructions, so fewer phases beat more resident warps down to 16 warps
+    // per SM (K = 64, n = 1.25e7: BW 8 / 16 / 32 = 1.91 / 1.57 / 3.00 ms, profiles/r2_k2_k64.md)
+    if (K <= 64) return launch_csr_bw<AT, 16>(ctx, ds, K, assign_c, S, N);
+    if (K <= 128) return launch_csr_bw<AT, 8>(ctx, ds, K, assign_c, S, N);
     return launch_csr_bw<AT, 4>(ctx, ds, K, assign_c, S, N);
 }
 

@@ -12,4 +12,4 @@ for _ in range(3): L.step(gamma, gamma, True)
 ctx.timing_enable(True); ctx.timing_read()
 for _ in range(5): st = L.step(gamma, gamma, True)
 t = ctx.timing_read()
-print(json.dumps({"n": n, "kernel": L.kernel_name, "assign_ms": t["assign"][0] / 5, "recheck_ms": t["recheck"][0] / 5, "last_prune": L.last_prune()}))
+print(json.dumps({"n": n, "kernel": L.kernel_name, "assign_ms": t["assign"][0] / 5, "recheck_ms": t["recheck"][0] / 5, "accumulate_ms": t["accumulate"][0] / 5, "last_prune": L.last_prune()}))
