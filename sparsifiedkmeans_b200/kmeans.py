@@ -9,7 +9,7 @@ sequences them the way kmeans_sparsified.m:213-607 does.
 
 Scope: the sparsified path (`Sparsify=True`) with the Hadamard sketch, the DCT
 sketch (p not a power of two, :226-231) or 'none', from memory or from a file on disk (`DataFile`, a
-memory-mapped .npy here; the reference reads -v7.3 .mat through matfile).  The dense path
+MATLAB -v7.3 .mat read by matfile73.py, or a memory-mapped .npy).  The dense path
 (Sparsify=False) is outside the hot path and raises NotImplementedError.  The two-pass outputs (`nargout` 6..9:
 centers_twoPass, assignments_twoPass, distances_twoPass, SUMD_twoPass; kmeans_sparsified.m:525-571)
 come from one streamed pass over the original data (skm_second_pass).
@@ -141,25 +141,26 @@ def Arthur_initialization(ds: Dataset, K: int, gamma, rng=None, first=None, unif
 def _open_data_file(path: str):
     """DataFile mode (kmeans_sparsified.m:180-207, private/sampleAndMixFromLargeFile.m:60-107): the matrix
     stays on disk and is read in column chunks.  The reference reads a MATLAB -v7.3 .mat through `matfile`
-    (HDF5); this image has no HDF5 reader, so the container here is a NumPy .npy file (2-D, float32 or
-    float64), memory-mapped: the precondition+sample pipeline and the second pass stream it chunk by chunk
-    without loading it.  A .mat path is tried through h5py when that module exists."""
+    (HDF5): `.mat` paths go through matfile73.py, a reader of the HDF5 subset MATLAB writes for a dense matrix
+    (contiguous datasets are memory-mapped in place, chunked / deflated ones are decoded into a memory-mapped
+    temporary file).  A NumPy .npy file (2-D, float32 or float64), memory-mapped, is accepted as well.  Either way
+    the precondition+sample pipeline and the second pass stream the matrix chunk by chunk without loading it."""
     import os
-    cand = [path, path + ".npy", path + ".mat"]
+    cand = [path, path + ".mat", path + ".npy"]                                       # :187-189: '.mat' is appended
     found = next((c for c in cand if os.path.isfile(c)), None)
     if found is None:
         raise KMeansError("Cannot find specified data file to load")                  # :191
-    if found.endswith(".mat"):
+    if not found.endswith(".npy"):
+        from . import matfile73
         try:
-            import h5py                                                               # noqa: F401
-        except ImportError as e:
-            raise NotImplementedError("MATLAB -v7.3 files need h5py (HDF5), which this image lacks; save the matrix "
-                                      "with numpy.save and pass the .npy path") from e
-        f = h5py.File(found, "r")
-        names = [k for k in f.keys() if not k.startswith("#")]
-        if len(names) != 1:
-            raise KMeansError("Expected a single variable")                           # sampleAndMixFromLargeFile.m:62
-        return np.asarray(f[names[0]]).T                                              # HDF5 stores MATLAB arrays transposed
+            A, _ = matfile73.open_matrix(found)
+        except matfile73.MatFileError as e:
+            raise KMeansError(str(e)) from e
+        if A.ndim != 2 or A.shape[0] < 1 or A.shape[1] < 1:
+            raise KMeansError("Error reading file; returned bad size for matrix")     # :204
+        if A.dtype not in (np.float32, np.float64):
+            A = np.asarray(A, dtype=np.float64)                                       # integer classes: as MATLAB's double()
+        return A
     A = np.load(found, mmap_mode="r")
     if A.ndim != 2 or A.shape[0] < 1 or A.shape[1] < 1:
         raise KMeansError("Error reading file; returned bad size for matrix")         # :204

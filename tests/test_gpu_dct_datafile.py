@@ -118,3 +118,25 @@ def test_kmeans_from_data_file(ctx, tmp_path):
     np.save(str(tmp_path / "f32.npy"), X.astype(np.float32))
     f32 = kmeans_sparsified(str(tmp_path / "f32.npy"), 3, **kw)
     assert _accuracy(f32[0], lab, 3) > 0.98
+
+
+@pytest.mark.parametrize("layout", ["contiguous", "chunked_deflate"])
+def test_kmeans_from_v73_mat_file(ctx, tmp_path, layout):
+    """DataFile pointing at a MATLAB -v7.3 .mat (the reference's container, private/sampleAndMixFromLargeFile.m:60-66):
+    same answer as the in-core call, in both orientations (ColumnSamples)."""
+    from sparsifiedkmeans_b200 import kmeans_sparsified, matfile73
+    X, lab = _mixture(64, 4000, 3, seed=8)
+    kwf = dict(chunks=(512, 48), compress=2) if layout == "chunked_deflate" else {}
+    matfile73.write_matrix(str(tmp_path / "rows.mat"), X, name="X", **kwf)                 # n x p, rows are samples
+    matfile73.write_matrix(str(tmp_path / "cols.mat"), np.ascontiguousarray(X.T), name="data", **kwf)
+    kw = dict(Sparsify=True, SparsityLevel=0.25, Seed=3, Replicates=2, nargout=9, Context=ctx)
+    mem = kmeans_sparsified(X, 3, **kw)
+    a = kmeans_sparsified(str(tmp_path / "rows.mat"), 3, **kw)
+    b = kmeans_sparsified(None, 3, DataFile=str(tmp_path / "cols"), ColumnSamples=True, **kw)   # '.mat' appended (:187-189)
+    assert a[4]["LoadFromDisk"] and b[4]["LoadFromDisk"]
+    for got in (a, b):
+        assert np.array_equal(got[0], mem[0])
+        assert np.array_equal(got[6], mem[6])
+    np.testing.assert_allclose(a[1], mem[1], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(b[1], mem[1].T, rtol=1e-9, atol=1e-12)
+    assert _accuracy(a[0], lab, 3) > 0.98

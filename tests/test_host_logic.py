@@ -103,12 +103,15 @@ def test_data_file_container_checks(tmp_path):
         km._open_data_file(str(tmp_path / "ints.npy"))
     with pytest.raises(km.KMeansError, match="Cannot find"):
         km._open_data_file(str(tmp_path / "missing"))
-    (tmp_path / "data.mat").write_bytes(b"MATLAB 7.3 MAT-file")
-    try:
-        import h5py  # noqa: F401
-    except ImportError:
-        with pytest.raises(NotImplementedError, match="h5py"):
-            km._open_data_file(str(tmp_path / "data.mat"))
+    (tmp_path / "data.mat").write_bytes(b"MATLAB 5.0 MAT-file, Platform: GLNXA64" + b" " * 200)
+    with pytest.raises(km.KMeansError, match="not -v7.3"):
+        km._open_data_file(str(tmp_path / "data.mat"))
+    from sparsifiedkmeans_b200 import matfile73
+    X = np.random.default_rng(0).standard_normal((6, 40))
+    matfile73.write_matrix(str(tmp_path / "v73.mat"), X, chunks=(16, 6), compress=3)
+    A = km._open_data_file(str(tmp_path / "v73"))                             # '.mat' appended (:187-189)
+    assert A.shape == (6, 40) and np.array_equal(np.asarray(A), X)
+    assert A.T.flags["C_CONTIGUOUS"], "columns are contiguous: the chunked upload streams them without a copy"
 
 
 def test_driver_accepts_the_iteration_mode_options():
