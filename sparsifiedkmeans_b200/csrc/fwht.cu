@@ -314,18 +314,20 @@ __global__ void __launch_bounds__(32 * W) k_fwht_cta_x(int64_t n, float *__restr
 // is only busy during the one exchange between the lane stages and the warp stages; as soon as every thread has
 // read its operands back, one thread issues cp.async.bulk for the next column into the same buffer (mbarrier
 // complete_tx), which then overlaps the last butterflies and the stores of the current column.
-template <int W>
+template <int W, int NBUF>
 __global__ void __launch_bounds__(32 * W) k_fwht_cta_tma(int64_t n, float *__restrict__ x, const float *__restrict__ signs, float divide_by)
 {
+    // NBUF = 2 (columns of <= 32 KB): the column after the next one is prefetched into the buffer the current column has
+    // just left, so a load is in flight during the whole of a column's processing, not only during its second half
     extern __shared__ __align__(128) unsigned char fc_raw[];
-    float *s = reinterpret_cast<float *>(fc_raw);
-    __shared__ uint64_t bar;
+    float *sbase = reinterpret_cast<float *>(fc_raw);
+    __shared__ uint64_t bar[NBUF];
     constexpr int T = 32 * W, P2 = 1024 * W, G = 32 / W;
     constexpr uint32_t BYTES = P2 * 4;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
-    const uint32_t s_a = (uint32_t)__cvta_generic_to_shared(s);
-    auto prefetch = [&](int64_t col) {                        // one thread
+    auto prefetch = [&](int64_t col, int b) {                 // one thread
+        const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar[b]);
+        const uint32_t s_a = (uint32_t)__cvta_generic_to_shared(sbase + (size_t)b * P2);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic reads of the buffer come first
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(BYTES) : "memory");
         const char *src = reinterpret_cast<const char *>(x + col * P2);
@@ -336,22 +338,27 @@ __global__ void __launch_bounds__(32 * W) k_fwht_cta_tma(int64_t n, float *__res
         }
     };
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        for (int b = 0; b < NBUF; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&bar[b])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (threadIdx.x == 0 && (int64_t)blockIdx.x < n) prefetch(blockIdx.x);
-    uint32_t parity = 0;
-    for (int64_t col = blockIdx.x; col < n; col += gridDim.x) {
+    if (threadIdx.x == 0)
+        for (int b = 0; b < NBUF; ++b)
+            if ((int64_t)blockIdx.x + (int64_t)b * gridDim.x < n) prefetch(blockIdx.x + (int64_t)b * gridDim.x, b);
+    int64_t it = 0;
+    for (int64_t col = blockIdx.x; col < n; col += gridDim.x, ++it) {
         float *g = x + col * P2;
+        const int b = (int)(it % NBUF);
+        float *s = sbase + (size_t)b * P2;
         {
+            const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar[b]);
+            const uint32_t parity = (uint32_t)((it / NBUF) & 1);
             uint32_t done = 0, spins = 0;
             while (!done) {
                 asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
                              : "=r"(done) : "r"(bar_a), "r"(parity) : "memory");
                 if (!done && ++spins > (1u << 26)) __trap();
             }
-            parity ^= 1;
         }
         float v[32];
 #pragma unroll
@@ -372,12 +379,12 @@ __global__ void __launch_bounds__(32 * W) k_fwht_cta_tma(int64_t n, float *__res
             for (int jw = 0; jw < W; ++jw) v[i * W + jw] = s[(jw << 10) | (i * T + threadIdx.x)];
         }
         __syncthreads();                                       // the buffer is free again
-        if (threadIdx.x == 0 && col + gridDim.x < n) prefetch(col + gridDim.x);
+        if (threadIdx.x == 0 && col + (int64_t)NBUF * gridDim.x < n) prefetch(col + (int64_t)NBUF * gridDim.x, b);
 #pragma unroll
         for (int h = 1; h < W; h <<= 1) {
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
-                if (!((q % W) & h)) { const float a = v[q], b = v[q + h]; v[q] = a + b; v[q + h] = a - b; }
+                if (!((q % W) & h)) { const float a = v[q], b2 = v[q + h]; v[q] = a + b2; v[q + h] = a - b2; }
             }
         }
 #pragma unroll
@@ -409,8 +416,15 @@ int launch_fwht_cta(skm_ctx *ctx, int64_t n, float *x, const float *signs, float
     static const bool no_tma = getenv("SKM_FWHT_NO_TMA") != nullptr;
     static const char *xe = getenv("SKM_FWHT_X");           // 1: shuffle-free variant for every size, 0: never
     const bool use_x = xe ? atoi(xe) != 0 : false;          // measured 3-14 % SLOWER than the shuffle kernels at every size: opt-in only
-    const size_t smem = use_x ? (size_t)1056 * W * sizeof(float) : (size_t)1024 * W * sizeof(float);
-    auto kern = use_x ? k_fwht_cta_x<W> : ((W >= 8 && !no_tma) ? k_fwht_cta_tma<W> : k_fwht_cta<W>);
+    size_t smem = use_x ? (size_t)1056 * W * sizeof(float) : (size_t)1024 * W * sizeof(float);
+    // TMA prefetch of the next column for every CTA size (p2 = 2048 / 4096: 0.71 / 0.67 -> 0.77 / 0.77 of the HBM peak).  A second
+    // column buffer (SKM_FWHT_TMA_NBUF=2, W <= 8) halves the resident CTAs and measured SLOWER: 0.70 / 0.73 / 0.71 at 2048 /
+    // 4096 / 8192 against 0.77 / 0.77 / 0.74 (profiles/r2_fwht.md), so it stays an experiment.
+    static const char *nb = getenv("SKM_FWHT_TMA_NBUF");
+    const bool tma = !use_x && !no_tma;
+    const bool two = tma && W <= 8 && nb && atoi(nb) == 2;
+    if (tma) smem = (size_t)(two ? 2 : 1) * 1024 * W * sizeof(float);
+    auto kern = use_x ? k_fwht_cta_x<W> : (tma ? (two ? k_fwht_cta_tma<W, 2> : k_fwht_cta_tma<W, 1>) : k_fwht_cta<W>);
     SKM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     SKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * W, smem));
