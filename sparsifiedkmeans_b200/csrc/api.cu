@@ -988,6 +988,32 @@ extern "C" int skm_lloyd_last_assign(skm_lloyd *L, int64_t *n_flagged)
     return SKM_OK;
 }
 
+// Every centre for the columns a bounded / pruned pass could not keep (L->flagged, nfl of them, counted on the host).
+// Short lists go straight to the fp64 kernel (reference order; ~3.4 us per 1000 columns at K = 64, DRAM-light).  Long lists
+// first take the fp32 K1 kernels restricted to the list (k_assign_list: same tables, guard and outputs as the full pass),
+// and only what those cannot certify goes to fp64.  The list kernel reads 16 bytes per lane 512 bytes apart, which DRAM
+// serves as 64-byte bursts: ncu shows it at the DRAM peak moving 2 KB per column and launch (5x the useful bytes), 1.4 us
+// per 1000 columns for lists above n/10 and 3.7 us at n/70 where neighbouring lanes no longer share bursts -- so it takes
+// over from fp64 at n/32 (profiles/r2_prune.md).  Both refresh lb for the columns they touch.
+static int reevaluate_flagged(skm_lloyd *L, const ExactArgs &ea, const FastPlan &pl, bool list_ok, int64_t nfl)
+{
+    skm_dataset *ds = L->ds;
+    skm_ctx *ctx = ds->ctx;
+    const char *le = getenv("SKM_LIST_MIN");                          // knob (read every call: tests switch it): shortest list for the fp32 kernels
+    const int64_t list_min = le ? atoll(le) : std::max<int64_t>(16384, ds->n / 32);
+    if (!list_ok || nfl < list_min) {
+        SKM_TRY(skm_launch_exact_assign(ctx, ea, L->assign, nullptr, L->dist_f32, L->flagged, L->nflag, ds->n, L->lb));
+        return SKM_OK;
+    }
+    if (!L->flagged2) SKM_TRY(skm_big_alloc(L->ctx, (void **)&L->flagged2, sizeof(int32_t) * ds->n, "flagged2"));
+    SKM_TRY(skm_launch_build_table(ctx, ds->p, L->K, L->cscaled_t, pl, L->table, L->cmax));
+    SKM_TRY(skm_launch_assign_fast(ctx, ds, L->K, pl, L->table, L->cmax, L->assign, L->dist_f32, L->best2, L->flagged2, L->nflag + 1,
+                                   nullptr, L->lb, 0, L->flagged, nfl));
+    SKM_TRY(skm_launch_exact_assign(ctx, ea, L->assign, nullptr, L->dist_f32, L->flagged2, L->nflag + 1, ds->n, L->lb));
+    SKM_CUDA(cudaMemcpyAsync(L->nflag, L->nflag + 1, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));   // statistics: fp64 columns
+    return SKM_OK;
+}
+
 extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
 {
     SKM_REQUIRE(L, "NULL argument");
@@ -1012,8 +1038,11 @@ extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
     ExactArgs ea = exact_args(ds, L->K, L->cscaled_t);
     L->last_rechecked = -1;
     L->last_bounded_flagged = -1;
+    L->last_prune[0] = L->last_prune[1] = -1;
+    L->last_pruned = false;
     const bool want_bounds = fast && L->assign_mode == 1;
     float *lb = want_bounds ? L->lb : nullptr;
+    const bool list_ok = fast && !use_tc && !pl.mode64 && !pl.global_table;     // k_assign_list reads the plan's own image / table
     if (want_bounds) {
         // bounded pass: valid when the bounds exist and refer to the same scaling of the centres
         const double gnow = has_gamma ? gamma : nan("");
@@ -1054,9 +1083,9 @@ extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
             L->last_bounded_flagged = nfl;
             if (nfl <= ds->n / 8) {
                 L->bounded_backoff = 0;
-                // few columns left their bound: every centre, fp64, the reference's order; refreshes their lb
+                // few columns left their bound: every centre for those (fp32 list pass + fp64, or fp64 alone); refreshes their lb
                 SkmTimed t(ctx, SKM_T_RECHECK);
-                SKM_TRY(skm_launch_exact_assign(ctx, ea, L->assign, nullptr, L->dist_f32, L->flagged, L->nflag, ds->n, L->lb));
+                SKM_TRY(reevaluate_flagged(L, ea, pl, list_ok, nfl));
                 L->dist_is_f64 = false;
                 L->assigned = true;
                 L->accumulated = false;
@@ -1067,7 +1096,6 @@ extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
             L->bounded_skip = L->bounded_backoff;
         }
     }
-    L->last_prune[0] = L->last_prune[1] = -1;
     bool pruned = false;
     {
         const int64_t w2max = ds->uniform_width ? ds->sell_width2 : ds->sell_wmax / 2;
@@ -1111,10 +1139,11 @@ extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
                 nfl = ctx->h_flag[10];
             }
             L->last_prune[0] = nfl; L->last_prune[1] = pairs;
-            // the fp64 re-evaluation costs ~3.4 us per 1000 columns at K = 64: up to n/16 columns the pruned pass still wins
-            if (nfl <= n / 16) {
+            // re-evaluating a column against every centre costs ~3.4 us per 1000 columns in fp64 and ~1.4 us with the fp32 list
+            // pass in front: up to n/16 resp. n/6 columns the pruned pass still beats the full one
+            if (nfl <= (list_ok ? n / 6 : n / 16)) {
                 SkmTimed t(ctx, SKM_T_RECHECK);
-                SKM_TRY(skm_launch_exact_assign(ctx, ea, L->assign, nullptr, L->dist_f32, L->flagged, L->nflag, n, L->lb));
+                SKM_TRY(reevaluate_flagged(L, ea, pl, list_ok, nfl));
                 L->prune_backoff = 0;
                 pruned = true;
             } else {
@@ -1125,6 +1154,7 @@ extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
         }
     }
     if (pruned) {
+        L->last_pruned = true;
         L->dist_is_f64 = false;
         if (want_bounds) L->lb_valid = true;
     } else if (use_tc) {
@@ -1335,7 +1365,7 @@ extern "C" const char *skm_lloyd_kernel_name(skm_lloyd *L)
     const skm_dataset *ds = L->ds;
     if (ds->store_dtype == SKM_F32 && L->table && skm_fast_plan(ds->ctx, ds->p, L->K, &pl, ds->max_col_nnz)) {
         if (tc_wanted(L) && ds->tsb) snprintf(name, sizeof name, "k_tcs_filter<%d> + k_assign_bounded", skm_tcs_bn(L->K));
-        else if (L->last_prune[0] >= 0 && L->last_prune[0] <= ds->n / 16) {
+        else if (L->last_prune[0] >= 0 && L->last_pruned) {
             Prefix16Plan hp;
             if (prune_half_table(ds->ctx, ds->p, L->K, &hp))
                 snprintf(name, sizeof name, "k_prefix16<%d> x%d on %lld of the entry pairs + k_assign_bounded", hp.kc, hp.nchunks,

@@ -214,6 +214,7 @@ struct skm_lloyd {
     void    *prune_table16;  // half-precision centre table of the one-launch prefix (prefix16.cu)
     float   *prune_scale;    // [4] its scale, 1/scale and rounding bound
     int64_t  last_prune[2];               // columns the pruned pass could not keep (-1: not tried), entry pairs it read
+    bool     last_pruned;                 // the last assignment pass was the pruned plan (it kept enough columns)
     // tensor-core filter plan (tcsparse.cu): -1 = automatic, 0 = off, 1 = on
     int      tc_filter;
     void    *tc_bimg;        // swizzled fp16 centre image
@@ -300,7 +301,7 @@ int  skm_launch_build_table(skm_ctx *ctx, int64_t p, int64_t K, const double *ct
 int  skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const FastPlan &pl,
                             const float *table, const float *cmax, int32_t *assign, float *dist,
                             float *best2, int32_t *flagged, int *nflag, const int *m_dev = nullptr,
-                            float *lb = nullptr, int max_pairs = 0);
+                            float *lb = nullptr, int max_pairs = 0, const int32_t *col_list = nullptr, int64_t nlist = 0);
 
 // prefix16.cu: the prefix launch of the pruned pass on a half-precision table (all K <= 64 centres in one launch)
 struct Prefix16Plan {
