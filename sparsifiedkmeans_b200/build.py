@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIBDIR, "libskm_b200.so")
-SOURCES = ["api.cu", "convert.cu", "exact.cu", "assign_fast.cu", "update.cu", "fwht.cu", "kpp.cu", "csr.cu", "stream.cu", "dense.cu", "dct.cu", "bounded.cu", "multi.cu", "tcgemm.cu", "tcsparse.cu", "prefix16.cu"]
+SOURCES = ["api.cu", "convert.cu", "exact.cu", "assign_fast.cu", "update.cu", "fwht.cu", "kpp.cu", "csr.cu", "stream.cu", "dense.cu", "dct.cu", "bounded.cu", "multi.cu", "tcgemm.cu", "tcsparse.cu", "prefix16.cu", "assign_cols.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -62,6 +62,8 @@ extern "C" int skm_ctx_create(int device, void *cuda_stream, skm_ctx **out)
     }
     ctx->d_flag = nullptr;
     ctx->h_flag = nullptr;
+    ctx->red_scratch = nullptr;
+    ctx->red_ticket = nullptr;
     ctx->timing = false;
     ctx->stream_cache = nullptr;
     ctx->stream_cache_free = nullptr;
@@ -84,6 +86,9 @@ extern "C" int skm_ctx_create(int device, void *cuda_stream, skm_ctx **out)
     ctx->ev = nullptr;
     memset(ctx->ev_count, 0, sizeof ctx->ev_count);
     if (cudaMalloc((void **)&ctx->d_flag, 16 * sizeof(int)) != cudaSuccess ||
+        cudaMalloc((void **)&ctx->red_scratch, SKM_RED_BLOCKS * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void **)&ctx->red_ticket, sizeof(unsigned int)) != cudaSuccess ||
+        cudaMemset(ctx->red_ticket, 0, sizeof(unsigned int)) != cudaSuccess ||
         cudaMallocHost((void **)&ctx->h_flag, 16 * sizeof(int)) != cudaSuccess) {
         skm_set_error("context scratch allocation failed");
         skm_ctx_destroy(ctx);
@@ -100,6 +105,8 @@ extern "C" void skm_ctx_destroy(skm_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->stream_cache && ctx->stream_cache_free) ctx->stream_cache_free(ctx->stream_cache);
     if (ctx->d_flag) cudaFree(ctx->d_flag);
+    if (ctx->red_scratch) cudaFree(ctx->red_scratch);
+    if (ctx->red_ticket) cudaFree(ctx->red_ticket);
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
     for (int i = 0; i < 2; ++i) { if (ctx->bounce[i]) cudaFreeHost(ctx->bounce[i]); if (ctx->bounce_ev[i]) cudaEventDestroy(ctx->bounce_ev[i]); }
     if (ctx->ev) {
@@ -711,7 +718,7 @@ extern "C" void skm_lloyd_destroy(skm_lloyd *L)
     cudaFree(L->stats);
     cudaFree(L->acc_local); skm_big_free(L->ctx, L->assign_prev); skm_big_free(L->ctx, L->changed); cudaFree(L->nchanged);
     skm_big_free(L->ctx, L->lb); cudaFree(L->centers_prev); cudaFree(L->table_t); cudaFree(L->shift); cudaFree(L->nchanged_pred);
-    cudaFree(L->prune_table16); cudaFree(L->prune_scale);
+    cudaFree(L->prune_table16); cudaFree(L->prune_scale); cudaFree(L->table_rm);
     cudaFree(L->tc_bimg); cudaFree(L->tc_scale); skm_big_free(L->ctx, L->tc_cand); skm_big_free(L->ctx, L->tc_lb4); cudaFree(L->tc_zshift); skm_big_free(L->ctx, L->flagged2);
     if (L->h_stats) cudaFreeHost(L->h_stats);
     if (L->h_counts) cudaFreeHost(L->h_counts);
@@ -751,6 +758,7 @@ static int skm_lloyd_create_ex(skm_dataset *ds, int64_t K, int want_f64_dist, sk
         if ((rc = dev_alloc((void **)&L->partials, sizeof(double) * (2 * p * K + K + 1), "partials"))) break;
         if ((rc = dev_alloc((void **)&L->stats, sizeof(double) * 8, "stats"))) break;
         if ((rc = dev_alloc((void **)&L->nflag, sizeof(int) * 4, "nflag"))) break;
+        if (cudaMemsetAsync(L->nflag, 0, sizeof(int) * 4, ds->ctx->stream) != cudaSuccess) { rc = SKM_ERR_CUDA; break; }   // read_stats copies all four
         if ((rc = dev_alloc((void **)&L->cmax, sizeof(float) * 4, "cmax"))) break;
         if (ds->store_dtype == SKM_F32) {
             if ((rc = skm_big_alloc(L->ctx, (void **)&L->dist_f32, sizeof(float) * n, "dist"))) break;
@@ -989,28 +997,30 @@ extern "C" int skm_lloyd_last_assign(skm_lloyd *L, int64_t *n_flagged)
 }
 
 // Every centre for the columns a bounded / pruned pass could not keep (L->flagged, nfl of them, counted on the host).
-// Short lists go straight to the fp64 kernel (reference order; ~3.4 us per 1000 columns at K = 64, DRAM-light).  Long lists
-// first take the fp32 K1 kernels restricted to the list (k_assign_list: same tables, guard and outputs as the full pass),
-// and only what those cannot certify goes to fp64.  The list kernel reads 16 bytes per lane 512 bytes apart, which DRAM
-// serves as 64-byte bursts: ncu shows it at the DRAM peak moving 2 KB per column and launch (5x the useful bytes), 1.4 us
-// per 1000 columns for lists above n/10 and 3.7 us at n/70 where neighbouring lanes no longer share bursts -- so it takes
-// over from fp64 at n/32 (profiles/r2_prune.md).  Both refresh lb for the columns they touch.
-static int reevaluate_flagged(skm_lloyd *L, const ExactArgs &ea, const FastPlan &pl, bool list_ok, int64_t nfl)
+// Lists of 2048 columns and more first take the K1 arithmetic in fp32 restricted to the list (assign_cols.cu: a warp per
+// column on the column-major image, certified with the K1 guard; ~1.5 us per 1000 columns at K = 64 whatever the list
+// length), and only what that cannot certify goes to the fp64 kernel (reference order, ~3.4 us per 1000 columns); shorter
+// lists go to fp64 directly.  Both refresh lb for the columns they touch.  (A lane-per-column walk of the SELL image was
+// tried first and dropped: its 16-byte loads 512 bytes apart cost 64-byte DRAM bursts, profiles/r2_prune.md.)
+static int reevaluate_flagged(skm_lloyd *L, const ExactArgs &ea, int64_t nfl)
 {
     skm_dataset *ds = L->ds;
     skm_ctx *ctx = ds->ctx;
-    const char *le = getenv("SKM_LIST_MIN");                          // knob (read every call: tests switch it): shortest list for the fp32 kernels
-    const int64_t list_min = le ? atoll(le) : std::max<int64_t>(16384, ds->n / 32);
-    if (!list_ok || nfl < list_min) {
-        SKM_TRY(skm_launch_exact_assign(ctx, ea, L->assign, nullptr, L->dist_f32, L->flagged, L->nflag, ds->n, L->lb));
+    const char *le = getenv("SKM_LIST_MIN");                          // knob (read every call: tests switch it): shortest list for the fp32 kernel
+    const char *how = getenv("SKM_REEVAL");                           // knob: "fp64" switches the fp32 list kernel off
+    const bool cols_ok = !(how && !strcmp(how, "fp64")) && skm_assign_cols_supported(ds, L->K);
+    if (cols_ok && nfl >= (le ? atoll(le) : 2048)) {
+        if (!L->flagged2) SKM_TRY(skm_big_alloc(L->ctx, (void **)&L->flagged2, sizeof(int32_t) * ds->n, "flagged2"));
+        if (!L->table_rm)
+            SKM_TRY(dev_alloc((void **)&L->table_rm, sizeof(float) * (size_t)(ds->p + 1) * skm_assign_cols_kpad(L->K), "row-major table"));
+        SKM_TRY(skm_launch_build_table_rm(ctx, ds->p, L->K, L->cscaled_t, L->table_rm, L->cmax));
+        SKM_TRY(skm_launch_assign_cols(ctx, ds, L->K, L->table_rm, L->cmax, L->flagged, nfl, L->assign, L->dist_f32, L->lb,
+                                       L->flagged2, L->nflag + 1));
+        SKM_TRY(skm_launch_exact_assign(ctx, ea, L->assign, nullptr, L->dist_f32, L->flagged2, L->nflag + 1, ds->n, L->lb));
+        SKM_CUDA(cudaMemcpyAsync(L->nflag, L->nflag + 1, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));   // statistics: fp64 columns
         return SKM_OK;
     }
-    if (!L->flagged2) SKM_TRY(skm_big_alloc(L->ctx, (void **)&L->flagged2, sizeof(int32_t) * ds->n, "flagged2"));
-    SKM_TRY(skm_launch_build_table(ctx, ds->p, L->K, L->cscaled_t, pl, L->table, L->cmax));
-    SKM_TRY(skm_launch_assign_fast(ctx, ds, L->K, pl, L->table, L->cmax, L->assign, L->dist_f32, L->best2, L->flagged2, L->nflag + 1,
-                                   nullptr, L->lb, 0, L->flagged, nfl));
-    SKM_TRY(skm_launch_exact_assign(ctx, ea, L->assign, nullptr, L->dist_f32, L->flagged2, L->nflag + 1, ds->n, L->lb));
-    SKM_CUDA(cudaMemcpyAsync(L->nflag, L->nflag + 1, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));   // statistics: fp64 columns
+    SKM_TRY(skm_launch_exact_assign(ctx, ea, L->assign, nullptr, L->dist_f32, L->flagged, L->nflag, ds->n, L->lb));
     return SKM_OK;
 }
 
@@ -1042,7 +1052,6 @@ extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
     L->last_pruned = false;
     const bool want_bounds = fast && L->assign_mode == 1;
     float *lb = want_bounds ? L->lb : nullptr;
-    const bool list_ok = fast && !use_tc && !pl.mode64 && !pl.global_table;     // k_assign_list reads the plan's own image / table
     if (want_bounds) {
         // bounded pass: valid when the bounds exist and refer to the same scaling of the centres
         const double gnow = has_gamma ? gamma : nan("");
@@ -1085,7 +1094,7 @@ extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
                 L->bounded_backoff = 0;
                 // few columns left their bound: every centre for those (fp32 list pass + fp64, or fp64 alone); refreshes their lb
                 SkmTimed t(ctx, SKM_T_RECHECK);
-                SKM_TRY(reevaluate_flagged(L, ea, pl, list_ok, nfl));
+                SKM_TRY(reevaluate_flagged(L, ea, nfl));
                 L->dist_is_f64 = false;
                 L->assigned = true;
                 L->accumulated = false;
@@ -1139,11 +1148,11 @@ extern "C" int skm_lloyd_assign(skm_lloyd *L, int has_gamma, double gamma)
                 nfl = ctx->h_flag[10];
             }
             L->last_prune[0] = nfl; L->last_prune[1] = pairs;
-            // re-evaluating a column against every centre costs ~3.4 us per 1000 columns in fp64 and ~1.4 us with the fp32 list
-            // pass in front: up to n/16 resp. n/6 columns the pruned pass still beats the full one
-            if (nfl <= (list_ok ? n / 6 : n / 16)) {
+            // re-evaluating a column against every centre costs ~3.4 us per 1000 columns in fp64 and ~1.5 us with the fp32 list
+            // kernel in front: up to n/16 resp. n/4 columns the pruned pass still beats the full one
+            if (nfl <= (skm_assign_cols_supported(ds, K) ? n / 4 : n / 16)) {
                 SkmTimed t(ctx, SKM_T_RECHECK);
-                SKM_TRY(reevaluate_flagged(L, ea, pl, list_ok, nfl));
+                SKM_TRY(reevaluate_flagged(L, ea, nfl));
                 L->prune_backoff = 0;
                 pruned = true;
             } else {

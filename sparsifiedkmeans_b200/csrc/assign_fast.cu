@@ -43,9 +43,6 @@ struct FastParams {
     int           *nflag;
     float         *lb;           // optional: lower bound on the distance to every centre but the winner (bounded.cu)
     int            max_pairs;    // > 0: only the first max_pairs entry pairs of every column (partial-distance pass)
-    const int32_t *col_list;     // LIST kernels: the columns to evaluate (any order), one per lane
-    int64_t        nlist;
-    int            pad_row;      // LIST kernels: a zero row of the table (p) for lanes whose column is shorter than the warp's longest
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -89,7 +86,7 @@ __device__ __forceinline__ void tma_stage(void *smem_dst, const void *gsrc, uint
 // Per-column epilogue shared by the fast kernels: best / second best of this chunk, merge with
 // earlier chunks, exactness guard, results.
 template <int KC>
-__device__ __forceinline__ void finish_column(const FastParams &P, const float (&acc)[KC], int64_t j)
+__device__ __forceinline__ void finish_column(const FastParams &P, const float (&acc)[KC], int64_t slice, int lane)
 {
         // ---- per-column epilogue: best / second best of this chunk ----
     const float INF = __int_as_float(0x7f800000);
@@ -108,7 +105,8 @@ __device__ __forceinline__ void finish_column(const FastParams &P, const float (
     }
     if (bad) b2 = QNAN;
 
-    if (j < 0 || j >= P.n) return;
+    const int64_t j = slice * SKM_SLICE + lane;
+    if (j >= P.n) return;
     if (!P.first) {                                        // merge with earlier chunks
         const float2 r = P.best2[j];
         const int ri = P.assign[j];
@@ -223,63 +221,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assign_fast(const FastParams 
             step<KC>(acc, tab, ks, q.z, __int_as_float(q.w));
         }
 
-        finish_column<KC>(P, acc, slice * SKM_SLICE + lane);
-    }
-}
-
-// LIST variant: every centre against a LIST of columns (one per lane, any order) instead of all slices -- the columns a
-// pruned or bounded pass could not keep (api.cu).  A lane reads its column's entries where they lie in the SELL image
-// (16-byte loads, 512 bytes apart: one 32-byte sector each, twice the useful bytes, which a short list affords), so
-// the same tables, sums, guard and outputs as the full pass apply; lanes of one warp no longer share a slice, so the
-// conflict-free entry order of the dual tables does not carry over (a few replays instead).
-template <int KC, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) k_assign_list(const FastParams P)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t bar;
-    float *stab = reinterpret_cast<float *>(smem_raw);
-    tma_stage(stab, P.table, P.table_bytes, &bar);
-    const float *tab = stab;
-
-    const int lane = threadIdx.x & 31;
-    const int64_t warps_total = ((int64_t)gridDim.x * THREADS) >> 5;
-    const int64_t ngroups = (P.nlist + 31) >> 5;
-    const int ks = P.ks;
-    const int4 padq = make_int4(P.pad_row, 0, P.pad_row, 0);
-
-    for (int64_t grp = ((int64_t)blockIdx.x * THREADS + threadIdx.x) >> 5; grp < ngroups; grp += warps_total) {
-        const int64_t pos = grp * 32 + lane;
-        int64_t j = pos < P.nlist ? (int64_t)P.col_list[pos] : -1;
-        if (j >= P.n) j = -1;
-        int64_t base = 0;
-        int w2 = 0;
-        if (j >= 0) {
-            const int64_t sl = j >> 5;
-            if (P.uniform) { base = sl * (int64_t)P.width2 * 32; w2 = P.width2; }
-            else { base = P.slice_ptr[sl]; w2 = (int)((P.slice_ptr[sl + 1] - base) >> 5); }
-            base += (j & 31);
-        }
-        const int wmax = __reduce_max_sync(0xffffffffu, w2);
-        const int4 *src = P.sell + base;
-
-        float acc[KC];
-#pragma unroll
-        for (int k = 0; k < KC; ++k) acc[k] = 0.f;
-        int t2 = 0;
-        for (; t2 + 2 <= wmax; t2 += 2) {
-            const int4 q0 = (t2 + 0 < w2) ? __ldg(src + (t2 + 0) * 32) : padq;
-            const int4 q1 = (t2 + 1 < w2) ? __ldg(src + (t2 + 1) * 32) : padq;
-            step<KC>(acc, tab, ks, q0.x, __int_as_float(q0.y));
-            step<KC>(acc, tab, ks, q0.z, __int_as_float(q0.w));
-            step<KC>(acc, tab, ks, q1.x, __int_as_float(q1.y));
-            step<KC>(acc, tab, ks, q1.z, __int_as_float(q1.w));
-        }
-        for (; t2 < wmax; ++t2) {
-            const int4 q = (t2 < w2) ? __ldg(src + t2 * 32) : padq;
-            step<KC>(acc, tab, ks, q.x, __int_as_float(q.y));
-            step<KC>(acc, tab, ks, q.z, __int_as_float(q.w));
-        }
-        finish_column<KC>(P, acc, j);
+        finish_column<KC>(P, acc, slice, lane);
     }
 }
 
@@ -350,7 +292,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assign_fast64(const FastParam
             step64<KC>(acc, tab, q.x, __int_as_float(q.y));
             step64<KC>(acc, tab, q.z, __int_as_float(q.w));
         }
-        finish_column<KC>(P, acc, slice * SKM_SLICE + lane);
+        finish_column<KC>(P, acc, slice, lane);
     }
 }
 
@@ -394,26 +336,6 @@ int launch_fast(skm_ctx *ctx, const FastParams &P, size_t smem)
     }
     int64_t blocks = (int64_t)ctx->sm_count * per_sm;
     int64_t need = (P.nslices * 32 + THREADS - 1) / THREADS;
-    if (blocks > need) blocks = need;
-    if (blocks < 1) blocks = 1;
-    kern<<<(unsigned)blocks, THREADS, smem, ctx->stream>>>(P);
-    SKM_CHECK_LAUNCH(ctx);
-    return SKM_OK;
-}
-
-template <int KC, int THREADS, int MINB>
-int launch_list(skm_ctx *ctx, const FastParams &P, size_t smem)
-{
-    auto kern = k_assign_list<KC, THREADS, MINB>;
-    SKM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    SKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
-    if (per_sm < 1) {
-        skm_set_error("assign_list<%d>: kernel does not fit on an SM (smem %zu)", KC, smem);
-        return SKM_ERR_UNSUPPORTED;
-    }
-    int64_t blocks = (int64_t)ctx->sm_count * per_sm;
-    const int64_t need = (((P.nlist + 31) / 32) * 32 + THREADS - 1) / THREADS;
     if (blocks > need) blocks = need;
     if (blocks < 1) blocks = 1;
     kern<<<(unsigned)blocks, THREADS, smem, ctx->stream>>>(P);
@@ -582,15 +504,10 @@ int skm_launch_build_table(skm_ctx *ctx, int64_t p, int64_t K, const double *ct,
 
 int skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const FastPlan &pl,
                            const float *table, const float *cmax, int32_t *assign, float *dist,
-                           float *best2, int32_t *flagged, int *nflag, const int *m_dev, float *lb, int max_pairs,
-                           const int32_t *col_list, int64_t nlist)
+                           float *best2, int32_t *flagged, int *nflag, const int *m_dev, float *lb, int max_pairs)
 {
     SKM_CUDA(cudaMemsetAsync(nflag, 0, sizeof(int), ctx->stream));
-    if (ds->n == 0 || (col_list && nlist <= 0)) return SKM_OK;
-    if (col_list && (pl.mode64 || pl.global_table)) {
-        skm_set_error("assign_fast: the column-list pass needs a 16-byte shared-memory table plan");
-        return SKM_ERR_UNSUPPORTED;
-    }
+    if (ds->n == 0) return SKM_OK;
     const double u = 5.9604644775390625e-08;   // 2^-24
     const double m = (double)(ds->max_col_nnz > 0 ? ds->max_col_nnz : 1);
     FastParams P;
@@ -615,7 +532,6 @@ int skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const
     P.nflag = nflag;
     P.lb = lb;
     P.max_pairs = max_pairs;
-    P.col_list = col_list; P.nlist = nlist; P.pad_row = (int)ds->p;
     for (int c = 0; c < pl.nchunks; ++c) {
         P.table = table + (size_t)c * pl.rows * pl.ks;
         P.k0 = c * pl.kc;
@@ -650,21 +566,6 @@ int skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const
         }
         // CTA shape by table size: one wide CTA per SM when the table leaves room for nothing else
         const bool one = pl.smem > 110 * 1024, two = !one && pl.smem > 54 * 1024;
-        if (col_list) {
-            switch (pl.kc) {
-                case 4:  rc = one ? launch_list<4, 1024, 1>(ctx, P, pl.smem) : two ? launch_list<4, 512, 2>(ctx, P, pl.smem) : launch_list<4, 256, 4>(ctx, P, pl.smem); break;
-                case 8:  rc = one ? launch_list<8, 1024, 1>(ctx, P, pl.smem) : two ? launch_list<8, 512, 2>(ctx, P, pl.smem) : launch_list<8, 256, 4>(ctx, P, pl.smem); break;
-                case 12: rc = one ? launch_list<12, 1024, 1>(ctx, P, pl.smem) : two ? launch_list<12, 512, 2>(ctx, P, pl.smem) : launch_list<12, 256, 4>(ctx, P, pl.smem); break;
-                case 16: rc = one ? launch_list<16, 1024, 1>(ctx, P, pl.smem) : two ? launch_list<16, 512, 2>(ctx, P, pl.smem) : launch_list<16, 256, 4>(ctx, P, pl.smem); break;
-                case 24: rc = one ? launch_list<24, 512, 1>(ctx, P, pl.smem) : launch_list<24, 256, 3>(ctx, P, pl.smem); break;
-                case 32: rc = one ? launch_list<32, 512, 1>(ctx, P, pl.smem) : launch_list<32, 256, 2>(ctx, P, pl.smem); break;
-                case 48: rc = one ? launch_list<48, 512, 1>(ctx, P, pl.smem) : launch_list<48, 256, 2>(ctx, P, pl.smem); break;
-                case 64: rc = one ? launch_list<64, 512, 1>(ctx, P, pl.smem) : launch_list<64, 256, 2>(ctx, P, pl.smem); break;
-                default: skm_set_error("assign_list: unsupported chunk %d", pl.kc); return SKM_ERR_UNSUPPORTED;
-            }
-            if (rc != SKM_OK) return rc;
-            continue;
-        }
         switch (pl.kc) {
             case 4:  rc = one ? launch_fast<4, 1024, 1>(ctx, P, pl.smem) : two ? launch_fast<4, 512, 2>(ctx, P, pl.smem) : launch_fast<4, 256, 4>(ctx, P, pl.smem); break;
             case 8:  rc = one ? launch_fast<8, 1024, 1>(ctx, P, pl.smem) : two ? launch_fast<8, 512, 2>(ctx, P, pl.smem) : launch_fast<8, 256, 4>(ctx, P, pl.smem); break;

@@ -56,6 +56,7 @@ enum { SKM_T_ASSIGN = 0, SKM_T_RECHECK = 1, SKM_T_ACCUM = 2, SKM_T_FINAL = 3, SK
        SKM_T_FWHT = 5, SKM_T_KPP = 6, SKM_T_UPLOAD = 7, SKM_T_SLOTS = 8 };
 #define SKM_T_RING 512
 
+#define SKM_RED_BLOCKS 4096
 struct skm_ctx {
     int          device;
     cudaStream_t stream;
@@ -65,6 +66,8 @@ struct skm_ctx {
     int          smem_optin;       // max dynamic shared memory per block (bytes)
     int         *d_flag;           // device int[4] scratch (validation / counters)
     int         *h_flag;           // pinned host mirror
+    double      *red_scratch;      // [SKM_RED_BLOCKS] per-block partials of the order-independent reductions (update.cu)
+    unsigned int *red_ticket;      // their ticket counter (zero between launches)
     bool         timing;
     cudaEvent_t (*ev)[SKM_T_RING][2];   // [SKM_T_SLOTS][SKM_T_RING][2], created lazily
     int          ev_count[SKM_T_SLOTS];
@@ -211,6 +214,7 @@ struct skm_lloyd {
     // partial-distance pruning of the full pass (multi-launch plans, K > 16): -1 = automatic, 0 = off, 1 = always try
     int      prune_mode;
     int      prune_skip, prune_backoff;   // full passes to run unpruned after a pruned pass that kept too few columns
+    float   *table_rm;       // [p + 1][kpad] fp32 centres, row-major (assign_cols.cu)
     void    *prune_table16;  // half-precision centre table of the one-launch prefix (prefix16.cu)
     float   *prune_scale;    // [4] its scale, 1/scale and rounding bound
     int64_t  last_prune[2];               // columns the pruned pass could not keep (-1: not tried), entry pairs it read
@@ -301,7 +305,7 @@ int  skm_launch_build_table(skm_ctx *ctx, int64_t p, int64_t K, const double *ct
 int  skm_launch_assign_fast(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const FastPlan &pl,
                             const float *table, const float *cmax, int32_t *assign, float *dist,
                             float *best2, int32_t *flagged, int *nflag, const int *m_dev = nullptr,
-                            float *lb = nullptr, int max_pairs = 0, const int32_t *col_list = nullptr, int64_t nlist = 0);
+                            float *lb = nullptr, int max_pairs = 0);
 
 // prefix16.cu: the prefix launch of the pruned pass on a half-precision table (all K <= 64 centres in one launch)
 struct Prefix16Plan {
@@ -316,6 +320,14 @@ int    skm_launch_build_table16(skm_ctx *ctx, int64_t p, int64_t K, const double
                                 void *table, float *scale);
 int    skm_launch_prefix16(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const Prefix16Plan &pl, const void *table,
                            const float *scale, int32_t *assign, float *best2, float *lb, int max_pairs);
+
+// assign_cols.cu: every centre for a list of columns, fp32 with the K1 guard (warp per column, column-major image)
+int  skm_assign_cols_kpad(int64_t K);
+bool skm_assign_cols_supported(const skm_dataset *ds, int64_t K);
+int  skm_launch_build_table_rm(skm_ctx *ctx, int64_t p, int64_t K, const double *ct, float *table, float *cmax);
+int  skm_launch_assign_cols(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const float *table_rm, const float *cmax,
+                            const int32_t *list, int64_t nlist, int32_t *assign, float *dist, float *lb,
+                            int32_t *flagged_out, int *nflag_out);
 
 // bounded.cu
 int skm_launch_center_shift(skm_ctx *ctx, int64_t p, int64_t K, const double *centers, double *centers_prev,

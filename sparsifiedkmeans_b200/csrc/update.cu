@@ -9,12 +9,16 @@
 
 namespace {
 
+__device__ __forceinline__ void ordered_block_sum(double s_block, double *__restrict__ scratch, unsigned int *__restrict__ ticket,
+                                                  double *__restrict__ out);
+
 // v1: one warp per column, lanes over the column's stored entries, fp64 atomics to L2.
 template <typename VT>
 __global__ void k_accumulate_csc(int64_t p, int64_t n, int64_t K, const int64_t *__restrict__ colptr,
                                  const int32_t *__restrict__ rowidx, const VT *__restrict__ val,
                                  const int32_t *__restrict__ assign, const float *__restrict__ dist32,
-                                 const double *__restrict__ dist64, double *__restrict__ partials)
+                                 const double *__restrict__ dist64, double *__restrict__ partials,
+                                 double *__restrict__ red_scratch, unsigned int *__restrict__ red_ticket)
 {
     double *S = partials, *N = partials + p * K, *counts = partials + 2 * p * K;
     double *sumsq = counts + K;
@@ -41,20 +45,51 @@ __global__ void k_accumulate_csc(int64_t p, int64_t n, int64_t K, const int64_t 
     __shared__ double red[32];
     if (lane == 0) red[threadIdx.x >> 5] = local_sq;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.0;
+    double s = 0.0;
+    if (threadIdx.x == 0)
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
-        if (s != 0.0 || s != s) atomicAdd(sumsq, s);
-    }
+    ordered_block_sum(s, red_scratch, red_ticket, sumsq);
 }
 
+
+// Sum of one double per block, independent of the order the blocks finish in: every block deposits its partial and takes
+// a ticket; the block that draws the last ticket adds the partials up in a fixed pattern (thread t takes t, t + T, ...;
+// then a fixed tree).  The objective (sum of squared distances) decides between replicates that reach the same clustering,
+// so it must not depend on scheduling (an fp64 atomicAdd per block made two identical runs differ in the last bits).
+__device__ __forceinline__ void ordered_block_sum(double s_block /* valid in thread 0 */, double *__restrict__ scratch,
+                                                  unsigned int *__restrict__ ticket, double *__restrict__ out)
+{
+    __shared__ bool last;
+    __shared__ double tree[32];
+    if (threadIdx.x == 0) {
+        scratch[blockIdx.x] = s_block;
+        __threadfence();
+        last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    double t = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) t += __ldcg(scratch + b);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) tree[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += tree[w];
+        *out += tot;
+        *ticket = 0;                                          // ready for the next launch on this stream
+    }
+}
 
 // members per cluster, sum of squared distances, and the compact copy of the assignments that
 // K2's row-major pass gathers from (1 byte per column when K <= 256).
 template <typename AT>
 __global__ void k_count_sumsq(int64_t n, int64_t K, const int32_t *__restrict__ assign,
                               const float *__restrict__ dist32, const double *__restrict__ dist64,
-                              AT *__restrict__ assign_c, double *__restrict__ counts, double *__restrict__ sumsq)
+                              AT *__restrict__ assign_c, double *__restrict__ counts, double *__restrict__ sumsq,
+                              double *__restrict__ red_scratch, unsigned int *__restrict__ red_ticket)
 {
     extern __shared__ int hist[];
     for (int k = threadIdx.x; k < K; k += blockDim.x) hist[k] = 0;
@@ -77,12 +112,11 @@ __global__ void k_count_sumsq(int64_t n, int64_t K, const int32_t *__restrict__ 
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
     __syncthreads();
     for (int k = threadIdx.x; k < K; k += blockDim.x)
-        if (hist[k]) atomicAdd(&counts[k], (double)hist[k]);
-    if (threadIdx.x == 0) {
-        double s = 0.0;
+        if (hist[k]) atomicAdd(&counts[k], (double)hist[k]);      // integers: exact in any order
+    double s = 0.0;
+    if (threadIdx.x == 0)
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
-        if (s != 0.0 || s != s) atomicAdd(sumsq, s);
-    }
+    ordered_block_sum(s, red_scratch, red_ticket, sumsq);
 }
 
 // K2 over the row-major image: one warp per work unit (a run of one row's entries).  Lanes own
@@ -216,7 +250,8 @@ __global__ void k_accumulate_csr(int64_t p, int k0, int kb, int64_t nunits,
 // (that one changes for every column, so it is recomputed in full here).
 __global__ void k_diff_assign(int64_t n, int64_t K, const int32_t *__restrict__ assign, const int32_t *__restrict__ prev,
                               const float *__restrict__ dist32, const double *__restrict__ dist64,
-                              int32_t *__restrict__ changed, int *__restrict__ nchanged, double *__restrict__ sumsq)
+                              int32_t *__restrict__ changed, int *__restrict__ nchanged, double *__restrict__ sumsq,
+                              double *__restrict__ red_scratch, unsigned int *__restrict__ red_ticket)
 {
     double local = 0.0;
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -234,11 +269,10 @@ __global__ void k_diff_assign(int64_t n, int64_t K, const int32_t *__restrict__ 
     for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.0;
+    double s = 0.0;
+    if (threadIdx.x == 0)
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
-        if (s != 0.0 || s != s) atomicAdd(sumsq, s);
-    }
+    ordered_block_sum(s, red_scratch, red_ticket, sumsq);
 }
 
 // one warp per changed column: its entries leave the old cluster's sums and join the new one's
@@ -467,7 +501,8 @@ static int accumulate_csr(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const 
         if (blocks > cap) blocks = cap;
         const size_t sm = sizeof(int) * (size_t)K;
         if (sm > 48 * 1024) SKM_CUDA(cudaFuncSetAttribute(k_count_sumsq<AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        k_count_sumsq<AT><<<(unsigned)blocks, 256, sm, ctx->stream>>>(n, K, assign, dist32, dist64, (AT *)assign_c, counts, sumsq);
+        k_count_sumsq<AT><<<(unsigned)blocks, 256, sm, ctx->stream>>>(n, K, assign, dist32, dist64, (AT *)assign_c, counts, sumsq,
+                                                                     ctx->red_scratch, ctx->red_ticket);
         SKM_CHECK_LAUNCH(ctx);
     }
     return accumulate_csr_bins<AT>(ctx, ds, K, (const AT *)assign_c, S, N);
@@ -545,10 +580,10 @@ int skm_launch_accumulate(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const 
     if (blocks > cap) blocks = cap;
     if (ds->store_dtype == SKM_F32)
         k_accumulate_csc<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>(
-            p, n, K, ds->colptr, ds->rowidx, (const float *)ds->val, assign, dist32, dist64, partials);
+            p, n, K, ds->colptr, ds->rowidx, (const float *)ds->val, assign, dist32, dist64, partials, ctx->red_scratch, ctx->red_ticket);
     else
         k_accumulate_csc<double><<<(unsigned)blocks, 256, 0, ctx->stream>>>(
-            p, n, K, ds->colptr, ds->rowidx, (const double *)ds->val, assign, dist32, dist64, partials);
+            p, n, K, ds->colptr, ds->rowidx, (const double *)ds->val, assign, dist32, dist64, partials, ctx->red_scratch, ctx->red_ticket);
     SKM_CHECK_LAUNCH(ctx);
     return SKM_OK;
 }
@@ -631,7 +666,8 @@ int skm_launch_diff_assign(skm_ctx *ctx, int64_t n, int64_t K, const int32_t *as
     int64_t blocks = (n + 255) / 256;
     const int64_t cap = (int64_t)ctx->sm_count * 16;
     if (blocks > cap) blocks = cap;
-    k_diff_assign<<<(unsigned)blocks, 256, 0, ctx->stream>>>(n, K, assign, prev, dist32, dist64, changed, nchanged, sumsq);
+    k_diff_assign<<<(unsigned)blocks, 256, 0, ctx->stream>>>(n, K, assign, prev, dist32, dist64, changed, nchanged, sumsq,
+                                                             ctx->red_scratch, ctx->red_ticket);
     SKM_CHECK_LAUNCH(ctx);
     return SKM_OK;
 }

@@ -363,3 +363,27 @@ def test_kpp_filtered_rounds_match_reference(ctx, kind):
         ds.close()
     finally:
         del os.environ["SKM_NO_KPP_FILTER"]
+
+
+def test_objective_is_bit_reproducible(ctx):
+    """The sum of squared distances is reduced in a fixed order (ordered_block_sum in update.cu), not with one fp64 atomic
+    per block: replicates that reach the same clustering are told apart by it (kmeans_sparsified.m:489-497), so two
+    identical passes must give the same bits, in the recompute and in the incremental update."""
+    from sparsifiedkmeans_b200 import Dataset, Lloyd
+    X, c, gamma = make_sparsified(p=128, n=150000, m=12, K=7, seed=77, kind="unstructured")
+    ds = Dataset.from_scipy(X, store="f32", ctx=ctx)
+    for incremental in (False, True):
+        seen = set()
+        # every row of this matrix is one work unit of K2 (< 16 K entries), so the recomputed centres are reproducible too;
+        # the incremental +/- updates are fp64 atomics in arbitrary order, so only its first two objectives are
+        for rep in range(6):
+            L = Lloyd(ds, 7, incremental=incremental)
+            L.set_centers(c)
+            vals = []
+            for _ in range(2 if incremental else 3):
+                st = L.step(gamma, gamma, True)
+                vals.append(st.sumsq)
+            seen.add(tuple(np.float64(v).tobytes() for v in vals))
+            L.close()
+        assert len(seen) == 1, f"incremental={incremental}: {len(seen)} different objective bit patterns over 6 identical runs"
+    ds.close()
