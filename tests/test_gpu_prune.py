@@ -13,9 +13,10 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("prefix", ["half", "f32"])
 @pytest.mark.parametrize("kind", ["mixture", "unstructured"])
 @pytest.mark.parametrize("K,p,m,ragged", [(64, 1024, 51, False), (33, 256, 26, True), (100, 512, 40, False), (17, 784, 78, True),
-                                          (130, 300, 40, True)])
+                                          (130, 300, 40, True), (40, 2048, 40, False), (40, 4096, 40, False)])
 def test_pruned_pass_matches_reference(ctx, monkeypatch, prefix, kind, K, p, m, ragged):
-    """Both prefix kernels: the one-launch half-precision table (prefix16.cu, default) and the fp32 K1 kernels."""
+    """Both prefix kernels: the one-launch half-precision table (prefix16.cu, default) and the fp32 K1 kernels.  p = 2048:
+    the 64-centre half table does not fit, two launches of 32 centres; p = 4096: no half table fits, fp32 prefix."""
     from sparsifiedkmeans_b200 import Dataset, Lloyd
     if prefix == "f32":
         monkeypatch.setenv("SKM_PRUNE_F32", "1")
@@ -34,7 +35,9 @@ def test_pruned_pass_matches_reference(ctx, monkeypatch, prefix, kind, K, p, m, 
     not_kept, pairs = L.last_prune()
     assert pairs >= 2 and 0 <= not_kept <= X.shape[1]
     limit = X.shape[1] // (4 if K <= 128 else 16)          # with / without the fp32 list kernel behind the pruned pass (K <= 128)
-    assert ("k_prefix16" in L.kernel_name) == (prefix == "half" and not_kept <= limit), L.kernel_name
+    assert ("k_prefix16" in L.kernel_name) == (prefix == "half" and p < 4096 and not_kept <= limit), L.kernel_name
+    if p == 2048 and prefix == "half" and not_kept <= limit:
+        assert "k_prefix16<32> x2" in L.kernel_name, L.kernel_name
     if kind == "mixture" and not ragged:
         assert not_kept <= X.shape[1] // 20, "separated clusters: the prefix pass bounds (nearly) every other centre away"
     # the sums that follow are the same as without pruning
