@@ -833,7 +833,11 @@ extern "C" int skm_lloyd_set_assign_mode(skm_lloyd *L, int mode)
         // each buffer on its own: the pruned / tensor-core passes may already have allocated some of them
         const int64_t p = L->ds->p, n = L->ds->n, K = L->K;
         if (!L->lb) SKM_TRY(skm_big_alloc(L->ctx, (void **)&L->lb, sizeof(float) * n, "lb"));
-        if (!L->centers_prev) SKM_TRY(dev_alloc((void **)&L->centers_prev, sizeof(double) * p * K, "centers_prev"));
+        if (!L->centers_prev) {
+            SKM_TRY(dev_alloc((void **)&L->centers_prev, sizeof(double) * p * K, "centers_prev"));
+            // the first movement is measured against zeros and never used (no bounds exist yet), but it is read (initcheck)
+            SKM_CUDA(cudaMemsetAsync(L->centers_prev, 0, sizeof(double) * p * K, L->ds->ctx->stream));
+        }
         if (!L->table_t) SKM_TRY(dev_alloc((void **)&L->table_t, sizeof(float) * K * (p + 1), "table_t"));
         if (!L->shift) SKM_TRY(dev_alloc((void **)&L->shift, sizeof(float) * (K + 4), "shift"));
         if (!L->nchanged_pred) SKM_TRY(dev_alloc(&L->nchanged_pred, 16, "predict counter"));
