@@ -5,6 +5,7 @@
 // The partials buffer is [S (p*K) | N (p*K) | counts (K) | sumsq (1)] in doubles, column-major
 // per cluster (S[k*p + r]); it is what the multi-GPU all-reduce sums.
 #include "common.cuh"
+#include <algorithm>
 #include <stdlib.h>
 
 namespace {
@@ -497,7 +498,7 @@ static int accumulate_csr(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const 
     double *S = partials, *N = partials + p * K, *counts = partials + 2 * p * K, *sumsq = counts + K;
     {
         int64_t blocks = (n + 255) / 256;
-        const int64_t cap = (int64_t)ctx->sm_count * 8;
+        const int64_t cap = std::min<int64_t>((int64_t)ctx->sm_count * 8, SKM_RED_BLOCKS);   // ordered_block_sum: one scratch slot per block
         if (blocks > cap) blocks = cap;
         const size_t sm = sizeof(int) * (size_t)K;
         if (sm > 48 * 1024) SKM_CUDA(cudaFuncSetAttribute(k_count_sumsq<AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -576,7 +577,7 @@ int skm_launch_accumulate(skm_ctx *ctx, const skm_dataset *ds, int64_t K, const 
         return accumulate_csr<int32_t>(ctx, ds, K, assign, assign_c, dist32, dist64, partials);
     }
     int64_t blocks = (n * 32 + 255) / 256;
-    int64_t cap = (int64_t)ctx->sm_count * 8;
+    int64_t cap = std::min<int64_t>((int64_t)ctx->sm_count * 8, SKM_RED_BLOCKS);
     if (blocks > cap) blocks = cap;
     if (ds->store_dtype == SKM_F32)
         k_accumulate_csc<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>(
@@ -664,7 +665,7 @@ int skm_launch_diff_assign(skm_ctx *ctx, int64_t n, int64_t K, const int32_t *as
     SKM_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(double), ctx->stream));
     if (n == 0) return SKM_OK;
     int64_t blocks = (n + 255) / 256;
-    const int64_t cap = (int64_t)ctx->sm_count * 16;
+    const int64_t cap = std::min<int64_t>((int64_t)ctx->sm_count * 16, SKM_RED_BLOCKS);
     if (blocks > cap) blocks = cap;
     k_diff_assign<<<(unsigned)blocks, 256, 0, ctx->stream>>>(n, K, assign, prev, dist32, dist64, changed, nchanged, sumsq,
                                                              ctx->red_scratch, ctx->red_ticket);
