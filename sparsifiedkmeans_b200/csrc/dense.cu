@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace {
@@ -216,6 +217,7 @@ __global__ void k_dense_exact(int64_t p, int64_t K, const XT *__restrict__ xraw,
 }
 
 // per-cluster sums of dense columns.  grid.x = row tiles of 128, grid.y = column ranges.
+template <int UC>                                             // columns in flight per thread
 __global__ void __launch_bounds__(128) k_dense_sums(int64_t p, int64_t n, int kb, int k0,
                                                     const float *__restrict__ x, const int32_t *__restrict__ assign1,
                                                     double *__restrict__ S /* [K][p] */)
@@ -229,7 +231,6 @@ __global__ void __launch_bounds__(128) k_dense_sums(int64_t p, int64_t n, int kb
     const int64_t ja = (int64_t)blockIdx.y * per, jb = min(n, ja + per);
     const bool live = r < p;
     int64_t j = ja;
-    constexpr int UC = 8;                                  // columns in flight per thread
     for (; j + UC <= jb; j += UC) {
         int a[UC];
         float v[UC];
@@ -318,13 +319,17 @@ static int dense_chunk(skm_ctx *ctx, int64_t p, int64_t nc, int64_t K, const Den
         int kb = (int)std::min<int64_t>(K, (int64_t)(budget / (128 * sizeof(double))));
         if (kb > 96) kb = 96;                                      // keep a few CTAs resident
         const size_t smem = (size_t)kb * 128 * sizeof(double);
-        SKM_CUDA(cudaFuncSetAttribute(k_dense_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // few CTAs fit beside many clusters' bins (K = 64: 64 KB each, 12 warps per SM): more columns in flight per thread then
+        static const char *uce = getenv("SKM_DENSE_SUMS_UC");           // tuning knob
+        const int uc = uce ? atoi(uce) : (kb > 24 ? 32 : 16);    // K = 10: 2.10 / 2.01 / 2.48 ms, K = 64: 5.67 / 4.55 / 3.89 ms at UC = 8 / 16 / 32 (n = 2e6)
+        auto kern = uc >= 32 ? k_dense_sums<32> : (uc >= 16 ? k_dense_sums<16> : k_dense_sums<8>);
+        SKM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned tiles = (unsigned)((p + 127) / 128);
         int64_t ranges = std::max<int64_t>(1, ((int64_t)ctx->sm_count * 16) / tiles);
         ranges = std::min<int64_t>(ranges, std::max<int64_t>(1, nc / 64));
         for (int64_t k0 = 0; k0 < K; k0 += kb) {
             const int kbb = (int)std::min<int64_t>(kb, K - k0);
-            k_dense_sums<<<dim3(tiles, (unsigned)ranges), 128, smem, ctx->stream>>>(p, nc, kbb, (int)k0, x32, assign_in, S);
+            kern<<<dim3(tiles, (unsigned)ranges), 128, smem, ctx->stream>>>(p, nc, kbb, (int)k0, x32, assign_in, S);
             SKM_CHECK_LAUNCH(ctx);
         }
     }
