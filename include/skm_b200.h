@@ -222,8 +222,9 @@ int   skm_lloyd_accumulate(skm_lloyd *L);
  * assigned one is carried from call to call and lowered by the movement of the centres (the masked distance
  * is a seminorm of the centre, so it changes by at most ||c_new - c_old||); a column whose distance to its
  * own centre stays below that bound, with the fast kernel's rounding guard and a 1e-6 relative margin, keeps
- * its assignment after ONE centre evaluation; the others are re-evaluated against every centre (fp64,
- * reference order).  Assignments and distances are the same as in mode 0.  The bounds are dropped whenever
+ * its assignment after ONE centre evaluation; the others are re-evaluated against every centre (lists of 2048
+ * columns and more by an fp32 list kernel with the fast kernel's guard first; what that cannot certify, and short
+ * lists, in fp64 in the reference's order).  Assignments and distances are the same as in mode 0.  The bounds are dropped whenever
  * the mode is set. */
 int   skm_lloyd_set_assign_mode(skm_lloyd *L, int mode);
 /* Columns the last bounded skm_lloyd_assign had to re-evaluate (-1: that call evaluated every column). */
@@ -232,9 +233,11 @@ int   skm_lloyd_last_assign(skm_lloyd *L, int64_t *n_flagged);
  * automatic, 0: off, 1: always try.  A pass over the first ~15 % of every column's stored entries for all K centres
  * gives a candidate winner and -- every term of the masked distance being non-negative -- a lower bound on the distance
  * to every other centre; the candidate is then evaluated exactly on all entries and kept iff it stays below that bound
- * (rounding guards on both sides).  Columns that cannot be kept are evaluated against every centre (fp64, reference
- * order, when they are fewer than n/16; otherwise the ordinary full pass runs and the pruned pass sits out 1, 2, 4, ... 32
- * calls).  Assignments and distances are the same as without it. */
+ * (rounding guards on both sides).  The prefix runs on a half-precision centre table (all K <= 64 centres in one launch)
+ * whose rounding is part of the bound.  Columns that cannot be kept are evaluated against every centre (fp32 list kernel
+ * with the usual guard, then fp64 in the reference's order for what it cannot certify) when they are fewer than n/4
+ * (n/16 for K > 128); otherwise the ordinary full pass runs and the pruned pass sits out 1, 2, 4, ... 32 calls.
+ * Assignments and distances are the same as without it. */
 int   skm_lloyd_set_prune(skm_lloyd *L, int mode);
 /* Columns the last pruned pass could not keep (-1: the last pass was not pruned) and the entry pairs it read per column. */
 int   skm_lloyd_last_prune(skm_lloyd *L, int64_t *not_kept, int64_t *pairs);
