@@ -441,20 +441,28 @@ def _datatype_msg(dt: np.dtype) -> bytes:
     raise MatFileError(f"cannot write dtype {dt}")
 
 
-def _string_attr(name: str, value: str) -> bytes:
+def _string_attr(name: str, value: str, version: int = 1) -> bytes:
     nb = name.encode() + b"\0"
     vb = value.encode()
     dtype = struct.pack("<BBBBI", 0x13, 0, 0, 0, len(vb))                  # class 3, null-terminated ASCII
-    space = struct.pack("<BBB5x", 1, 0, 0)                                 # scalar
-    body = struct.pack("<BxHHH", 1, len(nb), len(dtype), len(space)) + _pad8(nb) + _pad8(dtype) + _pad8(space) + vb
+    if version == 1:
+        space = struct.pack("<BBB5x", 1, 0, 0)                             # scalar, dataspace version 1
+        body = struct.pack("<BxHHH", 1, len(nb), len(dtype), len(space)) + _pad8(nb) + _pad8(dtype) + _pad8(space) + vb
+    else:                                                                  # versions 2 / 3: no padding (3 adds the name's character set)
+        space = struct.pack("<BBBB", 2, 0, 0, 0)                           # scalar, dataspace version 2
+        body = struct.pack("<BBHHH", version, 0, len(nb), len(dtype), len(space)) + (b"\0" if version == 3 else b"")
+        body += nb + dtype + space + vb
     return _msg(0x0C, body)
 
 
 def write_matrix(path: str, X, name: str = "X", chunks=None, compress: int | None = None, shuffle: bool = False,
-                 matlab_class: str | None = None) -> None:
+                 matlab_class: str | None = None, message_versions: str = "old") -> None:
     """Write the (p, n) matrix X as the variable `name` of a -v7.3 MAT-file the way MATLAB lays it out (HDF5 dataset of
     shape (n, p) behind a 512-byte header).  chunks=(rows, cols) of the stored (n, p) array switches to chunked storage;
-    compress = zlib level adds the deflate filter (MATLAB's default for large arrays), shuffle the byte-shuffle filter."""
+    compress = zlib level adds the deflate filter (MATLAB's default for large arrays), shuffle the byte-shuffle filter.
+    message_versions: "old" = what HDF5 1.6/1.8 in its default (earliest) format and MATLAB write (dataspace 1, layout 3,
+    filter pipeline 1, attribute 1); "new" = the later versions of the same messages (dataspace 2, filter pipeline 2,
+    attribute 3) inside the same version-1 object headers; "v1layout" = the HDF5 1.4 layout message (version 1)."""
     X = np.asarray(X)
     if X.ndim != 2:
         raise MatFileError("write_matrix needs a 2-D array")
@@ -525,18 +533,32 @@ def write_matrix(path: str, X, name: str = "X", chunks=None, compress: int | Non
             level += 1
         layout = struct.pack("<BBBQ", 3, 2, 3, btree) + struct.pack("<III", c0, c1, es)
     # ---- dataset object header ----
-    msgs = _msg(0x01, struct.pack("<BBB5xQQ", 1, 2, 0, n, p))
+    newer = message_versions == "new"
+    if newer:
+        msgs = _msg(0x01, struct.pack("<BBBBQQ", 2, 2, 0, 1, n, p))           # dataspace version 2, simple
+    else:
+        msgs = _msg(0x01, struct.pack("<BBB5xQQ", 1, 2, 0, n, p))
     msgs += _msg(0x03, _datatype_msg(A.dtype), flags=1)
     msgs += _msg(0x05, struct.pack("<BBBB", 2, 2, 0, 0))                    # fill value: version 2, undefined
-    if filters:
+    if filters and newer:
+        fb = struct.pack("<BB", 2, len(filters))                           # version 2: no name for predefined filters, no padding
+        for fid, cv in filters:
+            fb += struct.pack("<HHH", fid, 1, len(cv)) + b"".join(struct.pack("<I", v) for v in cv)
+        msgs += _msg(0x0B, fb)
+    elif filters:
         fb = struct.pack("<BB6x", 1, len(filters))
         for fid, cv in filters:
             fb += struct.pack("<HHHH", fid, 0, 1, len(cv)) + b"".join(struct.pack("<I", v) for v in cv)
             if len(cv) % 2:
                 fb += b"\0" * 4
         msgs += _msg(0x0B, fb)
+    if message_versions == "v1layout":
+        if chunks is None:
+            layout = struct.pack("<BBB5xQ", 1, 2, 1, data_addr) + struct.pack("<II", n, p)
+        else:
+            layout = struct.pack("<BBB5xQ", 1, 3, 2, btree) + struct.pack("<III", c0, c1, es)
     msgs += _msg(0x08, layout)
-    msgs += _string_attr("MATLAB_class", matlab_class)
+    msgs += _string_attr("MATLAB_class", matlab_class, version=3 if newer else 1)
     nmsg = 5 + (1 if filters else 0)
     ds_hdr = alloc(struct.pack("<BBHII4x", 1, 0, nmsg, 1, len(msgs)) + msgs)
     # ---- root group: local heap, symbol node, B-tree, object header ----

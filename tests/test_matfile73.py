@@ -95,3 +95,20 @@ def test_integer_classes_and_big_files_are_mapped_not_read(tmp_path):
     r = m.H5Reader(str(tmp_path / "i16.mat"))
     assert r.object(r.variables()[0][1]).attrs["MATLAB_class"] == "int16"
     r.close()
+
+
+@pytest.mark.parametrize("message_versions", ["new", "v1layout"])
+@pytest.mark.parametrize("kw", [dict(), dict(chunks=(7, 5)), dict(chunks=(16, 33), compress=4, shuffle=True)])
+def test_other_message_versions(tmp_path, message_versions, kw):
+    """The later versions of the header messages (dataspace 2, filter pipeline 2, attribute 3) and the HDF5 1.4 layout
+    message (version 1): files from other HDF5 writers that keep version-1 object headers and B-trees."""
+    X = np.random.default_rng(5).standard_normal((33, 50))
+    path = str(tmp_path / "a.mat")
+    m.write_matrix(path, X, message_versions=message_versions, **kw)
+    Y, name = m.open_matrix(path)
+    assert name == "X" and np.array_equal(np.asarray(Y), X)
+    r = m.H5Reader(path)
+    obj = r.object(r.variables()[0][1])
+    assert obj.attrs["MATLAB_class"] == "double" and obj.shape == (50, 33)
+    assert [f[0] for f in obj.filters] == ([2, 1] if kw.get("shuffle") else [])
+    r.close()
