@@ -456,7 +456,7 @@ def _string_attr(name: str, value: str, version: int = 1) -> bytes:
 
 
 def write_matrix(path: str, X, name: str = "X", chunks=None, compress: int | None = None, shuffle: bool = False,
-                 matlab_class: str | None = None, message_versions: str = "old") -> None:
+                 matlab_class: str | None = None, message_versions: str = "old", continuation: bool = False) -> None:
     """Write the (p, n) matrix X as the variable `name` of a -v7.3 MAT-file the way MATLAB lays it out (HDF5 dataset of
     shape (n, p) behind a 512-byte header).  chunks=(rows, cols) of the stored (n, p) array switches to chunked storage;
     compress = zlib level adds the deflate filter (MATLAB's default for large arrays), shuffle the byte-shuffle filter.
@@ -558,8 +558,16 @@ def write_matrix(path: str, X, name: str = "X", chunks=None, compress: int | Non
         else:
             layout = struct.pack("<BBB5xQ", 1, 3, 2, btree) + struct.pack("<III", c0, c1, es)
     msgs += _msg(0x08, layout)
-    msgs += _string_attr("MATLAB_class", matlab_class, version=3 if newer else 1)
+    attr = _string_attr("MATLAB_class", matlab_class, version=3 if newer else 1)
     nmsg = 5 + (1 if filters else 0)
+    if continuation:
+        # the attribute lives in a continuation block, as in headers that grew after they were created (MATLAB adds
+        # its attributes after the dataset exists)
+        cont_addr = alloc(attr)
+        msgs += _msg(0x10, struct.pack("<QQ", cont_addr, len(attr)))
+        nmsg += 1
+    else:
+        msgs += attr
     ds_hdr = alloc(struct.pack("<BBHII4x", 1, 0, nmsg, 1, len(msgs)) + msgs)
     # ---- root group: local heap, symbol node, B-tree, object header ----
     heap_data = _pad8(b"\0" * 8 + name.encode() + b"\0")

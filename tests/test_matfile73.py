@@ -112,3 +112,17 @@ def test_other_message_versions(tmp_path, message_versions, kw):
     assert obj.attrs["MATLAB_class"] == "double" and obj.shape == (50, 33)
     assert [f[0] for f in obj.filters] == ([2, 1] if kw.get("shuffle") else [])
     r.close()
+
+
+def test_object_header_continuation(tmp_path):
+    """The MATLAB_class attribute in a continuation block of the object header (message 0x0010)."""
+    X = np.arange(12.0).reshape(3, 4)
+    path = str(tmp_path / "c.mat")
+    m.write_matrix(path, X, continuation=True, chunks=(2, 2), compress=1)
+    Y, _ = m.open_matrix(path)
+    assert np.array_equal(np.asarray(Y), X)
+    r = m.H5Reader(path)
+    msgs = r._messages(r.variables()[0][1])
+    assert [t for t, _ in msgs].count(0x10) == 1 and msgs[-1][0] == 0x0C
+    assert r.object(r.variables()[0][1]).attrs["MATLAB_class"] == "double"
+    r.close()
