@@ -190,3 +190,26 @@ def test_list_pass_reevaluates_what_was_not_kept(ctx, monkeypatch, kind, K, p, m
             L.accumulate(); L.finalize(gamma)
         L.close()
     ds.close()
+
+
+def test_pruned_pass_with_duplicate_centres(ctx, monkeypatch):
+    """Two identical centres tie exactly for half of the columns: the pruned pass can never keep those (its bound on the twin
+    equals the candidate's own distance), the list kernel cannot certify them, and the fp64 kernel applies MATLAB's
+    first-index rule -- the reference's assignments, also with the twin in a different 64-centre chunk."""
+    from sparsifiedkmeans_b200 import Dataset, Lloyd
+    monkeypatch.delenv("SKM_PRUNE_F32", raising=False)
+    for K, twin in ((40, (3, 17)), (100, (5, 90))):
+        X, c, gamma = make_sparsified(p=256, n=5000, m=26, K=K, seed=K, kind="mixture", f32=True)
+        c = c.copy()
+        c[:, twin[1]] = c[:, twin[0]]
+        ds = Dataset.from_scipy(X, store="f32", ctx=ctx)
+        wa, wd, _ = host_ref.find_cluster_assignments(X, c, gamma)
+        assert np.count_nonzero(wa == twin[0] + 1) > 0 and np.count_nonzero(wa == twin[1] + 1) == 0   # labels are 1-based; the first index wins every tie
+        L = Lloyd(ds, K)
+        L.set_prune(True)
+        L.set_centers(c)
+        L.assign(gamma)
+        a, d = L.assignments()
+        assert np.array_equal(a, wa), f"K={K}: {np.count_nonzero(a != wa)} assignments differ"
+        np.testing.assert_allclose(d, wd, rtol=2e-5, atol=1e-30)
+        L.close(); ds.close()
