@@ -404,12 +404,14 @@ def open_matrix(path: str, tmpdir: str | None = None):
     """The single variable of a -v7.3 MAT-file as a (p, n) array (private/sampleAndMixFromLargeFile.m:60-66: more than
     one variable is an error).  Returns (array, variable name)."""
     r = H5Reader(path)
-    names = r.variables()
-    if len(names) != 1:
+    try:
+        names = r.variables()
+        if len(names) != 1:
+            raise MatFileError("Expected a single variable")     # sampleAndMixFromLargeFile.m:62
+        name, addr = names[0]
+        return r.read_matrix(addr, tmpdir=tmpdir), name          # a contiguous matrix is its own mapping of the file
+    finally:
         r.close()
-        raise MatFileError("Expected a single variable")         # sampleAndMixFromLargeFile.m:62
-    name, addr = names[0]
-    return r.read_matrix(addr, tmpdir=tmpdir), name
 
 
 # ------------------------------------------------------------------------------------------------------------------
