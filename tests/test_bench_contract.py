@@ -31,3 +31,17 @@ def test_ours_arm_fails_loudly_without_a_gpu():
                          capture_output=True, text=True, timeout=600)
     assert out.returncode != 0
     assert "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_ncu_traffic_table_covers_the_bench_plans():
+    """bench.py fills roofline.traffic from profiles/ncu_traffic.json, keyed by the plan name the library reports
+    (skm_lloyd_kernel_name); the plans of the headline (config 2) and of the north-star shape (config 3) must be there."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "profiles", "ncu_traffic.json")) as f:
+        table = json.load(f)
+    for name in ("k_assign_fast64<10>", "k_prefix16<64> x1 on 4 of the entry pairs + k_assign_bounded"):
+        assert name in table and table[name]["dram_bytes_per_point"] > 0 and "source" in table[name]
+    # algorithmic bytes per point (SURVEY 8d: 8 m + 8): the pruned plan's traffic stays within 1.3x of it (VERDICT r1 item 2)
+    assert table["k_prefix16<64> x1 on 4 of the entry pairs + k_assign_bounded"]["dram_bytes_per_point"] <= 1.3 * (51 * 8 + 8)
